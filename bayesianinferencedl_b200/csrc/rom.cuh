@@ -1,0 +1,188 @@
+// K3: batched LSPG reduced-order solve (rom/averaged_affine_ROM.py:278-310, 323-333).
+//
+// Offline (host, once per basis):  Psi_t = V_t phi,  S_pq = sym(Psi_p^T Psi_q),  G_t = Psi_t^T b.
+// Online, per sample with th_0 = 1:
+//     A_r = sum_{p<=q} th_p th_q S_pq          (n_r x n_r, SPD)       \  one GEMM  C = Coef * S_aug
+//     B_r = sum_t th_t G_t   ( = pairs (0,t) )                         /  (N x P2) . (P2 x Taug)
+//     L L^T = A_r,  w_r = A_r^{-1} B_r,  qoi = (B_obs phi) w_r            one warp per sample
+//
+// Internal packed layout ("augmented lower, column-major"): column j holds rows i = j..n_r of the
+// (n_r+1) x n_r matrix [A_r; B_r^T]:  off(j) = j (n_r+1) - j (j-1)/2,  Taug = T + n_r.  The extra row makes
+// the forward substitution L y = B_r part of the factorisation (y is the last row of the factor).
+#pragma once
+
+#include "common.cuh"
+
+namespace tfin {
+
+__host__ __device__ inline int rom_col_off(int j, int nr) { return j * (nr + 1) - (j * (j - 1)) / 2; }
+__host__ __device__ inline int rom_taug(int nr) { return nr * (nr + 1) / 2 + nr; }
+
+constexpr int ROM_BM = 64;    // samples per CTA tile
+constexpr int ROM_BN = 128;   // packed entries per CTA tile
+constexpr int ROM_MAXP2 = TFIN_MAX_TERMS * (TFIN_MAX_TERMS + 1) / 2;
+
+// ------------------------------------------------------------------------------------------- R1
+// C[s][t] = sum_pq coef[s][pq] * S[pq][t],  coef[s][(p,q)] = th_p th_q.  Register tile 4 samples x 8 entries.
+// Shared memory: coef [P2][BM] + S tile [P2][BN]  (P2 = 55: 28 KB + 56 KB -> 2 CTAs / SM).
+__global__ void __launch_bounds__(256) rom_combine_kernel(const double* __restrict__ theta,  // (N, n_terms-1)
+                                                          long long s_begin, long long s_end, int n_terms,
+                                                          const double* __restrict__ S,  // [P2][Taug]
+                                                          int Taug, double* __restrict__ C /* [Nchunk][Taug] */) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int P2 = n_terms * (n_terms + 1) / 2;
+    double* s_coef = reinterpret_cast<double*>(smem);          // [P2][BM]
+    double* s_S = s_coef + (size_t)P2 * ROM_BM;                 // [P2][BN]
+    double* s_th = s_S + (size_t)P2 * ROM_BN;                   // [BM][n_terms]
+    const int tid = threadIdx.x;
+    const long long s0 = s_begin + (long long)blockIdx.x * ROM_BM;
+    const int t0 = blockIdx.y * ROM_BN;
+
+    for (int e = tid; e < ROM_BM * n_terms; e += 256) {
+        const int sl = e / n_terms, t = e - sl * n_terms;
+        const long long s = s0 + sl;
+        s_th[e] = (t == 0) ? 1.0 : (s < s_end ? theta[s * (n_terms - 1) + t - 1] : 0.0);
+    }
+    for (int e = tid; e < P2 * ROM_BN; e += 256) {
+        const int pq = e / ROM_BN, tl = e - pq * ROM_BN;
+        s_S[e] = (t0 + tl < Taug) ? S[(size_t)pq * Taug + t0 + tl] : 0.0;
+    }
+    __syncthreads();
+    {
+        int pq = 0;
+        for (int p = 0; p < n_terms; ++p)
+            for (int q = p; q < n_terms; ++q, ++pq)
+                for (int sl = tid; sl < ROM_BM; sl += 256)
+                    s_coef[pq * ROM_BM + sl] = s_th[sl * n_terms + p] * s_th[sl * n_terms + q];
+    }
+    __syncthreads();
+
+    const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads: samples 4*ty..+3, entries tx + 16 j
+    double acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    for (int pq = 0; pq < P2; ++pq) {
+        const double4 a = *reinterpret_cast<const double4*>(&s_coef[pq * ROM_BM + 4 * ty]);
+        double b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = s_S[pq * ROM_BN + tx + 16 * j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            acc[0][j] = fma(a.x, b[j], acc[0][j]);
+            acc[1][j] = fma(a.y, b[j], acc[1][j]);
+            acc[2][j] = fma(a.z, b[j], acc[2][j]);
+            acc[3][j] = fma(a.w, b[j], acc[3][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long s = s0 + 4 * ty + i;
+        if (s >= s_end) continue;
+        double* row = C + (size_t)(s - s_begin) * Taug;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int t = t0 + tx + 16 * j;
+            if (t < Taug) row[t] = acc[i][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- R2
+// One warp per sample: left-looking Cholesky of the augmented packed matrix in shared memory, back
+// substitution, observation projection.  Lane l owns rows j + l + 32 m of the current column.
+template <int MAXM /* ceil((n_r+1)/32) */>
+__global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict__ C, long long s_begin,
+                                                       long long s_end, int nr, int n_obs,
+                                                       const double* __restrict__ obs_phi,  // [n_obs][nr]
+                                                       double* __restrict__ wr_out, double* __restrict__ qoi_out,
+                                                       int* __restrict__ status_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int Taug = rom_taug(nr);
+    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = ((Taug + 2 * nr + 2) + 1) & ~1;           // A | dinv[nr] | w[nr+1]
+    double* A = reinterpret_cast<double*>(smem) + (size_t)warp * per_warp;
+    double* dinv = A + Taug;
+    double* wv = dinv + nr;
+    const int nrow = nr + 1;
+
+    for (long long s = s_begin + (long long)blockIdx.x * wpb + warp; s < s_end;
+         s += (long long)gridDim.x * wpb) {
+        const double* src = C + (size_t)(s - s_begin) * Taug;
+        for (int e = lane; e < Taug; e += 32) A[e] = ldg_stream(src + e);
+        __syncwarp();
+        int status = TFIN_STATUS_CONVERGED;
+        for (int j = 0; j < nr; ++j) {
+            const int oj = rom_col_off(j, nr);
+            double c0[MAXM], c1[MAXM];
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                const int i = j + lane + 32 * m;
+                c0[m] = i < nrow ? A[oj + lane + 32 * m] : 0.0;
+                c1[m] = 0.0;
+            }
+            int k = 0;
+            for (; k + 1 < j; k += 2) {
+                const int ok0 = rom_col_off(k, nr) + (j - k), ok1 = rom_col_off(k + 1, nr) + (j - k - 1);
+                const double l0 = A[ok0], l1 = A[ok1];
+#pragma unroll
+                for (int m = 0; m < MAXM; ++m) {
+                    const int i = j + lane + 32 * m;
+                    if (i < nrow) {
+                        c0[m] = fma(-A[ok0 + lane + 32 * m], l0, c0[m]);
+                        c1[m] = fma(-A[ok1 + lane + 32 * m], l1, c1[m]);
+                    }
+                }
+            }
+            if (k < j) {
+                const int ok0 = rom_col_off(k, nr) + (j - k);
+                const double l0 = A[ok0];
+#pragma unroll
+                for (int m = 0; m < MAXM; ++m) {
+                    const int i = j + lane + 32 * m;
+                    if (i < nrow) c0[m] = fma(-A[ok0 + lane + 32 * m], l0, c0[m]);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) c0[m] += c1[m];
+            const double d = __shfl_sync(0xffffffffu, c0[0], 0);
+            if (!(d > 0.0)) status = TFIN_STATUS_BREAKDOWN;
+            const double inv = rsqrt(d);   // correctly rounded enough: refined below
+            const double ljj = sqrt(d);
+            const double invl = inv * (2.0 - ljj * inv) ;  // one Newton step on 1/ljj
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                const int i = j + lane + 32 * m;
+                if (i < nrow) A[oj + lane + 32 * m] = (i == j) ? ljj : c0[m] * invl;
+            }
+            if (lane == 0) dinv[j] = invl;
+            __syncwarp();
+        }
+        // y = last row of the factor; back substitution L^T w = y (column j of L is contiguous)
+        for (int j = lane; j < nr; j += 32) wv[j] = A[rom_col_off(j, nr) + (nr - j)];
+        __syncwarp();
+        for (int j = nr - 1; j >= 0; --j) {
+            const double wj = wv[j] * dinv[j];
+            __syncwarp();
+            if (lane == 0) wv[j] = wj;
+            // y_i -= L[j][i] w_j for i < j   (L[j][i] sits in column i at offset j - i)
+            for (int i = lane; i < j; i += 32) wv[i] = fma(-A[rom_col_off(i, nr) + (j - i)], wj, wv[i]);
+            __syncwarp();
+        }
+        if (status_out && lane == 0) status_out[s] = status;
+        if (wr_out)
+            for (int j = lane; j < nr; j += 32) wr_out[s * nr + j] = wv[j];
+        if (qoi_out) {
+            for (int o = 0; o < n_obs; ++o) {
+                double acc = 0.0;
+                for (int j = lane; j < nr; j += 32) acc = fma(obs_phi[o * nr + j], wv[j], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) qoi_out[s * n_obs + o] = acc;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace tfin

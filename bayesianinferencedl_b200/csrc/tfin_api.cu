@@ -1,0 +1,633 @@
+// libtfin: C ABI (include/tfin.h) over the sm_100a kernels.  Host side: CSR -> ELL conversion, per-handle
+// device workspaces, launch geometry, host<->device staging.  No CPU compute path exists here.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "common.cuh"
+#include "pcg_small.cuh"
+#include "rom.cuh"
+
+using namespace tfin;
+
+struct tfin_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+
+    // ---- affine operator (K1)
+    int n = 0, ld = 0, n_terms = 0, W = 0;
+    std::vector<int32_t> h_row_ptr, h_col_idx;    // kept for tfin_set_cells
+    std::vector<double> h_const;                  // vals[0] on the CSR pattern
+    DevBuf<uint16_t> d_col;
+    DevBuf<double> d_val, d_diag, d_rhs;
+    // ---- observation / averaging
+    int n_obs = 0, n_avg = 0;
+    DevBuf<int> d_obs_ptr, d_obs_idx, d_avg_ptr, d_avg_idx;
+    DevBuf<double> d_obs_val, d_avg_val;
+    // ---- nodal operator (K2)
+    int n_cells = 0, Wn = 0;
+    DevBuf<uint16_t> d_ncol;
+    DevBuf<int> d_ncell, d_dptr, d_dcell, d_cells;
+    DevBuf<double> d_ncoef, d_ncst, d_dcoef, d_dcst;
+    // ---- ROM (K3)
+    int n_r = 0, rom_terms = 0, rom_obs = 0;
+    DevBuf<double> d_S, d_obs_phi, d_romC;
+    int64_t rom_chunk = 0;  // 0 = auto
+    // ---- batch staging / scratch
+    DevBuf<double> d_in, d_theta, d_w, d_qoi, d_relres, d_wr;
+    DevBuf<int> d_iters, d_status;
+    DevBuf<unsigned long long> d_counter;
+    // ---- tuning
+    int pcg_R = 0;  // 0 = auto
+    int last_T = 0, last_R = 0, last_occ = 0;
+    size_t last_smem = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int tfin_version(void) { return 100; }
+extern "C" const char* tfin_last_error(void) { return last_error().c_str(); }
+
+extern "C" int tfin_create(int device, tfin_handle_t* out) {
+    if (!out) return fail(TFIN_E_ARG, "tfin_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(TFIN_E_CUDA, "tfin_create: no CUDA device (%s); libtfin has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(TFIN_E_ARG, "tfin_create: device %d out of range", device);
+    TFIN_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TFIN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(TFIN_E_CUDA, "tfin_create: device %d is sm_%d%d; libtfin is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    tfin_ctx* c = new tfin_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    TFIN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (int err = c->d_counter.reserve(1)) return err;
+    *out = c;
+    return 0;
+}
+
+extern "C" int tfin_destroy(tfin_handle_t h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto* b : {&h->d_val, &h->d_diag, &h->d_rhs, &h->d_obs_val, &h->d_avg_val, &h->d_ncoef, &h->d_ncst,
+                    &h->d_dcoef, &h->d_dcst, &h->d_S, &h->d_obs_phi, &h->d_romC, &h->d_in, &h->d_theta, &h->d_w,
+                    &h->d_qoi, &h->d_relres, &h->d_wr})
+        b->release();
+    for (auto* b : {&h->d_obs_ptr, &h->d_obs_idx, &h->d_avg_ptr, &h->d_avg_idx, &h->d_ncell, &h->d_dptr,
+                    &h->d_dcell, &h->d_cells, &h->d_iters, &h->d_status})
+        b->release();
+    h->d_col.release();
+    h->d_ncol.release();
+    h->d_counter.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+#define CHECK_HANDLE(h)                                        \
+    if (!(h)) return fail(TFIN_E_ARG, "%s: NULL handle", __func__); \
+    TFIN_CUDA(cudaSetDevice((h)->device));
+
+// ------------------------------------------------------------------------------------------------ setup
+extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const int32_t* row_ptr,
+                                 const int32_t* col_idx, int32_t n_terms, const double* vals, const double* rhs,
+                                 int32_t prune_zeros) {
+    CHECK_HANDLE(h);
+    if (n <= 0 || nnz <= 0 || !row_ptr || !col_idx || !vals || !rhs)
+        return fail(TFIN_E_ARG, "tfin_set_operator: bad argument");
+    if (n_terms < 1 || n_terms > TFIN_MAX_TERMS)
+        return fail(TFIN_E_ARG, "tfin_set_operator: n_terms must be in [1, %d]", TFIN_MAX_TERMS);
+    if (n > 65535) return fail(TFIN_E_ARG, "tfin_set_operator: n = %d exceeds the on-chip PCG limit (65535)", n);
+    if (row_ptr[0] != 0 || row_ptr[n] != nnz) return fail(TFIN_E_ARG, "tfin_set_operator: malformed row_ptr");
+    const int ld = (n + 31) & ~31;
+    // pass 1: diagonal positions, off-diagonal widths
+    std::vector<int> diag_pos(n, -1);
+    std::vector<std::vector<int>> keep(n);
+    int W = 0;
+    for (int i = 0; i < n; ++i) {
+        if (row_ptr[i + 1] < row_ptr[i]) return fail(TFIN_E_ARG, "tfin_set_operator: malformed row_ptr");
+        for (int j = row_ptr[i]; j < row_ptr[i + 1]; ++j) {
+            const int c = col_idx[j];
+            if (c < 0 || c >= n) return fail(TFIN_E_ARG, "tfin_set_operator: column index out of range");
+            if (c == i) {
+                diag_pos[i] = j;
+                continue;
+            }
+            bool nz = !prune_zeros;
+            for (int t = 0; t < n_terms && !nz; ++t) nz = vals[(size_t)t * nnz + j] != 0.0;
+            if (nz) keep[i].push_back(j);
+        }
+        if (diag_pos[i] < 0) return fail(TFIN_E_ARG, "tfin_set_operator: row %d has no diagonal entry", i);
+        W = std::max(W, (int)keep[i].size());
+    }
+    if (W == 0) W = 1;
+    std::vector<uint16_t> col((size_t)W * ld);
+    std::vector<double> val((size_t)n_terms * W * ld, 0.0), diag((size_t)n_terms * ld, 0.0), b(ld, 0.0);
+    for (int w = 0; w < W; ++w)
+        for (int i = 0; i < ld; ++i) col[(size_t)w * ld + i] = (uint16_t)std::min(i, n - 1);
+    for (int i = 0; i < n; ++i) {
+        b[i] = rhs[i];
+        for (int t = 0; t < n_terms; ++t) diag[(size_t)t * ld + i] = vals[(size_t)t * nnz + diag_pos[i]];
+        for (int w = 0; w < (int)keep[i].size(); ++w) {
+            const int j = keep[i][w];
+            col[(size_t)w * ld + i] = (uint16_t)col_idx[j];
+            for (int t = 0; t < n_terms; ++t) val[((size_t)t * W + w) * ld + i] = vals[(size_t)t * nnz + j];
+        }
+        for (int w = (int)keep[i].size(); w < W; ++w) col[(size_t)w * ld + i] = (uint16_t)i;
+    }
+    h->n = n;
+    h->ld = ld;
+    h->n_terms = n_terms;
+    h->W = W;
+    h->h_row_ptr.assign(row_ptr, row_ptr + n + 1);
+    h->h_col_idx.assign(col_idx, col_idx + nnz);
+    h->h_const.assign(vals, vals + nnz);
+    if (int e = h->d_col.upload(col, h->stream)) return e;
+    if (int e = h->d_val.upload(val, h->stream)) return e;
+    if (int e = h->d_diag.upload(diag, h->stream)) return e;
+    if (int e = h->d_rhs.upload(b, h->stream)) return e;
+    TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    h->n_cells = 0;  // a new operator invalidates the nodal structures
+    return 0;
+}
+
+static int upload_csr(tfin_ctx* h, const char* who, int rows, const int32_t* ptr, const int32_t* idx,
+                      const double* val, DevBuf<int>& dptr, DevBuf<int>& didx, DevBuf<double>& dval) {
+    if (h->n <= 0) return fail(TFIN_E_STATE, "%s: call tfin_set_operator first", who);
+    if (rows <= 0 || !ptr || !idx || !val) return fail(TFIN_E_ARG, "%s: bad argument", who);
+    if (ptr[0] != 0) return fail(TFIN_E_ARG, "%s: ptr[0] must be 0", who);
+    const int nnz = ptr[rows];
+    for (int r = 0; r < rows; ++r)
+        if (ptr[r + 1] < ptr[r]) return fail(TFIN_E_ARG, "%s: malformed ptr", who);
+    for (int j = 0; j < nnz; ++j)
+        if (idx[j] < 0 || idx[j] >= h->n) return fail(TFIN_E_ARG, "%s: index out of range", who);
+    std::vector<int> p(ptr, ptr + rows + 1), ix(idx, idx + nnz);
+    std::vector<double> v(val, val + nnz);
+    if (int e = dptr.upload(p, h->stream)) return e;
+    if (int e = didx.upload(ix, h->stream)) return e;
+    if (int e = dval.upload(v, h->stream)) return e;
+    TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_t* ptr, const int32_t* idx,
+                                    const double* val) {
+    CHECK_HANDLE(h);
+    if (int e = upload_csr(h, "tfin_set_observation", n_obs, ptr, idx, val, h->d_obs_ptr, h->d_obs_idx, h->d_obs_val))
+        return e;
+    h->n_obs = n_obs;
+    return 0;
+}
+
+extern "C" int tfin_set_averaging(tfin_handle_t h, int32_t n_rows, const int32_t* ptr, const int32_t* idx,
+                                  const double* val) {
+    CHECK_HANDLE(h);
+    if (int e = upload_csr(h, "tfin_set_averaging", n_rows, ptr, idx, val, h->d_avg_ptr, h->d_avg_idx, h->d_avg_val))
+        return e;
+    h->n_avg = n_rows;
+    return 0;
+}
+
+extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* cells, const double* Ke,
+                              int32_t prune_zeros) {
+    CHECK_HANDLE(h);
+    if (h->n <= 0) return fail(TFIN_E_STATE, "tfin_set_cells: call tfin_set_operator first");
+    if (n_cells <= 0 || !cells || !Ke) return fail(TFIN_E_ARG, "tfin_set_cells: bad argument");
+    const int n = h->n, ld = h->ld;
+    const std::vector<int32_t>& rp = h->h_row_ptr;
+    const std::vector<int32_t>& ci = h->h_col_idx;
+    const int nnz = (int)ci.size();
+    // per CSR entry: list of (cell, coef)
+    std::vector<std::vector<std::pair<int, double>>> contrib(nnz);
+    auto find = [&](int r, int c) -> int {
+        const int32_t* b = ci.data() + rp[r];
+        const int32_t* e = ci.data() + rp[r + 1];
+        const int32_t* it = std::lower_bound(b, e, c);
+        if (it != e && *it == c) return (int)(it - ci.data());
+        for (const int32_t* q = b; q != e; ++q)  // unsorted rows
+            if (*q == c) return (int)(q - ci.data());
+        return -1;
+    };
+    for (int e = 0; e < n_cells; ++e)
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                const int r = cells[3 * e + a], c = cells[3 * e + b];
+                if (r < 0 || r >= n || c < 0 || c >= n) return fail(TFIN_E_ARG, "tfin_set_cells: vertex out of range");
+                const int j = find(r, c);
+                if (j < 0) return fail(TFIN_E_ARG, "tfin_set_cells: entry (%d,%d) not in the operator pattern", r, c);
+                contrib[j].push_back({e, Ke[9 * (size_t)e + 3 * a + b]});
+            }
+    std::vector<std::vector<int>> keep(n);
+    std::vector<int> diag_pos(n, -1);
+    int W = 0;
+    for (int i = 0; i < n; ++i) {
+        for (int j = rp[i]; j < rp[i + 1]; ++j) {
+            if (ci[j] == i) {
+                diag_pos[i] = j;
+                continue;
+            }
+            if (contrib[j].size() > 2)
+                return fail(TFIN_E_ARG, "tfin_set_cells: edge (%d,%d) belongs to %d cells (non-manifold mesh)", i,
+                            ci[j], (int)contrib[j].size());
+            bool nz = !prune_zeros || h->h_const[j] != 0.0;
+            for (auto& pc : contrib[j]) nz = nz || pc.second != 0.0;
+            if (nz) keep[i].push_back(j);
+        }
+        W = std::max(W, (int)keep[i].size());
+    }
+    if (W == 0) W = 1;
+    const size_t plane = (size_t)W * ld;
+    std::vector<uint16_t> col(plane);
+    std::vector<int> cell(2 * plane, n_cells), dptr(ld + 1, 0), dcell, cl(cells, cells + 3 * (size_t)n_cells);
+    std::vector<double> coef(2 * plane, 0.0), cst(plane, 0.0), dcoef, dcst(ld, 1.0);
+    for (int w = 0; w < W; ++w)
+        for (int i = 0; i < ld; ++i) col[(size_t)w * ld + i] = (uint16_t)std::min(i, n - 1);
+    for (int i = 0; i < n; ++i) {
+        for (int w = 0; w < (int)keep[i].size(); ++w) {
+            const int j = keep[i][w];
+            const size_t o = (size_t)w * ld + i;
+            col[o] = (uint16_t)ci[j];
+            cst[o] = h->h_const[j];
+            for (size_t c = 0; c < contrib[j].size(); ++c) {
+                cell[c * plane + o] = contrib[j][c].first;
+                coef[c * plane + o] = contrib[j][c].second;
+            }
+        }
+        for (int w = (int)keep[i].size(); w < W; ++w) col[(size_t)w * ld + i] = (uint16_t)i;
+        dptr[i] = (int)dcell.size();
+        dcst[i] = h->h_const[diag_pos[i]];
+        for (auto& pc : contrib[diag_pos[i]]) {
+            dcell.push_back(pc.first);
+            dcoef.push_back(pc.second);
+        }
+    }
+    for (int i = n; i <= ld; ++i) dptr[i] = (int)dcell.size();
+    h->Wn = W;
+    if (int e = h->d_ncol.upload(col, h->stream)) return e;
+    if (int e = h->d_ncell.upload(cell, h->stream)) return e;
+    if (int e = h->d_ncoef.upload(coef, h->stream)) return e;
+    if (int e = h->d_ncst.upload(cst, h->stream)) return e;
+    if (int e = h->d_dptr.upload(dptr, h->stream)) return e;
+    if (int e = h->d_dcell.upload(dcell, h->stream)) return e;
+    if (int e = h->d_dcoef.upload(dcoef, h->stream)) return e;
+    if (int e = h->d_dcst.upload(dcst, h->stream)) return e;
+    if (int e = h->d_cells.upload(cl, h->stream)) return e;
+    TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    h->n_cells = n_cells;
+    return 0;
+}
+
+extern "C" int tfin_set_rom(tfin_handle_t h, int32_t n_r, int32_t n_terms, int32_t n_obs, const double* S,
+                            const double* G, const double* obs_phi) {
+    CHECK_HANDLE(h);
+    if (n_r <= 0 || n_r > 127 || !S || !G || !obs_phi || n_obs <= 0)
+        return fail(TFIN_E_ARG, "tfin_set_rom: bad argument (n_r must be in [1,127])");
+    if (n_terms < 1 || n_terms > TFIN_MAX_TERMS) return fail(TFIN_E_ARG, "tfin_set_rom: bad n_terms");
+    const int P2 = n_terms * (n_terms + 1) / 2, T = n_r * (n_r + 1) / 2, Taug = rom_taug(n_r);
+    // repack: row-major packed lower (i>=j -> i(i+1)/2+j)  ->  augmented column-major, G in the extra row
+    std::vector<double> Saug((size_t)P2 * Taug, 0.0);
+    int pq = 0;
+    for (int p = 0; p < n_terms; ++p)
+        for (int q = p; q < n_terms; ++q, ++pq) {
+            double* dst = Saug.data() + (size_t)pq * Taug;
+            const double* src = S + (size_t)pq * T;
+            for (int j = 0; j < n_r; ++j) {
+                const int oj = rom_col_off(j, n_r);
+                for (int i = j; i < n_r; ++i) dst[oj + (i - j)] = src[(size_t)i * (i + 1) / 2 + j];
+                if (p == 0) dst[oj + (n_r - j)] = G[(size_t)q * n_r + j];  // coefficient th_0 th_q = th_q
+            }
+        }
+    std::vector<double> op(obs_phi, obs_phi + (size_t)n_obs * n_r);
+    if (int e = h->d_S.upload(Saug, h->stream)) return e;
+    if (int e = h->d_obs_phi.upload(op, h->stream)) return e;
+    TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    h->n_r = n_r;
+    h->rom_terms = n_terms;
+    h->rom_obs = n_obs;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ launch helpers
+struct PcgGeom {
+    int R, T, occ, grid;
+    size_t smem;
+};
+
+template <typename Kern>
+static int pcg_geom_for(tfin_ctx* h, Kern kern, int R, int maxT, int W, int n_cells, PcgGeom* g) {
+    const int n = h->n;
+    const int T = ((n + R - 1) / R + 31) & ~31;
+    if (T > maxT || T > 1024) return 1;
+    const PcgSmem L = PcgSmem::make(W, R * T, n_cells, n);
+    if (L.total > (size_t)h->max_smem_optin) return 1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, L.total) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return 1;
+    }
+    g->R = R;
+    g->T = T;
+    g->occ = occ;
+    g->smem = L.total;
+    return 0;
+}
+
+#define PCG_FOR_EACH_R(X) X(1, 1024) X(2, 768) X(3, 640) X(4, 512) X(5, 384) X(6, 352) X(8, 256)
+
+template <bool NODAL>
+static int launch_pcg(tfin_ctx* h, const double* d_in, int in_stride, int64_t N, double tol, int maxit,
+                      double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres,
+                      cudaStream_t st) {
+    const int W = NODAL ? h->Wn : h->W;
+    const int nc = NODAL ? h->n_cells : 0;
+    PcgGeom best{};
+    bool have = false;
+    // pick rows/thread: user override, else the geometry with the most resident threads per SM and,
+    // among those, the least padding
+    double best_score = -1.0;
+#define TRY_R(R_, MAXT_)                                                                              \
+    if (h->pcg_R == 0 || h->pcg_R == R_) {                                                            \
+        PcgGeom g{};                                                                                   \
+        int rc = NODAL ? pcg_geom_for(h, pcg_nodal_kernel<R_, MAXT_>, R_, MAXT_, W, nc, &g)           \
+                       : pcg_geom_for(h, pcg_affine_kernel<R_, MAXT_>, R_, MAXT_, W, nc, &g);         \
+        if (rc == 0) {                                                                                 \
+            const double pad = (double)h->n / (g.R * g.T);                                             \
+            const double score = std::min(g.occ * g.T, 1024) * pad * (g.occ >= 2 ? 1.15 : 1.0);       \
+            if (score > best_score) {                                                                  \
+                best_score = score;                                                                    \
+                best = g;                                                                              \
+                have = true;                                                                           \
+            }                                                                                          \
+        }                                                                                              \
+    }
+    PCG_FOR_EACH_R(TRY_R)
+#undef TRY_R
+    if (!have)
+        return fail(TFIN_E_STATE, "on-chip PCG: no launch geometry fits (n=%d, W=%d, rows/thread=%d)", h->n, W,
+                    h->pcg_R);
+    const int grid = (int)std::min<int64_t>(N, (int64_t)h->sm_count * best.occ);
+    h->last_R = best.R;
+    h->last_T = best.T;
+    h->last_occ = best.occ;
+    h->last_smem = best.smem;
+
+    TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
+    CsrRows obs{h->n_obs, h->d_obs_ptr.p, h->d_obs_idx.p, h->d_obs_val.p};
+    PcgIO io{d_in, (long long)N, in_stride, tol * tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres,
+             h->d_counter.p};
+    if (NODAL) {
+        EllNodal op{h->n,        h->ld,        W,           nc,          h->d_ncol.p, h->d_ncell.p,
+                    h->d_ncoef.p, h->d_ncst.p, h->d_dptr.p, h->d_dcell.p, h->d_dcoef.p, h->d_dcst.p,
+                    h->d_cells.p, h->d_rhs.p};
+#define LAUNCH_R(R_, MAXT_) \
+    if (best.R == R_) pcg_nodal_kernel<R_, MAXT_><<<grid, best.T, best.smem, st>>>(op, obs, io);
+        PCG_FOR_EACH_R(LAUNCH_R)
+#undef LAUNCH_R
+    } else {
+        EllAffine op{h->n, h->ld, W, h->n_terms, h->d_col.p, h->d_val.p, h->d_diag.p, h->d_rhs.p};
+#define LAUNCH_R(R_, MAXT_) \
+    if (best.R == R_) pcg_affine_kernel<R_, MAXT_><<<grid, best.T, best.smem, st>>>(op, obs, io);
+        PCG_FOR_EACH_R(LAUNCH_R)
+#undef LAUNCH_R
+    }
+    TFIN_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+static int launch_project(tfin_ctx* h, const CsrRows& op, const double* d_k, int64_t N, double* d_out,
+                          cudaStream_t st) {
+    const int64_t warps = N * op.rows;
+    const int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)h->sm_count * 16);
+    csr_project_kernel<<<std::max(blocks, 1), 256, 0, st>>>(op, d_k, (long long)N, h->n, d_out);
+    TFIN_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+// Host <-> device staging for one batch call.
+struct Staged {
+    tfin_ctx* h;
+    cudaStream_t st;
+    bool host;
+    template <typename T>
+    int in(const T* src, size_t count, DevBuf<T>& buf, const T** dev) {
+        if (!host) {
+            *dev = src;
+            return 0;
+        }
+        if (int e = buf.reserve(count)) return e;
+        TFIN_CUDA(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+        *dev = buf.p;
+        return 0;
+    }
+    template <typename T>
+    int out_alloc(T* dst, size_t count, DevBuf<T>& buf, T** dev) {
+        if (!dst) {
+            *dev = nullptr;
+            return 0;
+        }
+        if (!host) {
+            *dev = dst;
+            return 0;
+        }
+        if (int e = buf.reserve(count)) return e;
+        *dev = buf.p;
+        return 0;
+    }
+    template <typename T>
+    int out_copy(T* dst, size_t count, const T* dev) {
+        if (!dst || !host) return 0;
+        TFIN_CUDA(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ solves
+extern "C" int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double* theta_out,
+                               void* stream) {
+    CHECK_HANDLE(h);
+    if (h->n_avg <= 0) return fail(TFIN_E_STATE, "tfin_subfin_avg: call tfin_set_averaging first");
+    if (N < 0 || (N > 0 && (!k || !theta_out))) return fail(TFIN_E_ARG, "tfin_subfin_avg: bad argument");
+    if (N == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    Staged sg{h, st, mem == TFIN_MEM_HOST};
+    const double* d_k;
+    double* d_out;
+    if (int e = sg.in(k, (size_t)N * h->n, h->d_in, &d_k)) return e;
+    if (int e = sg.out_alloc(theta_out, (size_t)N * h->n_avg, h->d_theta, &d_out)) return e;
+    CsrRows avg{h->n_avg, h->d_avg_ptr.p, h->d_avg_idx.p, h->d_avg_val.p};
+    if (int e = launch_project(h, avg, d_k, N, d_out, st)) return e;
+    if (int e = sg.out_copy(theta_out, (size_t)N * h->n_avg, d_out)) return e;
+    if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int fom_common(tfin_handle_t h, bool nodal_op, const double* in, int64_t N, int32_t in_kind, int32_t mem,
+                      double tol, int32_t maxit, double* w_out, double* qoi_out, int32_t* iters_out,
+                      int32_t* status_out, double* relres_out, void* stream) {
+    if (h->n <= 0) return fail(TFIN_E_STATE, "FOM solve: call tfin_set_operator first");
+    if (N < 0 || (N > 0 && !in)) return fail(TFIN_E_ARG, "FOM solve: bad batch argument");
+    if (!(tol > 0.0) || maxit < 1) return fail(TFIN_E_ARG, "FOM solve: tol must be > 0 and maxit >= 1");
+    if (qoi_out && h->n_obs <= 0) return fail(TFIN_E_STATE, "FOM solve: qoi requested but no observation operator");
+    if (nodal_op && h->n_cells <= 0) return fail(TFIN_E_STATE, "tfin_fom_nodal: call tfin_set_cells first");
+    if (N == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    Staged sg{h, st, mem == TFIN_MEM_HOST};
+    const int nparam = h->n_terms - 1;
+    const bool nodal_in = nodal_op || in_kind == TFIN_IN_NODAL;
+    const int in_cols = nodal_in ? h->n : nparam;
+    const double* d_in;
+    if (int e = sg.in(in, (size_t)N * in_cols, h->d_in, &d_in)) return e;
+    const double* d_par = d_in;
+    int stride = in_cols;
+    if (!nodal_op && nodal_in) {  // AffineROMFin.forward(k): theta = subfin_avg_op(k)
+        if (h->n_avg != nparam) return fail(TFIN_E_STATE, "nodal input needs tfin_set_averaging with %d rows", nparam);
+        if (int e = h->d_theta.reserve((size_t)N * nparam)) return e;
+        CsrRows avg{h->n_avg, h->d_avg_ptr.p, h->d_avg_idx.p, h->d_avg_val.p};
+        if (int e = launch_project(h, avg, d_in, N, h->d_theta.p, st)) return e;
+        d_par = h->d_theta.p;
+        stride = nparam;
+    }
+    double *d_w, *d_qoi, *d_relres;
+    int *d_iters, *d_status;
+    if (int e = sg.out_alloc(w_out, (size_t)N * h->n, h->d_w, &d_w)) return e;
+    if (int e = sg.out_alloc(qoi_out, (size_t)N * h->n_obs, h->d_qoi, &d_qoi)) return e;
+    if (int e = sg.out_alloc(iters_out, (size_t)N, h->d_iters, &d_iters)) return e;
+    if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
+    if (int e = sg.out_alloc(relres_out, (size_t)N, h->d_relres, &d_relres)) return e;
+    int rc = nodal_op ? launch_pcg<true>(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st)
+                      : launch_pcg<false>(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st);
+    if (rc) return rc;
+    if (int e = sg.out_copy(w_out, (size_t)N * h->n, d_w)) return e;
+    if (int e = sg.out_copy(qoi_out, (size_t)N * h->n_obs, d_qoi)) return e;
+    if (int e = sg.out_copy(iters_out, (size_t)N, d_iters)) return e;
+    if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
+    if (int e = sg.out_copy(relres_out, (size_t)N, d_relres)) return e;
+    if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int tfin_fom_affine(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int32_t mem,
+                               double tol, int32_t maxit, double* w_out, double* qoi_out, int32_t* iters_out,
+                               int32_t* status_out, double* relres_out, void* stream) {
+    CHECK_HANDLE(h);
+    if (in_kind != TFIN_IN_PARAMS && in_kind != TFIN_IN_NODAL) return fail(TFIN_E_ARG, "tfin_fom_affine: bad in_kind");
+    return fom_common(h, false, in, N, in_kind, mem, tol, maxit, w_out, qoi_out, iters_out, status_out, relres_out,
+                      stream);
+}
+
+extern "C" int tfin_fom_nodal(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double tol, int32_t maxit,
+                              double* w_out, double* qoi_out, int32_t* iters_out, int32_t* status_out,
+                              double* relres_out, void* stream) {
+    CHECK_HANDLE(h);
+    return fom_common(h, true, k, N, TFIN_IN_NODAL, mem, tol, maxit, w_out, qoi_out, iters_out, status_out,
+                      relres_out, stream);
+}
+
+extern "C" int tfin_rom(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int32_t mem, double* wr_out,
+                        double* qoi_out, int32_t* status_out, void* stream) {
+    CHECK_HANDLE(h);
+    if (h->n_r <= 0) return fail(TFIN_E_STATE, "tfin_rom: call tfin_set_rom first");
+    if (in_kind != TFIN_IN_PARAMS && in_kind != TFIN_IN_NODAL) return fail(TFIN_E_ARG, "tfin_rom: bad in_kind");
+    if (N < 0 || (N > 0 && !in)) return fail(TFIN_E_ARG, "tfin_rom: bad batch argument");
+    if (N == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    Staged sg{h, st, mem == TFIN_MEM_HOST};
+    const int nt = h->rom_terms, nparam = nt - 1, nr = h->n_r, nobs = h->rom_obs;
+    const bool nodal_in = in_kind == TFIN_IN_NODAL;
+    if (nodal_in && h->n <= 0) return fail(TFIN_E_STATE, "tfin_rom: nodal input needs tfin_set_operator");
+    const int in_cols = nodal_in ? h->n : nparam;
+    const double* d_in;
+    if (int e = sg.in(in, (size_t)N * in_cols, h->d_in, &d_in)) return e;
+    const double* d_par = d_in;
+    if (nodal_in) {  // forward_reduced(k): theta = subfin_avg_op(k), averaged_affine_ROM.py:274
+        if (h->n_avg != nparam) return fail(TFIN_E_STATE, "tfin_rom: nodal input needs tfin_set_averaging with %d rows", nparam);
+        if (int e = h->d_theta.reserve((size_t)N * nparam)) return e;
+        CsrRows avg{h->n_avg, h->d_avg_ptr.p, h->d_avg_idx.p, h->d_avg_val.p};
+        if (int e = launch_project(h, avg, d_in, N, h->d_theta.p, st)) return e;
+        d_par = h->d_theta.p;
+    }
+    double *d_wr, *d_qoi;
+    int* d_status;
+    if (int e = sg.out_alloc(wr_out, (size_t)N * nr, h->d_wr, &d_wr)) return e;
+    if (int e = sg.out_alloc(qoi_out, (size_t)N * nobs, h->d_qoi, &d_qoi)) return e;
+    if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
+
+    const int Taug = rom_taug(nr), P2 = nt * (nt + 1) / 2;
+    const int per_warp = ((Taug + 2 * nr + 2) + 1) & ~1;
+    int wpb = std::min<int>(8, (int)((size_t)(h->max_smem_optin - 1024) / ((size_t)per_warp * 8)));
+    if (wpb < 1) return fail(TFIN_E_STATE, "tfin_rom: n_r = %d does not fit shared memory", nr);
+    const size_t chol_smem = (size_t)wpb * per_warp * 8;
+    const size_t comb_smem = ((size_t)P2 * (ROM_BM + ROM_BN) + (size_t)ROM_BM * nt) * 8;
+    const int64_t chunk = h->rom_chunk > 0 ? h->rom_chunk : (int64_t)h->sm_count * wpb * 8;
+    if (int e = h->d_romC.reserve((size_t)std::min<int64_t>(chunk, N) * Taug)) return e;
+    TFIN_CUDA(cudaFuncSetAttribute(rom_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comb_smem));
+    const int maxm = (nr + 1 + 31) / 32;
+    auto chol = maxm == 1 ? rom_chol_kernel<1> : maxm == 2 ? rom_chol_kernel<2> : maxm == 3 ? rom_chol_kernel<3> : rom_chol_kernel<4>;
+    TFIN_CUDA(cudaFuncSetAttribute(chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
+        const int64_t s1 = std::min<int64_t>(N, s0 + chunk);
+        dim3 g1((unsigned)((s1 - s0 + ROM_BM - 1) / ROM_BM), (unsigned)((Taug + ROM_BN - 1) / ROM_BN));
+        rom_combine_kernel<<<g1, 256, comb_smem, st>>>(d_par, s0, s1, nt, h->d_S.p, Taug, h->d_romC.p);
+        const int g2 = (int)std::min<int64_t>((s1 - s0 + wpb - 1) / wpb, (int64_t)h->sm_count * 4);
+        chol<<<g2, wpb * 32, chol_smem, st>>>(h->d_romC.p, s0, s1, nr, nobs, h->d_obs_phi.p, d_wr, d_qoi, d_status);
+        h->launches += 2;
+    }
+    TFIN_CUDA(cudaGetLastError());
+    if (int e = sg.out_copy(wr_out, (size_t)N * nr, d_wr)) return e;
+    if (int e = sg.out_copy(qoi_out, (size_t)N * nobs, d_qoi)) return e;
+    if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
+    if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ introspection
+extern "C" int64_t tfin_kernel_launches(tfin_handle_t h) { return h ? h->launches : -1; }
+
+extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
+    if (!h || !key) return -1;
+    const std::string k(key);
+    if (k == "n") return h->n;
+    if (k == "n_obs") return h->n_obs;
+    if (k == "n_terms") return h->n_terms;
+    if (k == "n_r") return h->n_r;
+    if (k == "n_cells") return h->n_cells;
+    if (k == "ell_width") return h->W;
+    if (k == "ell_width_nodal") return h->Wn;
+    if (k == "sm_count") return h->sm_count;
+    if (k == "pcg_threads") return h->last_T;
+    if (k == "pcg_rows_per_thread") return h->last_R;
+    if (k == "pcg_ctas_per_sm") return h->last_occ;
+    if (k == "pcg_smem_bytes") return (int64_t)h->last_smem;
+    if (k == "rom_chunk") return h->rom_chunk;
+    return -1;
+}
+
+extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
+    if (!h || !key) return fail(TFIN_E_ARG, "tfin_set_int: bad argument");
+    const std::string k(key);
+    if (k == "pcg_rows_per_thread") {
+        h->pcg_R = (int)value;
+        return 0;
+    }
+    if (k == "rom_chunk") {
+        h->rom_chunk = value;
+        return 0;
+    }
+    return fail(TFIN_E_ARG, "tfin_set_int: unknown key '%s'", key);
+}

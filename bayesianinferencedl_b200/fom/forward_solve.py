@@ -1,0 +1,168 @@
+"""``Fin`` -- full-order thermal-fin model with nodal (P1-field) conductivity, B200-native.
+
+Mirrors the forward-map part of the reference's ``fom/forward_solve.py`` (class ``Fin`` :93, ``forward`` :270,
+``forward_five_param`` :267, ``nine_param_to_function`` :482, ``qoi_operator`` :408, ``observation_operator``
+:488, ``subfin_avg_op`` :466, ``averaging_operator`` :396).  dolfin ``Function`` arguments are nodal arrays here
+(the reference itself round-trips through ``.vector()[:]`` / ``set_local``); wherever the reference takes ONE
+conductivity field, a leading batch axis is accepted as well: ``(n,) -> (n,)``, ``(N, n) -> (N, n)``.
+
+All solves run in the sm_100a kernels of libtfin.so through the C ABI (include/tfin.h); there is no CPU path.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .. import _cabi
+from ..assembly import BIOT, build_operators, five_to_nine, nine_param_nodal
+from .thermal_fin import FinSpace, Function
+
+__all__ = ["Fin"]
+
+DEFAULT_TOL = 1e-12      # on sqrt(r.z / r0.z0); observables are then ~1e-12 relative
+DEFAULT_MAXIT = 20000
+
+
+def _as_batch(a, width, what):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        if a.shape[0] != width:
+            raise ValueError(f"{what}: expected length {width}, got {a.shape[0]}")
+        return np.ascontiguousarray(a[None, :]), True
+    if a.ndim != 2 or a.shape[1] != width:
+        raise ValueError(f"{what}: expected shape ({width},) or (N, {width}), got {a.shape}")
+    return np.ascontiguousarray(a), False
+
+
+class Fin:
+    """Heat conduction in the thermal fin, ``-div(k grad w) = 0``, Robin (Bi = 0.1) on the exterior, unit
+    flux at the root (forward_solve.py:160-162)."""
+
+    def __init__(self, V: FinSpace, external_obs=False, *, device=0, tol=DEFAULT_TOL, maxit=DEFAULT_MAXIT,
+                 prune_zeros=True):
+        self.phi = None
+        self.V = V
+        self.ops = build_operators(V)
+        self.dofs = self.ops.n
+        self.Bi = BIOT
+        self.tol, self.maxit = float(tol), int(maxit)
+
+        self.B = self.ops.rhs.copy()                                    # forward_solve.py:163
+        self.C, self.domain_measure = self.averaging_operator()         # forward_solve.py:164
+        (self.fin1_A, self.fin2_A, self.fin3_A, self.fin4_A, self.fin5_A,
+         self.fin6_A, self.fin7_A, self.fin8_A, self.fin9_A) = self.ops.subfin_area   # :205-213
+
+        if external_obs is not False and external_obs is not None:       # forward_solve.py:215-228
+            self.n_obs = 40
+            b_vals = self._external_indices(external_obs)
+            self.B_obs = np.zeros((self.n_obs, self.dofs))
+            self.B_obs[np.arange(self.n_obs), b_vals] = 1
+            self.boundary_indices = np.zeros(self.dofs, dtype=bool)
+            self.boundary_indices[self.ops.boundary_dofs] = True
+        else:
+            self.n_obs = 9
+            self.B_obs = self.observation_operator()                     # forward_solve.py:229-231
+
+        self._h = _cabi.TfinHandle(device)
+        self._h.set_operator(self.ops.row_ptr, self.ops.col_idx, self.ops.vals, self.ops.rhs, prune_zeros)
+        self._h.set_observation(*self.ops.obs_csr(self.B_obs))
+        self._h.set_averaging(*self.ops.obs_csr(self.ops.B_obs))
+        self._h.set_cells(self.ops.cells, self.ops.Ke, prune_zeros)
+
+    # ------------------------------------------------------------------ helpers
+    def _external_indices(self, external_obs):
+        if not isinstance(external_obs, (bool, np.bool_)):
+            idx = np.asarray(external_obs, dtype=np.int64)
+            if idx.shape != (self.n_obs,):
+                raise ValueError("external_obs index array must have 40 entries")
+            return idx
+        path = os.path.join("..", "bayesian_inference", "rand_boundary_indices.npy")   # :226
+        if os.path.exists(path):
+            return np.load(path)
+        # the commented recipe of forward_solve.py:223-225
+        rs = np.random.RandomState(32)
+        return rs.choice(self.ops.boundary_dofs, self.n_obs)
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ------------------------------------------------------------------ forward map
+    def forward(self, k):
+        """forward_solve.py:270-291.  ``k``: nodal conductivity (n,) or (N, n).
+        Returns ``(w, None, None, None, None)`` like the reference (four legacy slots are None)."""
+        kb, single = _as_batch(k, self.dofs, "Fin.forward")
+        out = self._h.fom_nodal(kb, tol=self.tol, maxit=self.maxit, want_w=True, want_qoi=False)
+        self._last = out
+        self._raise_on_failure(out)
+        w = out["w"]
+        return Function(w[0] if single else w), None, None, None, None
+
+    def forward_qoi(self, k, return_stats=False):
+        """Fused ``qoi_operator(forward(k)[0])`` without materialising w: (n,)|(N,n) -> (n_obs,)|(N,n_obs)."""
+        kb, single = _as_batch(k, self.dofs, "Fin.forward_qoi")
+        out = self._h.fom_nodal(kb, tol=self.tol, maxit=self.maxit, want_w=False, want_qoi=True)
+        self._last = out
+        self._raise_on_failure(out)
+        q = out["qoi"][0] if single else out["qoi"]
+        return (q, out) if return_stats else q
+
+    def forward_five_param(self, k_s):
+        """forward_solve.py:267-268 (``five_param_to_function`` lives in forward_solve_petsc.py:243-260)."""
+        return self.forward(self.five_param_to_function(k_s))
+
+    def five_param_to_function(self, k_s):
+        return self.nine_param_to_function(five_to_nine(k_s))
+
+    def nine_param_to_function(self, k_s):
+        """forward_solve.py:482-486: interpolate the piecewise-constant SubfinValExpr to P1."""
+        k_s = np.asarray(k_s, dtype=np.float64)
+        if k_s.shape[-1] != 9:
+            raise ValueError("nine_param_to_function: need 9 values")
+        return Function(nine_param_nodal(self.ops.coords, k_s))
+
+    def _raise_on_failure(self, out):
+        st = out["status"]
+        if st is not None and np.any(st != _cabi.STATUS_CONVERGED):
+            bad = np.nonzero(st != _cabi.STATUS_CONVERGED)[0]
+            raise RuntimeError(f"PCG did not converge for {len(bad)} sample(s) (first: {bad[0]}, status "
+                               f"{int(st[bad[0]])}, relres {out['relres'][bad[0]]:.3e}); is k > 0 everywhere?")
+
+    # ------------------------------------------------------------------ observation
+    def qoi_operator(self, x):
+        """forward_solve.py:408-412: ``B_obs @ x`` for (n,) or (N, n)."""
+        x = np.asarray(x, dtype=np.float64)
+        return x @ self.B_obs.T if x.ndim == 2 else np.dot(self.B_obs, x)
+
+    def reduced_qoi_operator(self, z_r):
+        """forward_solve.py:415-419."""
+        return self.qoi_operator(np.dot(self.phi, z_r))
+
+    def observation_operator(self):
+        """forward_solve.py:488-511: 9 x n matrix of sub-fin averages of the test functions."""
+        return self.ops.B_obs.copy()
+
+    def subfin_avg_op(self, k):
+        """forward_solve.py:466-480: the nine sub-fin means of a nodal field; batched on the GPU."""
+        kb, single = _as_batch(k, self.dofs, "Fin.subfin_avg_op")
+        out = self._h.subfin_avg(kb)
+        return out[0] if single else out
+
+    def averaging_operator(self):
+        """forward_solve.py:396-406."""
+        return self.ops.C.copy(), self.ops.domain_measure
+
+    # ------------------------------------------------------------------ not on the batched path (yet)
+    def reduced_forward(self, A, B, C, psi, phi):
+        raise NotImplementedError("dense generic LSPG (forward_solve.py:421-452) is not part of the batched "
+                                  "path; use AffineROMFin.forward_reduced (DESIGN.md, 'next').")
+
+    def r_fwd_no_full(self, k, phi):
+        raise NotImplementedError("nodal-conductivity LSPG (forward_solve.py:454-464) is a 'next' row in DESIGN.md")
+
+    def gradient(self, k, data):
+        raise NotImplementedError("adjoint gradient (forward_solve.py:293-322) is a 'next' row in DESIGN.md")
+
+    def sensitivity(self, k):
+        raise NotImplementedError("sensitivity (forward_solve.py:324-342) is a 'next' row in DESIGN.md")

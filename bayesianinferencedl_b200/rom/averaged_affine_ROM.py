@@ -1,0 +1,194 @@
+"""``AffineROMFin`` -- nine-parameter affine thermal fin and its LSPG reduced-order model, B200-native.
+
+Mirrors the forward-map part of the reference's ``rom/averaged_affine_ROM.py`` (class ``AffineROMFin`` :52,
+``forward`` :237, ``forward_reduced`` :260, ``forward_nine_param_reduced`` :278, ``qoi`` :312, ``qoi_reduced``
+:323, ``subfin_avg_op`` :404, ``observation_operator`` :420, ``set_data`` :398, ``set_dl_model`` :401) plus the
+scalar-parameter entry point ``forward_nine_param`` of ``rom/generate_reduced_basis_nine_param.py:178-183``.
+
+A leading batch axis is accepted wherever the reference takes one sample.  The affine FOM runs in the batched
+PCG kernel, the ROM in the Gram-tensor GEMM + warp-per-sample Cholesky kernels of libtfin.so.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from .. import _cabi
+from ..assembly import BIOT, build_operators, five_to_nine
+from ..fom.forward_solve import DEFAULT_MAXIT, DEFAULT_TOL, _as_batch
+from ..fom.thermal_fin import FinSpace, Function
+
+__all__ = ["AffineROMFin", "rom_offline_tensors"]
+
+
+def rom_offline_tensors(ops, phi, B_obs):
+    """Offline tensors of the LSPG ROM (averaged_affine_ROM.py:292-304 rewritten for affine A):
+    Psi_t = V_t phi (V_0 = Bi M, V_q = K_q);  S_pq = Psi_p^T Psi_q (+ transpose if p<q), packed lower
+    row-major;  G_t = Psi_t^T b;  obs_phi = B_obs phi (averaged_affine_ROM.py:212)."""
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    n_terms = ops.vals.shape[0]
+    n_r = phi.shape[1]
+    Psi = [ops.csr(ops.vals[t]) @ phi for t in range(n_terms)]
+    il = np.tril_indices(n_r)
+    S = np.empty((n_terms * (n_terms + 1) // 2, len(il[0])))
+    pq = 0
+    for p in range(n_terms):
+        for q in range(p, n_terms):
+            M = Psi[p].T @ Psi[q]
+            if q != p:
+                M = M + M.T
+            S[pq] = M[il]
+            pq += 1
+    G = np.stack([P.T @ ops.rhs for P in Psi])
+    return S, G, B_obs @ phi
+
+
+class AffineROMFin:
+    """Affine FOM ``A(k_s) = sum_q k_s[q] K_q + Bi M`` (averaged_affine_ROM.py:156-162) and its LSPG ROM."""
+
+    def __init__(self, V: FinSpace, err_model, phi, external_obs=False, *, device=0, tol=DEFAULT_TOL,
+                 maxit=DEFAULT_MAXIT, prune_zeros=True):
+        self.fwd_time = 0.0                       # averaged_affine_ROM.py:64-67 (kept for API parity)
+        self.rom_grad_time = 0.0
+        self.romml_grad_time = 0.0
+        self.romml_grad_time_dl = 0.0
+        self.num_params = 9
+        self.tol, self.maxit = float(tol), int(maxit)
+
+        self.phi = np.ascontiguousarray(phi, dtype=np.float64)
+        if self.phi.ndim != 2:
+            raise ValueError("phi must be (n, n_r)")
+        (self.n, self.n_r) = self.phi.shape
+        self.V = V
+        self.ops = build_operators(V)
+        self.dofs = self.ops.n
+        if self.n != self.dofs:
+            raise ValueError(f"basis has {self.n} rows but the space has {self.dofs} dofs")
+        self.Bi = BIOT
+        self.B = self.ops.rhs.copy()
+        (self.fin1_A, self.fin2_A, self.fin3_A, self.fin4_A, self.fin5_A,
+         self.fin6_A, self.fin7_A, self.fin8_A, self.fin9_A) = self.ops.subfin_area
+
+        if external_obs is not False and external_obs is not None:
+            from ..fom.forward_solve import Fin
+            self.n_obs = 40
+            b_vals = Fin._external_indices(self, external_obs)
+            self.B_obs = np.zeros((self.n_obs, self.dofs))
+            self.B_obs[np.arange(self.n_obs), b_vals] = 1
+        else:
+            self.n_obs = 9
+            self.B_obs = self.observation_operator()
+        self.dsigma_dk = self.observation_operator()                   # :210
+        self.B_obs_phi = np.dot(self.B_obs, self.phi)                   # :212
+        self.dl_model = err_model
+        self.data = None
+
+        S, G, obs_phi = rom_offline_tensors(self.ops, self.phi, self.B_obs)
+        self._h = _cabi.TfinHandle(device)
+        self._h.set_operator(self.ops.row_ptr, self.ops.col_idx, self.ops.vals, self.ops.rhs, prune_zeros)
+        self._h.set_observation(*self.ops.obs_csr(self.B_obs))
+        self._h.set_averaging(*self.ops.obs_csr(self.ops.B_obs))
+        self._h.set_rom(S, G, obs_phi)
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ------------------------------------------------------------------ full-order affine model
+    def forward(self, k):
+        """:237-258.  ``k`` nodal field (n,) | (N, n): averaged over the sub-fins, then the affine solve."""
+        kb, single = _as_batch(k, self.dofs, "AffineROMFin.forward")
+        out = self._h.fom_affine(kb, _cabi.IN_NODAL, tol=self.tol, maxit=self.maxit, want_w=True, want_qoi=False)
+        self._check(out)
+        return Function(out["w"][0] if single else out["w"])
+
+    def forward_nine_param(self, k_s):
+        """generate_reduced_basis_nine_param.py:178-183: (9,) | (N, 9) sub-fin conductivities -> w."""
+        tb, single = _as_batch(k_s, self.num_params, "AffineROMFin.forward_nine_param")
+        out = self._h.fom_affine(tb, _cabi.IN_PARAMS, tol=self.tol, maxit=self.maxit, want_w=True, want_qoi=False)
+        self._check(out)
+        return Function(out["w"][0] if single else out["w"])
+
+    def forward_five_param(self, k_s):
+        return self.forward_nine_param(five_to_nine(k_s))
+
+    def forward_nine_param_qoi(self, k_s, return_stats=False):
+        """Fused ``qoi(forward_nine_param(k_s))`` without materialising w."""
+        tb, single = _as_batch(k_s, self.num_params, "AffineROMFin.forward_nine_param_qoi")
+        out = self._h.fom_affine(tb, _cabi.IN_PARAMS, tol=self.tol, maxit=self.maxit, want_w=False, want_qoi=True)
+        self._check(out)
+        q = out["qoi"][0] if single else out["qoi"]
+        return (q, out) if return_stats else q
+
+    def _check(self, out):
+        st = out["status"]
+        if st is not None and np.any(st != _cabi.STATUS_CONVERGED):
+            bad = np.nonzero(st != _cabi.STATUS_CONVERGED)[0]
+            raise RuntimeError(f"solve failed for {len(bad)} sample(s) (first: {bad[0]}, status {int(st[bad[0]])}); "
+                               "conductivities must be positive")
+
+    # ------------------------------------------------------------------ reduced-order model
+    def forward_reduced(self, k):
+        """:260-276.  ``k`` nodal field (n,) | (N, n) -> w_r (n_r,) | (N, n_r)."""
+        t_i = time.time()
+        kb, single = _as_batch(k, self.dofs, "AffineROMFin.forward_reduced")
+        out = self._h.rom(kb, _cabi.IN_NODAL, want_wr=True, want_qoi=False)
+        self._check(out)
+        self.fwd_time += time.time() - t_i
+        return out["w_r"][0] if single else out["w_r"]
+
+    def forward_nine_param_reduced(self, k_s):
+        """:278-310.  (9,) | (N, 9) -> w_r."""
+        t_i = time.time()
+        tb, single = _as_batch(k_s, self.num_params, "AffineROMFin.forward_nine_param_reduced")
+        out = self._h.rom(tb, _cabi.IN_PARAMS, want_wr=True, want_qoi=False)
+        self._check(out)
+        self.fwd_time += time.time() - t_i
+        return out["w_r"][0] if single else out["w_r"]
+
+    def forward_reduced_qoi(self, k_or_ks):
+        """Fused ``qoi_reduced(forward_[nine_param_]reduced(.))``; the input kind is inferred from the width."""
+        a = np.asarray(k_or_ks, dtype=np.float64)
+        kind = _cabi.IN_PARAMS if a.shape[-1] == self.num_params and self.num_params != self.dofs else _cabi.IN_NODAL
+        ab, single = _as_batch(a, self.num_params if kind == _cabi.IN_PARAMS else self.dofs, "forward_reduced_qoi")
+        out = self._h.rom(ab, kind, want_wr=False, want_qoi=True)
+        self._check(out)
+        return out["qoi"][0] if single else out["qoi"]
+
+    # ------------------------------------------------------------------ observation
+    def qoi(self, w):
+        """:312-321."""
+        w = np.asarray(w, dtype=np.float64)
+        return w @ self.B_obs.T if w.ndim == 2 else np.dot(self.B_obs, w)
+
+    def qoi_reduced(self, w_r):
+        """:323-333."""
+        t_i = time.time()
+        w_r = np.asarray(w_r, dtype=np.float64)
+        q = w_r @ self.B_obs_phi.T if w_r.ndim == 2 else np.dot(self.B_obs_phi, w_r)
+        self.fwd_time += time.time() - t_i
+        return q
+
+    def subfin_avg_op(self, k):
+        """:404-418, batched on the GPU."""
+        kb, single = _as_batch(k, self.dofs, "AffineROMFin.subfin_avg_op")
+        out = self._h.subfin_avg(kb)
+        return out[0] if single else out
+
+    def observation_operator(self):
+        """:420-445."""
+        return self.ops.B_obs.copy()
+
+    def set_data(self, data):
+        self.data = data
+
+    def set_dl_model(self, model):
+        self.dl_model = model
+
+    # ------------------------------------------------------------------ 'next' rows
+    def grad_reduced(self, k):
+        raise NotImplementedError("ROM adjoint gradient (averaged_affine_ROM.py:335-356) is a 'next' row in DESIGN.md")
+
+    def grad_romml(self, k):
+        raise NotImplementedError("ROM+NN gradient (averaged_affine_ROM.py:358-396) is out of scope (TensorFlow model)")

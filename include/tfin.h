@@ -1,0 +1,147 @@
+/*
+ * tfin.h -- C ABI of the B200-native thermal-fin batched forward map (libtfin.so).
+ *
+ * The reference (sheroze1123/BayesianInferenceDL) has no FFI: its hot path is Python methods calling
+ * FEniCS/PETSc/LAPACK one conductivity sample at a time.  Every entry point below therefore names the
+ * reference METHOD (file:line under /root/reference) whose per-sample arithmetic it performs for a whole
+ * batch; the Python facade in bayesianinferencedl_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - all functions return 0 on success, <0 on error; tfin_last_error() gives the message (thread local)
+ *   - all floating point data is IEEE fp64, row-major, C-contiguous; indices are int32
+ *   - the caller owns every buffer; the library owns only the handle and its device workspaces
+ *   - `mem` says where the batch buffers (inputs AND outputs of a solve call) live:
+ *       TFIN_MEM_HOST   host pointers (pageable or pinned); the call copies H2D/D2H on its stream and
+ *                       returns after the outputs are complete
+ *       TFIN_MEM_DEVICE device pointers on the handle's device; the call only enqueues work on `stream`
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream)
+ *   - operator/setup arrays passed to tfin_set_* are always HOST pointers and are copied
+ *   - there is no CPU fallback: every solve call fails if no sm_100 device is usable
+ */
+#ifndef TFIN_H
+#define TFIN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfin_ctx* tfin_handle_t;
+
+#define TFIN_MEM_HOST 0
+#define TFIN_MEM_DEVICE 1
+
+/* what the per-sample input rows of a solve call are */
+#define TFIN_IN_PARAMS 0 /* (N, n_terms-1) sub-domain conductivities theta            */
+#define TFIN_IN_NODAL 1  /* (N, n) nodal conductivity fields k                         */
+
+/* per-sample status */
+#define TFIN_STATUS_CONVERGED 0
+#define TFIN_STATUS_MAXIT 1     /* PCG hit maxit before reaching tol                    */
+#define TFIN_STATUS_BREAKDOWN 2 /* non-positive curvature / non-SPD pivot / NaN         */
+
+#define TFIN_MAX_TERMS 16
+
+int tfin_version(void);
+const char* tfin_last_error(void);
+
+/* Create / destroy a handle bound to CUDA device `device`. */
+int tfin_create(int device, tfin_handle_t* out);
+int tfin_destroy(tfin_handle_t h);
+
+/*
+ * Shared-pattern affine operator  A(theta) = vals[0] + sum_{q>=1} theta_q vals[q]  and right-hand side.
+ * Replaces the UFL forms + dolfin.assemble of AffineROMFin.__init__ / forward
+ * (rom/averaged_affine_ROM.py:156-163, 237-258) and of Fin.__init__ (fom/forward_solve.py:160-163):
+ * vals[0] = Bi*M_Gamma, vals[q] = stiffness over sub-domain q, rhs = int_root v.
+ *   row_ptr[n+1], col_idx[nnz] : CSR pattern (must contain the diagonal), vals[n_terms][nnz], rhs[n].
+ * prune_zeros != 0 drops off-diagonal entries that are exactly 0.0 in every term.
+ */
+int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const int32_t* row_ptr,
+                      const int32_t* col_idx, int32_t n_terms, const double* vals, const double* rhs,
+                      int32_t prune_zeros);
+
+/*
+ * Observation operator B_obs as CSR (n_obs rows over n dofs): Fin.qoi_operator / AffineROMFin.qoi
+ * (fom/forward_solve.py:408-412, 488-511; rom/averaged_affine_ROM.py:312-321).
+ */
+int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_t* ptr, const int32_t* idx,
+                         const double* val);
+
+/*
+ * Sub-fin averaging operator (n_terms-1 rows over n dofs) mapping a nodal field to theta:
+ * subfin_avg_op (fom/forward_solve.py:466-480, rom/averaged_affine_ROM.py:404-418).
+ * Needed for TFIN_IN_NODAL inputs of tfin_fom_affine / tfin_rom.
+ */
+int tfin_set_averaging(tfin_handle_t h, int32_t n_rows, const int32_t* ptr, const int32_t* idx,
+                       const double* val);
+
+/*
+ * Mesh cells + element stiffness matrices for the nodal-conductivity operator
+ * A(k) = sum_e mean(k on e) K_e + vals[0]  (Fin._F, fom/forward_solve.py:160-161).
+ *   cells[n_cells][3], Ke[n_cells][3][3].   Requires tfin_set_operator first (pattern, vals[0], rhs).
+ */
+int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* cells, const double* Ke,
+                   int32_t prune_zeros);
+
+/*
+ * Offline tensors of the LSPG reduced model (rom/averaged_affine_ROM.py:292-304, 212) for a basis phi
+ * (n x n_r), with Psi_t = vals[t] phi:
+ *   S[n_pairs][T]   n_pairs = n_terms(n_terms+1)/2 pairs (p<=q, p-major), T = n_r(n_r+1)/2 lower triangle
+ *                   row-major packed (i>=j -> i(i+1)/2+j);  S_pq = Psi_p^T Psi_q (+ transpose if p<q)
+ *   G[n_terms][n_r] G_t = Psi_t^T rhs
+ *   obs_phi[n_obs][n_r] = B_obs phi
+ */
+int tfin_set_rom(tfin_handle_t h, int32_t n_r, int32_t n_terms, int32_t n_obs, const double* S,
+                 const double* G, const double* obs_phi);
+
+/*
+ * Batched affine full-order solve A(theta_s) w_s = rhs by Jacobi-PCG, fused with qoi_s = B_obs w_s.
+ * = AffineROMFin.forward + qoi (rom/averaged_affine_ROM.py:237-258, 312-321) and forward_nine_param
+ * (rom/generate_reduced_basis_nine_param.py:178-183) for N samples.
+ *   in: (N, n_terms-1) if in_kind == TFIN_IN_PARAMS, (N, n) if TFIN_IN_NODAL
+ *   tol: stop when sqrt(r.z / r0.z0) <= tol;  maxit: iteration cap
+ *   w_out (N, n) | NULL, qoi_out (N, n_obs) | NULL, iters_out (N) | NULL, status_out (N) | NULL,
+ *   relres_out (N) | NULL: true relative residual ||b - A x|| / ||b|| recomputed after the last iteration
+ */
+int tfin_fom_affine(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int32_t mem,
+                    double tol, int32_t maxit, double* w_out, double* qoi_out, int32_t* iters_out,
+                    int32_t* status_out, double* relres_out, void* stream);
+
+/*
+ * Batched nodal-conductivity full-order solve (per-sample in-kernel assembly) fused with B_obs:
+ * = Fin.forward + qoi_operator (fom/forward_solve.py:270-291, 408-412) for N samples; k: (N, n).
+ */
+int tfin_fom_nodal(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double tol, int32_t maxit,
+                   double* w_out, double* qoi_out, int32_t* iters_out, int32_t* status_out,
+                   double* relres_out, void* stream);
+
+/*
+ * Batched LSPG reduced solve: A_r = sum_{p<=q} th_p th_q S_pq, B_r = sum_t th_t G_t (th_0 = 1),
+ * Cholesky solve, qoi = obs_phi w_r.
+ * = AffineROMFin.forward_reduced / forward_nine_param_reduced + qoi_reduced
+ * (rom/averaged_affine_ROM.py:260-310, 323-333) for N samples.
+ *   wr_out (N, n_r) | NULL, qoi_out (N, n_obs) | NULL, status_out (N) | NULL
+ */
+int tfin_rom(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int32_t mem, double* wr_out,
+             double* qoi_out, int32_t* status_out, void* stream);
+
+/* theta = averaging(k) for N nodal fields (subfin_avg_op batched); out (N, n_rows). */
+int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double* theta_out,
+                    void* stream);
+
+/* Number of CUDA kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t tfin_kernel_launches(tfin_handle_t h);
+
+/* Integer properties: "n", "n_obs", "n_terms", "n_r", "ell_width", "ell_width_nodal", "sm_count",
+ * "pcg_threads", "pcg_rows_per_thread", "pcg_ctas_per_sm", "pcg_smem_bytes"; returns -1 if unknown. */
+int64_t tfin_get_int(tfin_handle_t h, const char* key);
+
+/* Tuning knobs (before the next solve call): "pcg_rows_per_thread" (0 = auto), "rom_chunk" ...  */
+int tfin_set_int(tfin_handle_t h, const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFIN_H */

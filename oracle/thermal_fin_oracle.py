@@ -1,0 +1,286 @@
+"""CPU ORACLE -- test infrastructure, NOT product code.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs
+may import this module.  The product package (``bayesianinferencedl_b200``) never does.
+
+PARITY UNPINNED.  The reference (sheroze1123/BayesianInferenceDL) does all arithmetic of this path
+inside FEniCS 2018.1 / mshr / PETSc / LAPACK, none of which is installed or installable here, and it
+ships neither its mesh nor a single forward-solve output.  This file
+is a restatement, in numpy + scipy, of what those libraries compute at the reference's call sites; each
+function cites the reference lines it follows.  What CAN be pinned from the reference's shipped data
+(``data/B_obs.txt`` row sums, ``B_obs @ phi``, shapes/conditioning of the bases) is pinned in
+``tests/golden`` (see ``tests/golden/make_golden.py``).
+
+Deliberately written independently of ``bayesianinferencedl_b200/assembly.py`` (per-element gradient
+formulation, COO accumulation through scipy, loops over sub-domains) so that the two check each other.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+from scipy import spatial
+
+DOLFIN_EPS = 3.0e-16
+
+
+def between(x, lo, hi):
+    """dolfin ``between(x, (lo, hi))``: lo - eps <= x <= hi + eps."""
+    return (x >= lo - DOLFIN_EPS) and (x <= hi + DOLFIN_EPS)
+
+
+def near(x, a):
+    """dolfin ``near(x, a)``: |x - a| < eps."""
+    return abs(x - a) < DOLFIN_EPS
+
+
+# ------------------------------------------------------------------------------------------------
+# sub-domain predicates: fom/forward_solve.py:5-37 (duplicated in rom/averaged_affine_ROM.py:18-50)
+# ------------------------------------------------------------------------------------------------
+def subfin_inside(p, y_b, is_left):
+    """SubFin.inside, forward_solve.py:11-15."""
+    if is_left:
+        return between(p[1], y_b, y_b + 0.75) and between(p[0], 0.0, 2.5)
+    return between(p[1], y_b, y_b + 0.75) and between(p[0], 3.5, 6.0)
+
+
+def centerfin_inside(p):
+    """CenterFin.inside, forward_solve.py:31-33."""
+    return between(p[0], 2.5, 3.5)
+
+
+# order of fin1..fin9, forward_solve.py:125-133
+SUBDOMAINS = [(0.75, True), (1.75, True), (2.75, True), (3.75, True), None,
+              (3.75, False), (2.75, False), (1.75, False), (0.75, False)]
+
+
+def inside(q, p):
+    d = SUBDOMAINS[q - 1]
+    return centerfin_inside(p) if d is None else subfin_inside(p, d[0], d[1])
+
+
+def mark_cells(coords, cells):
+    """``finq.mark(domains, q)`` for q = 1..9 in order (forward_solve.py:134-144): a cell gets q iff all
+    vertices and the midpoint are inside; later ids overwrite; unmatched cells keep 0."""
+    out = np.zeros(len(cells), dtype=np.int64)
+    for e, tri in enumerate(cells):
+        pts = [coords[v] for v in tri] + [coords[tri].mean(axis=0)]
+        for q in range(1, 10):
+            if all(inside(q, p) for p in pts):
+                out[e] = q
+    return out
+
+
+def exterior_facets(cells):
+    """Facets (edges) with exactly one adjacent cell -- what dolfin's ``on_boundary`` / ``ds`` see."""
+    count = {}
+    for tri in cells:
+        for a, b in ((0, 1), (1, 2), (2, 0)):
+            k = (min(tri[a], tri[b]), max(tri[a], tri[b]))
+            count[k] = count.get(k, 0) + 1
+    return sorted(k for k, c in count.items() if c == 1)
+
+
+def mark_facets(coords, cells):
+    """forward_solve.py:147-152: exterior = "!near(x[1],0) && on_boundary" -> 1, bottom = "near(x[1],0)
+    && on_boundary" -> 2, both tested on the two vertices and the midpoint.  Returns (robin, root) lists.
+    The per-sub-domain split of averaged_affine_ROM.py:116-138 has the same union (appendix A.1)."""
+    robin, root = [], []
+    for (a, b) in exterior_facets(cells):
+        ys = [coords[a][1], coords[b][1], 0.5 * (coords[a][1] + coords[b][1])]
+        if all(not near(y, 0.0) for y in ys):
+            robin.append((a, b))
+        elif all(near(y, 0.0) for y in ys):
+            root.append((a, b))
+    return robin, root
+
+
+# ------------------------------------------------------------------------------------------------
+# P1 assembly (what dolfin.assemble produces for the forms of forward_solve.py:160-163)
+# ------------------------------------------------------------------------------------------------
+class FinOracle:
+    """Restatement of ``Fin`` (fom/forward_solve.py:93-265) + ``AffineROMFin`` forward map
+    (rom/averaged_affine_ROM.py:52-333) on a given triangle mesh."""
+
+    Bi = 0.1   # forward_solve.py:112
+
+    def __init__(self, coords, cells):
+        self.coords = np.asarray(coords, dtype=np.float64)
+        self.cells = np.asarray(cells, dtype=np.int64)
+        self.n = len(self.coords)
+        nc = len(self.cells)
+        # gradients of the barycentric basis: G = inv([[1,x0,y0],[1,x1,y1],[1,x2,y2]])[1:, :]
+        P = np.ones((nc, 3, 3))
+        P[:, :, 1:] = self.coords[self.cells]
+        Pinv = np.linalg.inv(P)
+        grads = Pinv[:, 1:, :]                          # (nc, 2, 3): d phi_a / d(x,y)
+        self.area = 0.5 * np.abs(np.linalg.det(P))
+        self.Ke = np.einsum("eda,edb->eab", grads, grads) * self.area[:, None, None]
+        self.markers = mark_cells(self.coords, self.cells)
+        self.robin, self.root = mark_facets(self.coords, self.cells)
+
+        # Bi * int_{exterior} w v ds   (forward_solve.py:161)
+        rows, cols, vals = [], [], []
+        for a, b in self.robin:
+            L = np.linalg.norm(self.coords[a] - self.coords[b])
+            rows += [a, b, a, b]
+            cols += [a, b, b, a]
+            vals += [L / 3.0, L / 3.0, L / 6.0, L / 6.0]
+        self.M_robin = sp.coo_matrix((vals, (rows, cols)), shape=(self.n, self.n)).tocsr()
+
+        # B = assemble(v * ds(2))   (forward_solve.py:162-163)
+        self.B = np.zeros(self.n)
+        for a, b in self.root:
+            L = np.linalg.norm(self.coords[a] - self.coords[b])
+            self.B[a] += 0.5 * L
+            self.B[b] += 0.5 * L
+
+        # K_q = assemble(inner(grad w, grad v) * dx(q))   (averaged_affine_ROM.py:156-162, 217)
+        self.K_q = [self._stiffness(np.where(self.markers == q, 1.0, 0.0)) for q in range(1, 10)]
+
+        # sub-fin areas and B_obs   (forward_solve.py:205-213, 488-511)
+        self.fin_area = np.array([self.area[self.markers == q].sum() for q in range(1, 10)])
+        self.B_obs = np.zeros((9, self.n))
+        for e, tri in enumerate(self.cells):
+            q = self.markers[e]
+            if q > 0:
+                for v in tri:
+                    self.B_obs[q - 1, v] += self.area[e] / 3.0
+        self.B_obs /= self.fin_area[:, None]
+        self.n_obs = 9
+
+        # averaging operator C   (forward_solve.py:396-406)
+        self.domain_measure = self.area.sum()
+        self.C = np.zeros(self.n)
+        for e, tri in enumerate(self.cells):
+            for v in tri:
+                self.C[v] += self.area[e] / 3.0
+        self.C /= self.domain_measure
+
+    def _stiffness(self, cell_coeff):
+        """sum_e cell_coeff[e] * K_e as CSR."""
+        r = np.repeat(self.cells, 3, axis=1).ravel()
+        c = np.tile(self.cells, (1, 3)).ravel()
+        v = (self.Ke * cell_coeff[:, None, None]).ravel()
+        return sp.coo_matrix((v, (r, c)), shape=(self.n, self.n)).tocsr()
+
+    # ---------------- full-order models ----------------
+    def matrix_nodal(self, k):
+        """A(k) of ``Fin._F`` (forward_solve.py:160-161) for a P1 conductivity with nodal values k:
+        int k grad w . grad v over a cell = mean(k at the 3 vertices) * K_e exactly."""
+        kbar = np.asarray(k, dtype=np.float64)[self.cells].mean(axis=1)
+        return (self._stiffness(kbar) + self.Bi * self.M_robin).tocsc()
+
+    def forward(self, k):
+        """``Fin.forward(k)`` (forward_solve.py:270-291): dolfin ``solve`` = sparse direct LU."""
+        return spla.splu(self.matrix_nodal(k)).solve(self.B)
+
+    def matrix_affine(self, theta):
+        """A(theta) of ``AffineROMFin._F`` (averaged_affine_ROM.py:156-162)."""
+        A = self.Bi * self.M_robin
+        for q in range(9):
+            A = A + float(theta[q]) * self.K_q[q]
+        return A.tocsc()
+
+    def forward_nine_param(self, theta):
+        """``forward_nine_param(k_s)`` (generate_reduced_basis_nine_param.py:178-183)."""
+        return spla.splu(self.matrix_affine(theta)).solve(self.B)
+
+    def forward_affine(self, k):
+        """``AffineROMFin.forward(k)`` (averaged_affine_ROM.py:237-258)."""
+        return self.forward_nine_param(self.subfin_avg_op(k))
+
+    def forward_five_param_affine(self, k5):
+        return self.forward_nine_param(five_param_to_nine(k5))
+
+    # ---------------- observation ----------------
+    def subfin_avg_op(self, k):
+        """forward_solve.py:466-480 / averaged_affine_ROM.py:404-418: assemble(k*dx(q))/area_q."""
+        return self.B_obs @ np.asarray(k, dtype=np.float64)
+
+    def qoi_operator(self, w):
+        """forward_solve.py:408-412."""
+        return np.dot(self.B_obs, w)
+
+    def nine_param_to_function(self, theta):
+        """interpolate(SubfinValExpr(k_s)) (forward_solve.py:61-91, 482-486), evaluated per vertex."""
+        k1, k2, k3, k4, k5, k6, k7, k8, k9 = [float(t) for t in theta]
+        out = np.zeros(self.n)
+        for i, (x, y) in enumerate(self.coords):
+            if between(x, 2.5, 3.5):
+                v = k5
+            elif x <= 2.5:
+                v = (k1 if between(y, 0.75, 1.0) else k2 if between(y, 1.75, 2.0) else
+                     k3 if between(y, 2.75, 3.0) else k4 if between(y, 3.75, 4.0) else 0.0)
+            else:
+                v = (k9 if between(y, 0.75, 1.0) else k8 if between(y, 1.75, 2.0) else
+                     k7 if between(y, 2.75, 3.0) else k6 if between(y, 3.75, 4.0) else 0.0)
+            out[i] = v
+        return out
+
+    # ---------------- reduced-order model (LSPG) ----------------
+    def forward_nine_param_reduced(self, theta, phi):
+        """averaged_affine_ROM.py:278-310, literally: psi = A phi; A_r = psi^T psi; B_r = psi^T B;
+        w_r = np.linalg.solve(A_r, B_r)."""
+        A = self.matrix_affine(theta).tocsr()
+        psi = A @ phi
+        A_r = psi.T @ psi
+        B_r = psi.T @ self.B
+        return np.linalg.solve(A_r, B_r)
+
+    def forward_reduced(self, k, phi):
+        """averaged_affine_ROM.py:260-276."""
+        return self.forward_nine_param_reduced(self.subfin_avg_op(k), phi)
+
+    def qoi_reduced(self, w_r, phi):
+        """averaged_affine_ROM.py:212, 323-333: (B_obs phi) w_r."""
+        return np.dot(np.dot(self.B_obs, phi), w_r)
+
+    def r_fwd_no_full(self, k, phi):
+        """forward_solve.py:421-464 (nodal-conductivity LSPG with the legacy scalar QoI C)."""
+        A = self.matrix_nodal(k).tocsr()
+        psi = A @ phi
+        A_r = psi.T @ (A @ phi)
+        B_r = psi.T @ self.B
+        C_r = self.C @ phi
+        x_r = np.linalg.solve(A_r, B_r)
+        return A_r, B_r, C_r, x_r, float(C_r @ x_r)
+
+
+def five_param_to_nine(k5):
+    """forward_solve_petsc.py:243-260: k1..k4 are the y-bands 0.75/1.75/2.75/3.75 on BOTH sides, k5 the
+    post.  In the numbering of forward_solve.py:125-133 (right fins counted top-down) this is
+    [k1,k2,k3,k4,k5,k4,k3,k2,k1]."""
+    k1, k2, k3, k4, k5 = [float(v) for v in k5]
+    return np.array([k1, k2, k3, k4, k5, k4, k3, k2, k1])
+
+
+def make_cov_chol(coords, kern_type="m52", length=1.6):
+    """bayesian_inference/gaussian_field.py:9-31 on the dof coordinates."""
+    d = spatial.distance.squareform(spatial.distance.pdist(np.asarray(coords)))
+    if kern_type == "sq_exp":
+        cov = np.exp(-d ** 2 / (2 * length ** 2)) + np.eye(len(d)) * 1e-5
+    elif kern_type == "m52":
+        t = np.sqrt(5) * d / length
+        cov = (1 + t + t * t / 3) * np.exp(-t)
+    else:
+        t = np.sqrt(3) * d / length
+        cov = (1 + t) * np.exp(-t)
+    return sla.cholesky(cov)
+
+
+def sample_field(chol, z):
+    """deep_learning/generate_fin_dataset.py:87-88: nodal_vals = exp(0.5 * chol.T @ norm)."""
+    return np.exp(0.5 * chol.T @ z)
+
+
+def pod_basis(oracle: FinOracle, n_snapshots=200, basis_size=81, seed=0, lo=0.1, hi=3.5):
+    """POD recipe of rom/generate_reduced_basis_nine_param.py:296-318 (commented script that produced
+    data/basis_nine_param.txt): snapshots of forward_nine_param at k ~ U(0.1, 3.5)^9, eigenvectors of
+    Y Y^T, UNNORMALISED modes U_i = sum_s v[s,i] Y[s,:].  (eigh + descending sort instead of eig.)"""
+    rng = np.random.default_rng(seed)
+    Y = np.stack([oracle.forward_nine_param(rng.uniform(lo, hi, 9)) for _ in range(n_snapshots)])
+    e, v = np.linalg.eigh(Y @ Y.T)
+    order = np.argsort(e)[::-1][:basis_size]
+    return (v[:, order].T @ Y).T

@@ -1,0 +1,182 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): observables agree to 1e-10 relative in fp64; sample indexing bit-exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+RTOL_FOM = 1e-10
+RTOL_ROM = 1e-10
+
+
+@pytest.fixture(scope="module")
+def rom_m3(space_m3, pod_m3):
+    from bayesianinferencedl_b200 import AffineROMFin
+    return AffineROMFin(space_m3, None, pod_m3)
+
+
+@pytest.fixture(scope="module")
+def fin_m3(space_m3):
+    from bayesianinferencedl_b200 import Fin
+    return Fin(space_m3)
+
+
+def test_config1_five_param_single(rom_m3, oracle_m3, pod_m3):
+    """BASELINE config 1: z_true of bayesian_inference/muq_old/bayes_inv.py:29, single FOM + ROM solve."""
+    from oracle.thermal_fin_oracle import five_param_to_nine
+    z = [0.41126864, 0.61789679, 0.75873243, 0.96527541, 0.22348076]
+    w = rom_m3.forward_five_param(z)
+    w_ref = oracle_m3.forward_nine_param(five_param_to_nine(z))
+    assert w.shape == (oracle_m3.n,)
+    assert np.max(np.abs(w - w_ref)) <= 1e-10 * np.max(np.abs(w_ref))
+    q = rom_m3.qoi(w)
+    assert relerr(q, oracle_m3.qoi_operator(w_ref)) <= RTOL_FOM
+    # mirror symmetry of the five-parameter problem
+    assert np.allclose(q[:4], q[:4:-1], rtol=1e-9)
+    theta = five_param_to_nine(z)
+    w_r = rom_m3.forward_nine_param_reduced(theta)
+    q_r = rom_m3.qoi_reduced(w_r)
+    q_r_ref = oracle_m3.qoi_reduced(oracle_m3.forward_nine_param_reduced(theta, pod_m3), pod_m3)
+    assert relerr(q_r, q_r_ref) <= RTOL_ROM
+
+
+def test_affine_fom_batch_vs_oracle(rom_m3, oracle_m3):
+    rng = np.random.default_rng(11)
+    theta = rng.uniform(0.1, 3.5, (24, 9))
+    q, stats = rom_m3.forward_nine_param_qoi(theta, return_stats=True)
+    assert np.all(stats["status"] == 0)
+    assert np.all(stats["relres"] < 1e-10)
+    assert 200 < stats["iters"].mean() < 1000
+    for s in range(len(theta)):
+        ref = oracle_m3.qoi_operator(oracle_m3.forward_nine_param(theta[s]))
+        assert relerr(q[s], ref) <= RTOL_FOM, s
+    w = rom_m3.forward_nine_param(theta[:3])
+    for s in range(3):
+        w_ref = oracle_m3.forward_nine_param(theta[s])
+        assert np.max(np.abs(w[s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref))
+
+
+def test_affine_fom_nodal_input(rom_m3, oracle_m3):
+    rng = np.random.default_rng(12)
+    k = np.exp(0.4 * rng.standard_normal((5, oracle_m3.n)))
+    w = rom_m3.forward(k)
+    th = rom_m3.subfin_avg_op(k)
+    for s in range(5):
+        assert relerr(th[s], oracle_m3.subfin_avg_op(k[s])) <= 1e-13
+        w_ref = oracle_m3.forward_affine(k[s])
+        assert np.max(np.abs(w[s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref))
+
+
+def test_nodal_fom_vs_oracle(fin_m3, oracle_m3, space_m3):
+    """Fin.forward: per-sample in-kernel assembly (K2) vs oracle assembly + sparse LU, Matern fields."""
+    from bayesianinferencedl_b200 import make_cov_chol, sample_fields
+    chol = make_cov_chol(space_m3, length=1.6)
+    rng = np.random.default_rng(3)
+    k = sample_fields(chol, rng.standard_normal((6, fin_m3.dofs)))
+    q, stats = fin_m3.forward_qoi(k, return_stats=True)
+    assert np.all(stats["status"] == 0)
+    w, *rest = fin_m3.forward(k)
+    assert rest == [None, None, None, None]
+    for s in range(len(k)):
+        w_ref = oracle_m3.forward(k[s])
+        assert np.max(np.abs(w[s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref)), s
+        assert relerr(q[s], oracle_m3.qoi_operator(w_ref)) <= RTOL_FOM, s
+    # odd and even row starts both exercise the TMA staging (n = 1597 is odd)
+    q1 = fin_m3.forward_qoi(k[1])
+    assert np.array_equal(q1, q[1])
+
+
+def test_nine_param_function_path(fin_m3, oracle_m3):
+    """SURVEY Q-2: Fin.forward(nine_param_to_function(theta)) (F1) differs from the affine F2 but must match
+    the oracle's F1."""
+    theta = np.array([0.5, 1.0, 1.5, 2.0, 2.5, 3.0, 0.3, 0.8, 1.2])
+    k = fin_m3.nine_param_to_function(theta)
+    assert np.array_equal(np.asarray(k), oracle_m3.nine_param_to_function(theta))
+    w = fin_m3.forward(k)[0]
+    w_ref = oracle_m3.forward(oracle_m3.nine_param_to_function(theta))
+    assert np.max(np.abs(w - w_ref)) <= 1e-10 * np.max(np.abs(w_ref))
+
+
+def test_rom_batch_vs_oracle(rom_m3, oracle_m3, pod_m3):
+    rng = np.random.default_rng(0)
+    theta = rng.uniform(0.1, 3.5, (40, 9))
+    q = rom_m3.forward_reduced_qoi(theta)
+    w_r = rom_m3.forward_nine_param_reduced(theta)
+    for s in range(len(theta)):
+        wr_ref = oracle_m3.forward_nine_param_reduced(theta[s], pod_m3)
+        q_ref = oracle_m3.qoi_reduced(wr_ref, pod_m3)
+        assert relerr(q[s], q_ref) <= RTOL_ROM, s
+        # w_r is basis dependent and ill-scaled: compare the lifted field
+        lift, lift_ref = pod_m3 @ w_r[s], pod_m3 @ wr_ref
+        assert np.max(np.abs(lift - lift_ref)) <= 1e-9 * np.max(np.abs(lift_ref)), s
+    assert relerr(rom_m3.qoi_reduced(w_r), q) <= 1e-12
+
+
+def test_rom_nodal_input(rom_m3, oracle_m3, pod_m3):
+    rng = np.random.default_rng(5)
+    k = np.exp(0.4 * rng.standard_normal((3, oracle_m3.n)))
+    w_r = rom_m3.forward_reduced(k)
+    for s in range(3):
+        q_ref = oracle_m3.qoi_reduced(oracle_m3.forward_reduced(k[s], pod_m3), pod_m3)
+        assert relerr(rom_m3.qoi_reduced(w_r[s]), q_ref) <= RTOL_ROM
+
+
+def test_sample_order_and_determinism(rom_m3):
+    """Sample indexing is bit-exact: a permuted batch gives the permuted result, run to run."""
+    rng = np.random.default_rng(7)
+    theta = rng.uniform(0.1, 3.5, (600, 9))
+    q1 = rom_m3.forward_nine_param_qoi(theta)
+    perm = rng.permutation(len(theta))
+    q2 = rom_m3.forward_nine_param_qoi(theta[perm])
+    assert np.array_equal(q1[perm], q2)
+    r1 = rom_m3.forward_reduced_qoi(theta)
+    r2 = rom_m3.forward_reduced_qoi(theta[perm])
+    assert np.array_equal(r1[perm], r2)
+
+
+def test_energy_balance_large_batch(rom_m3, oracle_m3):
+    """Size-independent property at batch scale: Bi * 1^T M_Gamma w = |Gamma_root| = 1 for every sample."""
+    rng = np.random.default_rng(8)
+    theta = rng.uniform(0.1, 10.0, (2000, 9))
+    w = rom_m3.forward_nine_param(theta)
+    flux = oracle_m3.Bi * (oracle_m3.M_robin @ w.T).sum(axis=0)
+    assert np.max(np.abs(flux - 1.0)) < 1e-10
+
+
+def test_edge_cases(rom_m3, fin_m3):
+    assert rom_m3.forward_nine_param_qoi(np.zeros((0, 9))).shape == (0, 9)
+    assert rom_m3.forward_reduced_qoi(np.zeros((0, 9))).shape == (0, 9)
+    with pytest.raises(ValueError):
+        rom_m3.forward_nine_param(np.ones(8))
+    with pytest.raises(ValueError):
+        fin_m3.forward(np.ones(fin_m3.dofs + 1))
+    with pytest.raises(RuntimeError):
+        rom_m3.forward_nine_param(-np.ones(9))       # not SPD -> breakdown reported, not silently wrong
+    # maxit cap is reported per sample
+    out = rom_m3.handle.fom_affine(np.ones((2, 9)), maxit=5)
+    assert np.all(out["status"] == 1) and np.all(out["iters"] == 5)
+
+
+@pytest.mark.parametrize("m", [1, 2])
+def test_other_mesh_sizes(m, request):
+    from bayesianinferencedl_b200 import AffineROMFin, Fin
+    V = request.getfixturevalue(f"space_m{m}")
+    orc = request.getfixturevalue(f"oracle_m{m}")
+    rng = np.random.default_rng(20 + m)
+    phi = np.linalg.qr(rng.standard_normal((orc.n, 12)))[0]
+    rom = AffineROMFin(V, None, phi)
+    theta = rng.uniform(0.1, 3.5, (7, 9))
+    q = rom.forward_nine_param_qoi(theta)
+    qr = rom.forward_reduced_qoi(theta)
+    fin = Fin(V)
+    k = np.exp(0.3 * rng.standard_normal((3, orc.n)))
+    qn = fin.forward_qoi(k)
+    for s in range(7):
+        assert relerr(q[s], orc.qoi_operator(orc.forward_nine_param(theta[s]))) <= RTOL_FOM
+        assert relerr(qr[s], orc.qoi_reduced(orc.forward_nine_param_reduced(theta[s], phi), phi)) <= 1e-8
+    for s in range(3):
+        assert relerr(qn[s], orc.qoi_operator(orc.forward(k[s]))) <= RTOL_FOM
