@@ -1,37 +1,36 @@
-// K1 / K2: batched Jacobi-PCG for meshes whose CG state fits one SM (n <~ 4k dofs).
+// K1 / K2: batched Jacobi-PCG for meshes whose CG state fits one SM (n <= 8191 dofs).
 //
 // One persistent CTA per resident slot; each CTA pulls samples from a global counter and solves
 //     A(sample) w = b,   qoi = B_obs w
 // entirely on chip:
-//   * the shared ELL sparsity pattern (uint16 columns) is loaded to shared memory ONCE per CTA
-//   * per sample the ELL values are formed in shared memory, either from the affine terms
+//   * the per-sample operator is formed in-kernel, either from the affine terms
 //       vals = sum_t theta_t V_t                       (K1, AffineROMFin._F, averaged_affine_ROM.py:156-162)
-//     or by in-kernel element assembly from the nodal field staged with a TMA bulk copy
+//     or by element assembly from the nodal field, staged in shared memory by a TMA bulk copy,
 //       vals = sum_e mean(k|e) K_e + Bi M              (K2, Fin._F, forward_solve.py:160-161)
-//   * thread t owns rows t, t+T, ..., t+(R-1)T: x, r, p, q, 1/diag live in registers, only the
-//     preconditioned residual z is published to shared memory for the SpMV gather
-//   * Chronopoulos-Gear PCG: ONE fused block reduction (r.z, z.Az) and two barriers per iteration
+//   * Jacobi preconditioning is applied as a symmetric diagonal scaling  A~ = D^-1/2 A D^-1/2  done once per
+//     sample, so the iteration is plain CG on a unit-diagonal matrix (identical iterates to Jacobi-PCG in
+//     exact arithmetic, no 1/diag multiply and no z vector in the loop)
+//   * thread t owns rows t, t+T, ..., t+(R-1)T: x, r, p, q live in registers; the packed ELL column offsets live
+//     in registers; the first WR off-diagonal values per row live in registers, the rest in shared memory; only
+//     the residual r is published to shared memory for the SpMV gather
+//   * Chronopoulos-Gear CG: ONE fused block reduction (r.r, r.Ar) and two barriers per iteration
 //   * epilogue: true residual, B_obs projection (warp per observation row), optional w write-back
 //
-// Results are independent of which CTA solves a sample (fixed reduction order), so sample indexing is
-// bit-reproducible for a given launch geometry.
+// Results do not depend on which CTA solves a sample (fixed reduction order) => bit-reproducible indexing.
 #pragma once
 
 #include "common.cuh"
 
 namespace tfin {
 
-struct EllAffine {
-    int n, ld, W, n_terms;
+struct PcgOp {
+    int n, ld, W, n_terms, n_cells;
     const uint16_t* col;  // [W][ld]   off-diagonal columns (padding: col = row, val = 0)
+    const double* rhs;    // [ld]
+    // affine (K1)
     const double* val;    // [n_terms][W][ld]
     const double* diag;   // [n_terms][ld]
-    const double* rhs;    // [ld]
-};
-
-struct EllNodal {
-    int n, ld, W, n_cells;
-    const uint16_t* col;  // [W][ld]
+    // nodal (K2)
     const int* cell;      // [2][W][ld]   the (<=2) cells sharing edge (row, col); n_cells = none
     const double* coef;   // [2][W][ld]   K_e[a][b] of that cell for this entry
     const double* cst;    // [W][ld]      constant (Robin) part
@@ -40,7 +39,6 @@ struct EllNodal {
     const double* dcoef;  // [dnnz]
     const double* dcst;   // [ld]
     const int* cells;     // [n_cells][3]
-    const double* rhs;    // [ld]
 };
 
 struct CsrRows {
@@ -66,266 +64,81 @@ struct PcgIO {
 
 // Shared-memory carve-up shared by host (size) and device (pointers).
 struct PcgSmem {
-    size_t val_off, z_off, part_off, misc_off, col_off, kbar_off, kbuf_off, total;
-    __host__ __device__ static PcgSmem make(int W, int np, int n_cells /*0 = affine*/, int n) {
+    size_t r_off, part_off, misc_off, dsi_off, kbar_off, kbuf_off, val_off, total;
+    __host__ __device__ static PcgSmem make(int w_smem, int np, int n_cells /*0 = affine*/, int n) {
         PcgSmem s;
         size_t o = 0;
-        s.val_off = o;  o += (size_t)W * np * sizeof(double);
-        s.z_off = o;    o += (size_t)np * sizeof(double);
-        s.part_off = o; o += 4 * 32 * sizeof(double);  // two regions of 32 double2 partials
+        s.r_off = o;    o += (size_t)np * sizeof(double);
+        s.part_off = o; o += 64 * sizeof(double);
         s.misc_off = o; o += 32 * sizeof(double);      // theta[16] | next sample | mbarrier
+        s.dsi_off = o;  o += (size_t)np * sizeof(double);
         s.kbar_off = o; o += n_cells ? (((size_t)n_cells + 2 + 1) & ~size_t(1)) * sizeof(double) : 0;
         s.kbuf_off = o; o += n_cells ? (((size_t)n + 4 + 1) & ~size_t(1)) * sizeof(double) : 0;
-        s.col_off = o;  o += (size_t)W * np * sizeof(uint16_t);
+        s.val_off = o;  o += (size_t)w_smem * np * sizeof(double);
         s.total = (o + 15) & ~size_t(15);
         return s;
     }
 };
 
+// Block-wide sums of two values with one barrier.  Stage 1 folds both values through ONE 5-step butterfly
+// (lower half-warp accumulates a, upper half b); stage 2 re-reduces the per-warp partials lane-parallel.
+// Every thread returns bit-identical totals.  s_part: 64 doubles.
 __device__ __forceinline__ void block_sum2(double& a, double& b, double* s_part, int lane, int warp,
                                            int nwarps) {
-    a = warp_sum(a);
-    b = warp_sum(b);
-    if (lane == 0) reinterpret_cast<double2*>(s_part)[warp] = make_double2(a, b);
+    const bool hi = lane >= 16;
+    const double send = hi ? a : b;
+    double keep = hi ? b : a;
+    keep += __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    double* base = s_part + (hi ? 32 : 0);
+    if ((lane & 15) == 0) base[warp] = keep;
     __syncthreads();
-    double sa = 0.0, sb = 0.0;
-    for (int w = 0; w < nwarps; ++w) {
-        const double2 v = reinterpret_cast<const double2*>(s_part)[w];
-        sa += v.x;
-        sb += v.y;
-    }
-    a = sa;
-    b = sb;
+    const int l = lane & 15;
+    double v = (l < nwarps ? base[l] : 0.0) + (l + 16 < nwarps ? base[l + 16] : 0.0);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    a = __shfl_sync(0xffffffffu, v, 0);
+    b = __shfl_sync(0xffffffffu, v, 16);
 }
 
-// The CG core.  On entry: s_val (this thread's rows) and dg[] (diagonal) are set, bvec[] = rhs rows.
-// On exit x[] holds the solution rows of this thread; returns iterations, sets status.
-template <int R>
-__device__ __forceinline__ int cg_core(const double* __restrict__ s_val, const uint16_t* __restrict__ s_col,
-                                       double* __restrict__ s_z, double* __restrict__ s_part, int W,
-                                       int np, int T, int tid, const double (&dg)[R],
-                                       const double (&bvec)[R], double tol2, int maxit, double (&x)[R],
-                                       int& status) {
-    const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-    double dinv[R], r[R], p[R], q[R], z[R], s[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-        dinv[k] = 1.0 / dg[k];
-        x[k] = 0.0;
-        r[k] = bvec[k];
-        z[k] = dinv[k] * r[k];
-        s_z[tid + k * T] = z[k];
-    }
-    __syncthreads();
-
-    auto spmv = [&](double& lg, double& ld) {
-#pragma unroll
-        for (int k = 0; k < R; ++k) s[k] = dg[k] * z[k];
-        for (int w = 0; w < W; ++w) {
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-                const int o = w * np + tid + k * T;
-                s[k] = fma(s_val[o], s_z[s_col[o]], s[k]);
-            }
-        }
-        lg = 0.0;
-        ld = 0.0;
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            lg = fma(r[k], z[k], lg);
-            ld = fma(z[k], s[k], ld);
-        }
-    };
-
-    double gam, del;
-    spmv(gam, del);
-    block_sum2(gam, del, s_part, lane, warp, nwarps);
-    status = TFIN_STATUS_MAXIT;
-    if (!(gam > 0.0) || !(del > 0.0)) {  // b == 0 (x = 0 is exact) or not SPD
-        status = (gam == 0.0) ? TFIN_STATUS_CONVERGED : TFIN_STATUS_BREAKDOWN;
-        return 0;
-    }
-    const double thresh = tol2 * gam;
-    double alpha = gam / del, denom = del;
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-        p[k] = z[k];
-        q[k] = s[k];
-    }
-    int it = 0;
-    while (it < maxit) {
-        ++it;
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            x[k] = fma(alpha, p[k], x[k]);
-            r[k] = fma(-alpha, q[k], r[k]);
-            z[k] = dinv[k] * r[k];
-            s_z[tid + k * T] = z[k];
-        }
-        __syncthreads();  // z visible; everyone is done reading s_part of the previous iteration
-        double gn, dl;
-        spmv(gn, dl);
-        block_sum2(gn, dl, s_part, lane, warp, nwarps);  // barrier inside: all gathers of z done
-        if (gn <= thresh) {
-            status = TFIN_STATUS_CONVERGED;
-            break;
-        }
-        const double beta = gn / gam;
-        denom = dl - beta * beta * denom;  // = dl - beta * gn / alpha_old
-        if (!(denom > 0.0) || !(gn == gn)) {
-            status = TFIN_STATUS_BREAKDOWN;
-            break;
-        }
-        alpha = gn / denom;
-        gam = gn;
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            p[k] = fma(beta, p[k], z[k]);
-            q[k] = fma(beta, q[k], s[k]);
-        }
-    }
-    return it;
-}
-
-// Epilogue shared by K1/K2: publish x, true residual, observation projection, outputs.
-template <int R>
-__device__ __forceinline__ void pcg_epilogue(const double* s_val, const uint16_t* s_col, double* s_z,
-                                             double* s_part, int W, int np, int T, int tid, int n,
-                                             const double (&dg)[R], const double (&bvec)[R],
-                                             const double (&x)[R], const CsrRows& obs, const PcgIO& io,
-                                             long long sample, int iters, int status) {
-    const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-    __syncthreads();  // all SpMV gathers of the last iteration are complete
-#pragma unroll
-    for (int k = 0; k < R; ++k) s_z[tid + k * T] = x[k];
-    __syncthreads();
-    if (io.relres_out || io.status_out) {
-        double rr = 0.0, bb = 0.0;
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            double ax = dg[k] * x[k];
-            for (int w = 0; w < W; ++w) {
-                const int o = w * np + tid + k * T;
-                ax = fma(s_val[o], s_z[s_col[o]], ax);
-            }
-            const double t = bvec[k] - ax;
-            rr = fma(t, t, rr);
-            bb = fma(bvec[k], bvec[k], bb);
-        }
-        block_sum2(rr, bb, s_part + 64, lane, warp, nwarps);
-        const double relres = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
-        if (!(relres == relres)) status = TFIN_STATUS_BREAKDOWN;
-        if (tid == 0 && io.relres_out) io.relres_out[sample] = relres;
-    }
-    if (tid == 0) {
-        if (io.iters_out) io.iters_out[sample] = iters;
-        if (io.status_out) io.status_out[sample] = status;
-    }
-    if (io.qoi_out) {
-        for (int o = warp; o < obs.rows; o += nwarps) {
-            double acc = 0.0;
-            for (int j = obs.ptr[o] + lane; j < obs.ptr[o + 1]; j += 32)
-                acc = fma(obs.val[j], s_z[obs.idx[j]], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) io.qoi_out[sample * obs.rows + o] = acc;
-        }
-    }
-    if (io.w_out) {
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const int i = tid + k * T;
-            if (i < n) io.w_out[sample * (long long)n + i] = x[k];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------- K1
-template <int R, int MAXT>
-__global__ void __launch_bounds__(MAXT) pcg_affine_kernel(EllAffine op, CsrRows obs, PcgIO io) {
+// R rows per thread, WT padded ELL width (even), WR of the WT off-diagonal values per row in registers.
+template <int R, int WT, int WR, bool NODAL, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, PcgIO io) {
+    static_assert(WT % 2 == 0 && WR <= WT, "bad ELL template widths");
+    constexpr int WS = WT - WR;  // slots whose values live in shared memory
     extern __shared__ __align__(16) unsigned char smem[];
-    const int T = blockDim.x, tid = threadIdx.x;
-    const int np = R * T, W = op.W, n = op.n, ld = op.ld;
-    const PcgSmem L = PcgSmem::make(W, np, 0, n);
-    double* s_val = reinterpret_cast<double*>(smem + L.val_off);
-    double* s_z = reinterpret_cast<double*>(smem + L.z_off);
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int np = R * T, W = op.W, n = op.n, ld = op.ld, nc = NODAL ? op.n_cells : 0;
+    const PcgSmem L = PcgSmem::make(WS, np, nc, n);
+    double* s_r = reinterpret_cast<double*>(smem + L.r_off);
     double* s_part = reinterpret_cast<double*>(smem + L.part_off);
     double* s_theta = reinterpret_cast<double*>(smem + L.misc_off);
     long long* s_next = reinterpret_cast<long long*>(smem + L.misc_off) + 16;
-    uint16_t* s_col = reinterpret_cast<uint16_t*>(smem + L.col_off);
-
-    double bvec[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-        const int i = tid + k * T;
-        bvec[k] = i < n ? op.rhs[i] : 0.0;
-        for (int w = 0; w < W; ++w) s_col[w * np + i] = i < n ? op.col[w * ld + i] : (uint16_t)i;
-    }
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) *s_next = (long long)atomicAdd(io.counter, 1ULL);
-        __syncthreads();
-        const long long sample = *s_next;
-        if (sample >= io.N) break;
-        if (tid < op.n_terms)
-            s_theta[tid] = tid == 0 ? 1.0 : io.in[sample * io.in_stride + tid - 1];
-        __syncthreads();
-
-        // ---- per-sample operator: vals = sum_t theta_t V_t (thread-private rows, no barrier needed)
-        double dg[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const int i = tid + k * T;
-            double d = 0.0;
-            if (i < n)
-                for (int t = 0; t < op.n_terms; ++t) d = fma(s_theta[t], op.diag[t * ld + i], d);
-            dg[k] = i < n ? d : 1.0;
-        }
-        for (int w = 0; w < W; ++w) {
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-                const int i = tid + k * T;
-                double v = 0.0;
-                if (i < n)
-                    for (int t = 0; t < op.n_terms; ++t)
-                        v = fma(s_theta[t], op.val[((size_t)t * W + w) * ld + i], v);
-                s_val[w * np + i] = v;
-            }
-        }
-
-        double x[R];
-        int status;
-        const int iters = cg_core<R>(s_val, s_col, s_z, s_part, W, np, T, tid, dg, bvec, io.tol2,
-                                     io.maxit, x, status);
-        pcg_epilogue<R>(s_val, s_col, s_z, s_part, W, np, T, tid, n, dg, bvec, x, obs, io, sample, iters,
-                        status);
-    }
-}
-
-// ------------------------------------------------------------------------------------------- K2
-template <int R, int MAXT>
-__global__ void __launch_bounds__(MAXT) pcg_nodal_kernel(EllNodal op, CsrRows obs, PcgIO io) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int T = blockDim.x, tid = threadIdx.x;
-    const int np = R * T, W = op.W, n = op.n, ld = op.ld, nc = op.n_cells;
-    const PcgSmem L = PcgSmem::make(W, np, nc, n);
-    double* s_val = reinterpret_cast<double*>(smem + L.val_off);
-    double* s_z = reinterpret_cast<double*>(smem + L.z_off);
-    double* s_part = reinterpret_cast<double*>(smem + L.part_off);
-    long long* s_next = reinterpret_cast<long long*>(smem + L.misc_off) + 16;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.misc_off) + 20;
+    double* s_dsi = reinterpret_cast<double*>(smem + L.dsi_off);
     double* s_kbar = reinterpret_cast<double*>(smem + L.kbar_off);
     double* s_kbuf = reinterpret_cast<double*>(smem + L.kbuf_off);
-    uint16_t* s_col = reinterpret_cast<uint16_t*>(smem + L.col_off);
+    double* s_val = reinterpret_cast<double*>(smem + L.val_off);
+    const unsigned char* s_rb = reinterpret_cast<const unsigned char*>(s_r);
 
-    double bvec[R];
+    // ---- once per CTA: packed byte offsets (8 * column) of this thread's ELL slots, two per register
+    uint32_t pk[R][WT / 2];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         const int i = tid + k * T;
-        bvec[k] = i < n ? op.rhs[i] : 0.0;
-        for (int w = 0; w < W; ++w) s_col[w * np + i] = i < n ? op.col[w * ld + i] : (uint16_t)i;
+#pragma unroll
+        for (int w = 0; w < WT; w += 2) {
+            const uint32_t c0 = (i < n && w < W) ? op.col[(size_t)w * ld + i] : (uint32_t)i;
+            const uint32_t c1 = (i < n && w + 1 < W) ? op.col[(size_t)(w + 1) * ld + i] : (uint32_t)i;
+            pk[k][w / 2] = (c0 << 3) | (c1 << 19);
+        }
     }
-    if (tid == 0) {
+    auto gather = [&](int k, int w) -> double {
+        const uint32_t off = (w & 1) ? (pk[k][w >> 1] >> 16) : (pk[k][w >> 1] & 0xffffu);
+        return *reinterpret_cast<const double*>(s_rb + off);
+    };
+    if (NODAL && tid == 0) {
         mbar_init(s_bar, 1);
         mbar_fence_init();
         s_kbar[nc] = 0.0;  // sentinel "no cell"
@@ -339,87 +152,217 @@ __global__ void __launch_bounds__(MAXT) pcg_nodal_kernel(EllNodal op, CsrRows ob
         const long long sample = *s_next;
         if (sample >= io.N) break;
 
-        // ---- stage the nodal field k (n doubles) into shared memory with ONE TMA bulk copy.
-        // cp.async.bulk needs 16-byte aligned addresses/sizes; rows of odd n start 8-byte aligned, so the
-        // row is placed in s_kbuf with the same 16-byte phase and the <=1 head / tail doubles are
-        // loaded with ordinary loads.
-        const double* krow = io.in + sample * (long long)io.in_stride;
-        const int off = (int)((reinterpret_cast<uintptr_t>(krow) >> 3) & 1);
-        const int head = off;                      // doubles before the first 16B boundary
-        const int body = (n - head) & ~1;          // doubles moved by the bulk copy
-        if (tid == 0) {
-            if (body > 0) {
-                mbar_expect_tx(s_bar, (uint32_t)body * 8u);
-                tma_bulk_g2s(s_kbuf + off + head, krow + head, (uint32_t)body * 8u, s_bar);
-            }
-            if (head) s_kbuf[off] = krow[0];
-            if (head + body < n) s_kbuf[off + n - 1] = krow[n - 1];
-        }
-        if (body > 0) mbar_wait(s_bar, parity);
-        parity ^= (body > 0);
-        __syncthreads();
-        const double* kk = s_kbuf + off;
-
-        // ---- cell means:  int k grad w.grad v over a cell = mean(k at its vertices) * K_e
-        for (int e = tid; e < nc; e += T) {
-            const int a = op.cells[3 * e], b = op.cells[3 * e + 1], c = op.cells[3 * e + 2];
-            s_kbar[e] = ((kk[a] + kk[b]) + kk[c]) / 3.0;
-        }
-        __syncthreads();
-
-        // ---- in-kernel assembly of this thread's rows
-        double dg[R];
+        // ================= per-sample operator =================
+        double dsi[R];      // 1/sqrt(diag)
+        double av[R][WR > 0 ? WR : 1];
+        if (!NODAL) {
+            if (tid < op.n_terms) s_theta[tid] = tid == 0 ? 1.0 : io.in[sample * io.in_stride + tid - 1];
+            __syncthreads();
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const int i = tid + k * T;
-            double d = 1.0;
-            if (i < n) {
-                d = op.dcst[i];
-                for (int j = op.dptr[i]; j < op.dptr[i + 1]; ++j) d = fma(op.dcoef[j], s_kbar[op.dcell[j]], d);
+            for (int k = 0; k < R; ++k) {
+                const int i = tid + k * T;
+                double d = 1.0;
+                if (i < n) {
+                    d = 0.0;
+                    for (int t = 0; t < op.n_terms; ++t) d = fma(s_theta[t], op.diag[t * ld + i], d);
+                }
+                dsi[k] = 1.0 / sqrt(d);
+                s_r[i] = dsi[k];
             }
-            dg[k] = d;
+        } else {
+            // stage the nodal field k (n doubles) into shared memory with ONE TMA bulk copy.  cp.async.bulk needs
+            // 16-byte aligned addresses/sizes; rows of odd n start 8-byte aligned, so the row is placed in s_kbuf
+            // with the same 16-byte phase and the <=1 head / tail doubles are loaded with ordinary loads.
+            const double* krow = io.in + sample * (long long)io.in_stride;
+            const int off = (int)((reinterpret_cast<uintptr_t>(krow) >> 3) & 1);
+            const int head = off;              // doubles before the first 16B boundary
+            const int body = (n - head) & ~1;  // doubles moved by the bulk copy
+            if (tid == 0) {
+                if (body > 0) {
+                    mbar_expect_tx(s_bar, (uint32_t)body * 8u);
+                    tma_bulk_g2s(s_kbuf + off + head, krow + head, (uint32_t)body * 8u, s_bar);
+                }
+                if (head) s_kbuf[off] = krow[0];
+                if (head + body < n) s_kbuf[off + n - 1] = krow[n - 1];
+            }
+            if (body > 0) mbar_wait(s_bar, parity);
+            parity ^= (body > 0);
+            __syncthreads();
+            const double* kk = s_kbuf + off;
+            // cell means:  int k grad w.grad v over a cell = mean(k at its vertices) * K_e
+            for (int e = tid; e < nc; e += T) {
+                const int a = op.cells[3 * e], b = op.cells[3 * e + 1], c = op.cells[3 * e + 2];
+                s_kbar[e] = ((kk[a] + kk[b]) + kk[c]) / 3.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int i = tid + k * T;
+                double d = 1.0;
+                if (i < n) {
+                    d = op.dcst[i];
+                    for (int j = op.dptr[i]; j < op.dptr[i + 1]; ++j)
+                        d = fma(op.dcoef[j], s_kbar[op.dcell[j]], d);
+                }
+                dsi[k] = 1.0 / sqrt(d);
+                s_r[i] = dsi[k];
+            }
         }
-        const size_t plane = (size_t)W * ld;
-        for (int w = 0; w < W; ++w) {
+        __syncthreads();  // 1/sqrt(diag) of every row visible
+#pragma unroll
+        for (int w = 0; w < WT; ++w) {
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 const int i = tid + k * T;
                 double v = 0.0;
-                if (i < n) {
+                if (i < n && w < W) {
                     const size_t o = (size_t)w * ld + i;
-                    v = op.cst[o];
-                    v = fma(op.coef[o], s_kbar[op.cell[o]], v);
-                    v = fma(op.coef[plane + o], s_kbar[op.cell[plane + o]], v);
+                    if (!NODAL) {
+                        for (int t = 0; t < op.n_terms; ++t)
+                            v = fma(s_theta[t], op.val[(size_t)t * W * ld + o], v);
+                    } else {
+                        const size_t plane = (size_t)W * ld;
+                        v = op.cst[o];
+                        v = fma(op.coef[o], s_kbar[op.cell[o]], v);
+                        v = fma(op.coef[plane + o], s_kbar[op.cell[plane + o]], v);
+                    }
+                    v *= dsi[k] * gather(k, w);
                 }
-                s_val[w * np + i] = v;
+                if (w < WR) av[k][w < WR ? w : 0] = v;
+                else s_val[(w - WR) * np + i] = v;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) s_dsi[tid + k * T] = dsi[k];
+        __syncthreads();  // all gathers of dsi done before s_r is reused for r
+
+        // ================= CG on the scaled system =================
+        auto spmv = [&](const double (&rv)[R], double (&sv)[R]) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) sv[k] = rv[k];  // unit diagonal
+#pragma unroll
+            for (int w = 0; w < WT; ++w) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const double a = (w < WR) ? av[k][w < WR ? w : 0] : s_val[(w - WR) * np + tid + k * T];
+                    sv[k] = fma(a, gather(k, w), sv[k]);
+                }
+            }
+        };
+        double x[R], r[R], p[R], q[R], s[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int i = tid + k * T;
+            x[k] = 0.0;
+            r[k] = (i < n ? op.rhs[i] : 0.0) * dsi[k];
+            s_r[i] = r[k];
+        }
+        __syncthreads();
+        spmv(r, s);
+        double gam = 0.0, del = 0.0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            gam = fma(r[k], r[k], gam);
+            del = fma(r[k], s[k], del);
+        }
+        block_sum2(gam, del, s_part, lane, warp, nwarps);
+        int status = TFIN_STATUS_MAXIT, it = 0;
+        if (!(gam > 0.0) || !(del > 0.0)) {  // b == 0 (x = 0 is exact) or not SPD / NaN
+            status = (gam == 0.0) ? TFIN_STATUS_CONVERGED : TFIN_STATUS_BREAKDOWN;
+        } else {
+            const double thresh = io.tol2 * gam;
+            double alpha = gam / del, denom = del;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                p[k] = r[k];
+                q[k] = s[k];
+            }
+            while (it < io.maxit) {
+                ++it;
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    x[k] = fma(alpha, p[k], x[k]);
+                    r[k] = fma(-alpha, q[k], r[k]);
+                    s_r[tid + k * T] = r[k];
+                }
+                __syncthreads();  // r visible; everyone is done with s_part of the previous iteration
+                spmv(r, s);
+                double gn = 0.0, dl = 0.0;
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    gn = fma(r[k], r[k], gn);
+                    dl = fma(r[k], s[k], dl);
+                }
+                block_sum2(gn, dl, s_part, lane, warp, nwarps);  // barrier inside: all gathers of r done
+                if (gn <= thresh) {
+                    status = TFIN_STATUS_CONVERGED;
+                    break;
+                }
+                const double beta = gn / gam;
+                denom = dl - beta * beta * denom;  // = dl - beta * gn / alpha_old
+                if (!(denom > 0.0) || !(gn == gn)) {
+                    status = TFIN_STATUS_BREAKDOWN;
+                    break;
+                }
+                alpha = gn / denom;
+                gam = gn;
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    p[k] = fma(beta, p[k], r[k]);
+                    q[k] = fma(beta, q[k], s[k]);
+                }
             }
         }
 
-        double x[R];
-        int status;
-        const int iters = cg_core<R>(s_val, s_col, s_z, s_part, W, np, T, tid, dg, bvec, io.tol2,
-                                     io.maxit, x, status);
-        pcg_epilogue<R>(s_val, s_col, s_z, s_part, W, np, T, tid, n, dg, bvec, x, obs, io, sample, iters,
-                        status);
-    }
-}
-
-// ------------------------------------------------------------------------------------------- K0
-// theta = Avg k for a batch of nodal fields: one warp per (sample, row); a streaming, HBM-bound kernel.
-__global__ void __launch_bounds__(256) csr_project_kernel(CsrRows op, const double* __restrict__ in,
-                                                          long long N, int n, double* __restrict__ out) {
-    const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const long long total = N * op.rows;
-    const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long t = gw; t < total; t += stride) {
-        const long long s = t / op.rows;
-        const int o = (int)(t - s * op.rows);
-        const double* row = in + s * (long long)n;
-        double acc = 0.0;
-        for (int j = op.ptr[o] + lane; j < op.ptr[o + 1]; j += 32) acc = fma(op.val[j], row[op.idx[j]], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) out[t] = acc;
+        // ================= epilogue =================
+        __syncthreads();
+        if (io.relres_out || io.status_out) {  // true residual of the scaled system: ||b~ - A~ x~|| / ||b~||
+#pragma unroll
+            for (int k = 0; k < R; ++k) s_r[tid + k * T] = x[k];
+            __syncthreads();
+            spmv(x, s);
+            double rr = 0.0, bb = 0.0;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int i = tid + k * T;
+                const double bt = (i < n ? op.rhs[i] : 0.0) * s_dsi[i];
+                const double t = bt - s[k];
+                rr = fma(t, t, rr);
+                bb = fma(bt, bt, bb);
+            }
+            block_sum2(rr, bb, s_part, lane, warp, nwarps);
+            const double relres = bb > 0.0 ? sqrt(rr / bb) : sqrt(rr);
+            if (!(relres == relres)) status = TFIN_STATUS_BREAKDOWN;
+            if (tid == 0 && io.relres_out) io.relres_out[sample] = relres;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            if (io.iters_out) io.iters_out[sample] = it;
+            if (io.status_out) io.status_out[sample] = status;
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int i = tid + k * T;
+            x[k] *= s_dsi[i];  // w = D^-1/2 x~
+            s_r[i] = x[k];
+        }
+        __syncthreads();
+        if (io.qoi_out) {
+            for (int o = warp; o < obs.rows; o += nwarps) {
+                double acc = 0.0;
+                for (int j = obs.ptr[o] + lane; j < obs.ptr[o + 1]; j += 32)
+                    acc = fma(obs.val[j], s_r[obs.idx[j]], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) io.qoi_out[sample * obs.rows + o] = acc;
+            }
+        }
+        if (io.w_out) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int i = tid + k * T;
+                if (i < n) io.w_out[sample * (long long)n + i] = x[k];
+            }
+        }
     }
 }
 

@@ -7,9 +7,26 @@
 
 #include "common.cuh"
 #include "pcg_small.cuh"
+#include "pcg_variants.h"
+#include "project.cuh"
 #include "rom.cuh"
 
 using namespace tfin;
+
+namespace tfin {
+#define DECL_G(g) const PcgVariant* pcg_variants_g##g##_n0(int*); const PcgVariant* pcg_variants_g##g##_n1(int*);
+DECL_G(0) DECL_G(1) DECL_G(2) DECL_G(3) DECL_G(4)
+#undef DECL_G
+const PcgVariant* pcg_variants(int group, int nodal, int* count) {
+    switch (group * 2 + (nodal ? 1 : 0)) {
+#define CASE_G(g) case g * 2: return pcg_variants_g##g##_n0(count); case g * 2 + 1: return pcg_variants_g##g##_n1(count);
+        CASE_G(0) CASE_G(1) CASE_G(2) CASE_G(3) CASE_G(4)
+#undef CASE_G
+    }
+    *count = 0;
+    return nullptr;
+}
+}  // namespace tfin
 
 struct tfin_ctx {
     int device = 0;
@@ -42,8 +59,9 @@ struct tfin_ctx {
     DevBuf<int> d_iters, d_status;
     DevBuf<unsigned long long> d_counter;
     // ---- tuning
-    int pcg_R = 0;  // 0 = auto
-    int last_T = 0, last_R = 0, last_occ = 0;
+    int pcg_R = 0;    // rows per thread, 0 = auto
+    int pcg_WR = -1;  // -1 auto, 0 = ELL values in shared memory, 1 = in registers
+    int last_T = 0, last_R = 0, last_occ = 0, last_WT = 0, last_WR = 0;
     size_t last_smem = 0;
 };
 
@@ -107,7 +125,7 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
         return fail(TFIN_E_ARG, "tfin_set_operator: bad argument");
     if (n_terms < 1 || n_terms > TFIN_MAX_TERMS)
         return fail(TFIN_E_ARG, "tfin_set_operator: n_terms must be in [1, %d]", TFIN_MAX_TERMS);
-    if (n > 65535) return fail(TFIN_E_ARG, "tfin_set_operator: n = %d exceeds the on-chip PCG limit (65535)", n);
+    if (n > 8191) return fail(TFIN_E_ARG, "tfin_set_operator: n = %d exceeds the on-chip PCG limit (8191)", n);
     if (row_ptr[0] != 0 || row_ptr[n] != nnz) return fail(TFIN_E_ARG, "tfin_set_operator: malformed row_ptr");
     const int ld = (n + 31) & ~31;
     // pass 1: diagonal positions, off-diagonal widths
@@ -319,92 +337,107 @@ extern "C" int tfin_set_rom(tfin_handle_t h, int32_t n_r, int32_t n_terms, int32
 
 // ------------------------------------------------------------------------------------------------ launch helpers
 struct PcgGeom {
-    int R, T, occ, grid;
+    const PcgVariant* v;
+    int T, occ;
     size_t smem;
 };
 
-template <typename Kern>
-static int pcg_geom_for(tfin_ctx* h, Kern kern, int R, int maxT, int W, int n_cells, PcgGeom* g) {
-    const int n = h->n;
+static bool pcg_geom_for(tfin_ctx* h, const PcgVariant* v, int n_cells, PcgGeom* g) {
+    const int n = h->n, R = v->R;
     const int T = ((n + R - 1) / R + 31) & ~31;
-    if (T > maxT || T > 1024) return 1;
-    const PcgSmem L = PcgSmem::make(W, R * T, n_cells, n);
-    if (L.total > (size_t)h->max_smem_optin) return 1;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
+    if (T > v->maxT || T > 1024 || R * T > 8192) return false;
+    const PcgSmem L = PcgSmem::make(v->WT - v->WR, R * T, n_cells, n);
+    if (L.total > (size_t)h->max_smem_optin) return false;
+    if (cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
         cudaGetLastError();
-        return 1;
+        return false;
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, L.total) != cudaSuccess || occ < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, T, L.total) != cudaSuccess || occ < 1) {
         cudaGetLastError();
-        return 1;
+        return false;
     }
-    g->R = R;
+    g->v = v;
     g->T = T;
     g->occ = occ;
     g->smem = L.total;
-    return 0;
+    return true;
 }
 
-#define PCG_FOR_EACH_R(X) X(1, 1024) X(2, 768) X(3, 640) X(4, 512) X(5, 384) X(6, 352) X(8, 256)
-
-template <bool NODAL>
-static int launch_pcg(tfin_ctx* h, const double* d_in, int in_stride, int64_t N, double tol, int maxit,
-                      double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres,
-                      cudaStream_t st) {
-    const int W = NODAL ? h->Wn : h->W;
-    const int nc = NODAL ? h->n_cells : 0;
-    PcgGeom best{};
-    bool have = false;
-    // pick rows/thread: user override, else the geometry with the most resident threads per SM and,
-    // among those, the least padding
-    double best_score = -1.0;
-#define TRY_R(R_, MAXT_)                                                                              \
-    if (h->pcg_R == 0 || h->pcg_R == R_) {                                                            \
-        PcgGeom g{};                                                                                   \
-        int rc = NODAL ? pcg_geom_for(h, pcg_nodal_kernel<R_, MAXT_>, R_, MAXT_, W, nc, &g)           \
-                       : pcg_geom_for(h, pcg_affine_kernel<R_, MAXT_>, R_, MAXT_, W, nc, &g);         \
-        if (rc == 0) {                                                                                 \
-            const double pad = (double)h->n / (g.R * g.T);                                             \
-            const double score = std::min(g.occ * g.T, 1024) * pad * (g.occ >= 2 ? 1.15 : 1.0);       \
-            if (score > best_score) {                                                                  \
-                best_score = score;                                                                    \
-                best = g;                                                                              \
-                have = true;                                                                           \
-            }                                                                                          \
-        }                                                                                              \
+static int launch_pcg(tfin_ctx* h, bool nodal, const double* d_in, int in_stride, int64_t N, double tol, int maxit,
+                      double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres, cudaStream_t st) {
+    const int W = nodal ? h->Wn : h->W;
+    const int nc = nodal ? h->n_cells : 0;
+    // candidates: variants with the smallest compiled ELL width >= W; user knobs filter further
+    int wt_min = 1 << 30;
+    for (int g = 0; g < PCG_NUM_GROUPS; ++g) {
+        int cnt = 0;
+        const PcgVariant* tab = pcg_variants(g, nodal, &cnt);
+        for (int i = 0; i < cnt; ++i)
+            if (tab[i].WT >= W) wt_min = std::min(wt_min, tab[i].WT);
     }
-    PCG_FOR_EACH_R(TRY_R)
-#undef TRY_R
-    if (!have)
-        return fail(TFIN_E_STATE, "on-chip PCG: no launch geometry fits (n=%d, W=%d, rows/thread=%d)", h->n, W,
+    PcgGeom best{};
+    double best_score = -1.0;
+    for (int g = 0; g < PCG_NUM_GROUPS; ++g) {
+        int cnt = 0;
+        const PcgVariant* tab = pcg_variants(g, nodal, &cnt);
+        for (int i = 0; i < cnt; ++i) {
+            const PcgVariant* v = &tab[i];
+            if (v->WT < W) continue;
+            if (h->pcg_R > 0 && v->R != h->pcg_R) continue;
+            if (h->pcg_WR >= 0 && (v->WR > 0) != (h->pcg_WR > 0)) continue;
+            PcgGeom geo{};
+            if (!pcg_geom_for(h, v, nc, &geo)) continue;
+            // score: resident rows per SM that do useful work, two CTAs per SM preferred (barrier latency of one
+            // CTA overlaps the SpMV of the other), narrower compiled width preferred
+            const double pad = (double)h->n / (v->R * geo.T);
+            double score = pad * (geo.occ >= 2 ? 1.5 : 1.0) * (v->WT == wt_min ? 1.0 : 0.5 * wt_min / v->WT);
+            if (v->R == 5) score *= 1.02;
+            if (score > best_score) {
+                best_score = score;
+                best = geo;
+            }
+        }
+    }
+    if (best_score < 0)
+        return fail(TFIN_E_STATE, "on-chip PCG: no compiled variant fits (n=%d, ell width=%d, rows/thread=%d)", h->n, W,
                     h->pcg_R);
     const int grid = (int)std::min<int64_t>(N, (int64_t)h->sm_count * best.occ);
-    h->last_R = best.R;
+    h->last_R = best.v->R;
     h->last_T = best.T;
     h->last_occ = best.occ;
     h->last_smem = best.smem;
+    h->last_WT = best.v->WT;
+    h->last_WR = best.v->WR;
 
     TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
     CsrRows obs{h->n_obs, h->d_obs_ptr.p, h->d_obs_idx.p, h->d_obs_val.p};
     PcgIO io{d_in, (long long)N, in_stride, tol * tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres,
              h->d_counter.p};
-    if (NODAL) {
-        EllNodal op{h->n,        h->ld,        W,           nc,          h->d_ncol.p, h->d_ncell.p,
-                    h->d_ncoef.p, h->d_ncst.p, h->d_dptr.p, h->d_dcell.p, h->d_dcoef.p, h->d_dcst.p,
-                    h->d_cells.p, h->d_rhs.p};
-#define LAUNCH_R(R_, MAXT_) \
-    if (best.R == R_) pcg_nodal_kernel<R_, MAXT_><<<grid, best.T, best.smem, st>>>(op, obs, io);
-        PCG_FOR_EACH_R(LAUNCH_R)
-#undef LAUNCH_R
+    PcgOp op{};
+    op.n = h->n;
+    op.ld = h->ld;
+    op.W = W;
+    op.n_terms = h->n_terms;
+    op.n_cells = nc;
+    op.rhs = h->d_rhs.p;
+    if (nodal) {
+        op.col = h->d_ncol.p;
+        op.cell = h->d_ncell.p;
+        op.coef = h->d_ncoef.p;
+        op.cst = h->d_ncst.p;
+        op.dptr = h->d_dptr.p;
+        op.dcell = h->d_dcell.p;
+        op.dcoef = h->d_dcoef.p;
+        op.dcst = h->d_dcst.p;
+        op.cells = h->d_cells.p;
     } else {
-        EllAffine op{h->n, h->ld, W, h->n_terms, h->d_col.p, h->d_val.p, h->d_diag.p, h->d_rhs.p};
-#define LAUNCH_R(R_, MAXT_) \
-    if (best.R == R_) pcg_affine_kernel<R_, MAXT_><<<grid, best.T, best.smem, st>>>(op, obs, io);
-        PCG_FOR_EACH_R(LAUNCH_R)
-#undef LAUNCH_R
+        op.col = h->d_col.p;
+        op.val = h->d_val.p;
+        op.diag = h->d_diag.p;
     }
-    TFIN_CUDA(cudaGetLastError());
+    void* args[] = {&op, &obs, &io};
+    TFIN_CUDA(cudaLaunchKernel(best.v->func, dim3(grid), dim3(best.T), args, best.smem, st));
     h->launches += 1;
     return 0;
 }
@@ -510,8 +543,7 @@ static int fom_common(tfin_handle_t h, bool nodal_op, const double* in, int64_t 
     if (int e = sg.out_alloc(iters_out, (size_t)N, h->d_iters, &d_iters)) return e;
     if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
     if (int e = sg.out_alloc(relres_out, (size_t)N, h->d_relres, &d_relres)) return e;
-    int rc = nodal_op ? launch_pcg<true>(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st)
-                      : launch_pcg<false>(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st);
+    int rc = launch_pcg(h, nodal_op, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st);
     if (rc) return rc;
     if (int e = sg.out_copy(w_out, (size_t)N * h->n, d_w)) return e;
     if (int e = sg.out_copy(qoi_out, (size_t)N * h->n_obs, d_qoi)) return e;
@@ -614,6 +646,8 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
     if (k == "pcg_rows_per_thread") return h->last_R;
     if (k == "pcg_ctas_per_sm") return h->last_occ;
     if (k == "pcg_smem_bytes") return (int64_t)h->last_smem;
+    if (k == "pcg_ell_width_compiled") return h->last_WT;
+    if (k == "pcg_reg_slots") return h->last_WR;
     if (k == "rom_chunk") return h->rom_chunk;
     return -1;
 }
@@ -627,6 +661,10 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
     }
     if (k == "rom_chunk") {
         h->rom_chunk = value;
+        return 0;
+    }
+    if (k == "pcg_reg_slots") {
+        h->pcg_WR = (int)value;
         return 0;
     }
     return fail(TFIN_E_ARG, "tfin_set_int: unknown key '%s'", key);

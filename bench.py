@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark of the thermal-fin batched forward map (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo's CUDA path)
+    python bench.py --impl reference --gpus N ...             # reference arm: CPU port on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic conductivity samples per GPU:
+  * FOM leg (headline `value`): BASELINE config "five-param batched FOM solves ... 10^5 samples on the reference
+    mesh, QoI = subfin averages" -> affine Jacobi-PCG kernel fused with B_obs (mesh: structured m=3, n = 1597)
+  * ROM leg (`rom` object): BASELINE config "nine-param batched ROM solves, 10^6 samples" (n_r = 81)
+Samples are sharded over ranks (weak scaling: the per-GPU batch is fixed); with N > 1 the step ends with the
+NCCL all-gather of the observables.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "thermal-fin forward solves/sec (FOM & ROM) at 1/2/4/8 B200; % HBM roofline"
+RESOLUTION = 40                 # reference's get_space(40); structured m = 3 -> n = 1597
+FOM_SEED, ROM_SEED = 1, 0
+TOL = 1e-12
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--fom-batch", type=int, default=100_000, help="FOM samples per GPU per step")
+    ap.add_argument("--rom-batch", type=int, default=1_000_000, help="ROM samples per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-fom-sample", type=int, default=2048)
+    ap.add_argument("--cpu-rom-sample", type=int, default=2048)
+    return ap.parse_args()
+
+
+def fom_inputs(n, seed):
+    """config 3: k ~ U(0.1, 1.0)^5 -> nine-vector [k1..k5,k4..k1] (generate_reduced_basis_five_param.py:34,57)."""
+    k5 = np.random.default_rng(seed).uniform(0.1, 1.0, (n, 5))
+    return np.ascontiguousarray(np.concatenate([k5, k5[:, 3::-1]], axis=1))
+
+
+def rom_inputs(n, seed):
+    """config 2: theta ~ U(0.1, 3.5)^9 (generate_reduced_basis_nine_param.py:299)."""
+    return np.random.default_rng(seed).uniform(0.1, 3.5, (n, 9))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY place bench.py touches oracle/): reported baseline + the --impl reference arm
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(coords, cells, phi):
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(1)
+    from oracle.thermal_fin_oracle import FinOracle
+    _W["o"] = FinOracle(coords, cells)
+    _W["phi"] = phi
+
+
+def _cpu_fom(theta_rows):
+    o = _W["o"]
+    return np.stack([o.qoi_operator(o.forward_nine_param(t)) for t in theta_rows])
+
+
+def _cpu_rom(theta_rows):
+    o, phi = _W["o"], _W["phi"]
+    return np.stack([o.qoi_reduced(o.forward_nine_param_reduced(t, phi), phi) for t in theta_rows])
+
+
+class CpuPool:
+    """All host cores, one single-threaded oracle per worker process (fork before any CUDA work)."""
+
+    def __init__(self, phi=None):
+        import multiprocessing as mp
+        from bayesianinferencedl_b200 import get_space
+        V = get_space(RESOLUTION)
+        self.cores = os.cpu_count() or 1
+        ctx = mp.get_context("fork")
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_init,
+                             initargs=(V.mesh().coordinates(), V.mesh().cells(), phi))
+        self.pool.map(_cpu_fom, [fom_inputs(1, 99)] * self.cores)       # warm every worker
+
+    def run(self, fn, rows):
+        chunks = [c for c in np.array_split(rows, self.cores * 4) if len(c)]
+        t0 = time.perf_counter()
+        out = self.pool.map(fn, chunks)
+        dt = time.perf_counter() - t0
+        return np.concatenate(out), dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_pod_basis():
+    """Reference-style POD basis built with the oracle (reference arm must not touch the CUDA path)."""
+    from bayesianinferencedl_b200 import get_space
+    from oracle.thermal_fin_oracle import FinOracle, pod_basis
+    V = get_space(RESOLUTION)
+    return pod_basis(FinOracle(V.mesh().coordinates(), V.mesh().cells()), 200, 81, seed=0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    phi = cpu_pod_basis()
+    pool = CpuPool(phi)
+    per_step = max(pool.cores * 16, 256)
+    th = fom_inputs(per_step * (args.steps + args.warmup), FOM_SEED)
+    thr = rom_inputs(per_step * (args.steps + args.warmup), ROM_SEED)
+    t_f = t_r = 0.0
+    for s in range(args.steps + args.warmup):
+        _, dt = pool.run(_cpu_fom, th[s * per_step:(s + 1) * per_step])
+        _, dtr = pool.run(_cpu_rom, thr[s * per_step:(s + 1) * per_step])
+        if s >= args.warmup:
+            t_f += dt
+            t_r += dtr
+    pool.close()
+    v = per_step * args.steps / t_f
+    vr = per_step * args.steps / t_r
+    sample = f"{per_step} five-param FOM solves per step (assemble + scipy splu + B_obs), {pool.cores} processes"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_f / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config[2] five-param batched FOM on the m=3 mesh (n=1597), CPU port of the "
+                               "reference path: FEniCS/PETSc are not installable here (parity unpinned)",
+                   "samples_per_step": per_step},
+        "cpu_baseline": {"value": v, "unit": "solves/s", "cores": pool.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "rom": {"value": vr, "unit": "solves/s", "ms_per_step": 1e3 * t_r / args.steps,
+                "sample": f"{per_step} literal LSPG ROM solves per step (A phi, psi^T psi, np.linalg.solve)"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_ev = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_ev.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_ev.wait(0.1)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    # ---- CPU baseline first (fork-based pool, before this process creates a CUDA context); rank 0, N=1 only
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        phi_cpu = cpu_pod_basis()
+        pool = CpuPool(phi_cpu)
+        _, dt_f = pool.run(_cpu_fom, fom_inputs(args.cpu_fom_sample, FOM_SEED))
+        _, dt_r = pool.run(_cpu_rom, rom_inputs(args.cpu_rom_sample, ROM_SEED))
+        pool.close()
+        cpu = {"value": args.cpu_fom_sample / dt_f, "unit": "solves/s", "cores": pool.cores, "kind": "port",
+               "sample": f"first {args.cpu_fom_sample} samples of the FOM workload: oracle port of the reference "
+                         f"path (numpy assembly + scipy splu + B_obs), {pool.cores} single-threaded processes, "
+                         f"{dt_f:.1f} s",
+               "rom_value": args.cpu_rom_sample / dt_r,
+               "rom_sample": f"first {args.cpu_rom_sample} ROM samples, literal averaged_affine_ROM.py:292-304 "
+                             f"(A phi, psi^T psi, np.linalg.solve), {dt_r:.1f} s"}
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bayesianinferencedl_b200 import AffineROMFin, _cabi, get_space
+    from bayesianinferencedl_b200.dist import gather_rows
+    from bayesianinferencedl_b200.rom.pod import generate_pod_basis
+
+    V = get_space(RESOLUTION)
+    phi = generate_pod_basis(V, 200, 81, seed=0, device=local_rank)
+    model = AffineROMFin(V, None, phi, device=local_rank)
+    h = model.handle
+    n, n_obs, n_r = model.dofs, model.n_obs, model.n_r
+    NF, NR = args.fom_batch, args.rom_batch
+
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    f64 = torch.float64
+    th_f_host = torch.from_numpy(fom_inputs(NF, FOM_SEED + rank)).pin_memory()
+    th_r_host = torch.from_numpy(rom_inputs(NR, ROM_SEED + rank)).pin_memory()
+    th_f, th_r = th_f_host.to(dev), th_r_host.to(dev)
+    q_f = torch.empty((NF, n_obs), dtype=f64, device=dev)
+    q_r = torch.empty((NR, n_obs), dtype=f64, device=dev)
+    it_f = torch.empty(NF, dtype=torch.int32, device=dev)
+    st_f = torch.empty(NF, dtype=torch.int32, device=dev)
+    st_r = torch.empty(NR, dtype=torch.int32, device=dev)
+    q_f_host = torch.empty((NF, n_obs), dtype=f64).pin_memory()
+    q_r_host = torch.empty((NR, n_obs), dtype=f64).pin_memory()
+    it_f_host = torch.empty(NF, dtype=torch.int32).pin_memory()
+    st_f_host = torch.empty(NF, dtype=torch.int32).pin_memory()
+    st_r_host = torch.empty(NR, dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def fom_dev():
+        h.fom_affine_raw(th_f.data_ptr(), NF, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_f.data_ptr(),
+                         iters=it_f.data_ptr(), status=st_f.data_ptr(), stream=sp)
+        return gather_rows(q_f, NF * world) if world > 1 else q_f
+
+    def rom_dev():
+        h.rom_raw(th_r.data_ptr(), NR, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, qoi=q_r.data_ptr(),
+                  status=st_r.data_ptr(), stream=sp)
+        return gather_rows(q_r, NR * world) if world > 1 else q_r
+
+    def fom_e2e():     # the C-ABI call a user of the facade makes: HOST buffers in, HOST buffers out
+        h.fom_affine_raw(th_f_host.data_ptr(), NF, _cabi.IN_PARAMS, _cabi.MEM_HOST, TOL, 20000,
+                         qoi=q_f_host.data_ptr(), iters=it_f_host.data_ptr(), status=st_f_host.data_ptr(), stream=sp)
+
+    def rom_e2e():
+        h.rom_raw(th_r_host.data_ptr(), NR, _cabi.IN_PARAMS, _cabi.MEM_HOST, qoi=q_r_host.data_ptr(),
+                  status=st_r_host.data_ptr(), stream=sp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """W warm-up + EXACTLY K steps bracketed by barrier + synchronize; CUDA events on the launching stream;
+        L2 flushed between steps; returns max-over-ranks milliseconds and this rank's launch count."""
+        for _ in range(warmup):
+            fn()
+            flush.fill_(1)
+        barrier()
+        l0 = h.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+            flush.fill_(1)
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=f64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), h.kernel_launches() - l0
+
+    # flush cost (inside the bracket) measured once so it can be reported
+    timed(lambda: None, 2, 1)
+    flush_ms, _ = timed(lambda: None, 4, 1)
+    flush_ms /= 4
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    K, Wm = args.steps, max(args.warmup, 3)
+    ms_f, launches_f = timed(fom_dev, K, Wm)
+    ms_r, launches_r = timed(rom_dev, K, Wm)
+    ms_fe, launches_fe = timed(fom_e2e, K, Wm)
+    ms_re, launches_re = timed(rom_e2e, K, Wm)
+    clocks = sampler.stop()
+
+    # ---- kernel-only duration of the dominant kernel (PCG) for the roofline: one more step, events tight
+    # around the single launch on its stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    for _ in range(3):
+        flush.fill_(1)
+        e0.record(stream)
+        h.fom_affine_raw(th_f.data_ptr(), NF, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_f.data_ptr(),
+                         iters=it_f.data_ptr(), status=st_f.data_ptr(), stream=sp)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        kms.append(e0.elapsed_time(e1))
+    k_ms = float(np.mean(kms))
+    iters_sum = int(it_f.to(torch.int64).sum().item())
+    ok_f = bool((st_f == 0).all().item())
+    ok_r = bool((st_r == 0).all().item())
+
+    # DGEMM rate of this GPU (cuBLAS) as the FP64 denominator for the ROM leg
+    a = torch.randn(4096, 4096, dtype=f64, device=dev)
+    b = torch.randn(4096, 4096, dtype=f64, device=dev)
+    for _ in range(2):
+        a @ b
+    e0.record(stream)
+    for _ in range(3):
+        a @ b
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dgemm_tflops = 3 * 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("pcg_affine_kernel")
+    except Exception:
+        pass
+
+    # algorithmic bytes of one PCG launch: 88 n bytes per iteration per sample + theta in, qoi out
+    alg_bytes = 88.0 * n * iters_sum + NF * (9 * 8 + n_obs * 8 + 8)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    step_ms_f = (ms_f / K) - flush_ms
+    step_ms_r = (ms_r / K) - flush_ms
+    fom_rate = world * NF / (step_ms_f * 1e-3)
+    rom_rate = world * NR / (step_ms_r * 1e-3)
+    fom_e2e_rate = world * NF / ((ms_fe / K - flush_ms) * 1e-3)
+    rom_e2e_rate = world * NR / ((ms_re / K - flush_ms) * 1e-3)
+    rom_flops = 2 * 55 * 3321 + 2 * 10 * 81 + 81 ** 3 / 3 + 2 * 81 ** 2 + 2 * 9 * 81     # SURVEY 8d, ~559 kflop
+
+    line = {
+        "metric": METRIC, "value": fom_rate, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": step_ms_f, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "FOM leg (value): config[2] five-param batched FOM, QoI = subfin averages; ROM leg (rom): "
+                        "config[1] nine-param batched ROM",
+            "fom_samples_per_gpu_per_step": NF, "rom_samples_per_gpu_per_step": NR,
+            "mesh": f"structured conforming fin mesh m=3, n={n} dofs (reference mshr mesh is not shipped)",
+            "n_r": n_r, "pcg_tol": TOL, "mean_pcg_iters": iters_sum / NF, "all_converged": ok_f and ok_r,
+            "pcg_geometry": {"threads": h.get_int("pcg_threads"), "rows_per_thread": h.get_int("pcg_rows_per_thread"),
+                             "ctas_per_sm": h.get_int("pcg_ctas_per_sm"), "smem_bytes": h.get_int("pcg_smem_bytes"),
+                             "ell_width": h.get_int("ell_width")},
+            "l2": f"flushed between steps by a 256 MiB write ({flush_ms:.3f} ms, subtracted)",
+            "parallelism": f"samples sharded x{world}, NCCL all-gather of observables" if world > 1 else "1 GPU",
+        },
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": traffic, "kernel": "pcg_affine_kernel", "kernel_ms": k_ms,
+            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+            "note": "algorithmic bytes = 88*n*iterations per solve (SURVEY 8d); at n=1597 the CG vectors and the "
+                    "per-sample operator live in shared memory/registers, so achieved/peak is NOT bounded by 1 "
+                    "and real DRAM traffic (traffic) is orders of magnitude below it",
+        },
+        "cpu_baseline": cpu,
+        "e2e": {"value": fom_e2e_rate, "unit": "solves/s", "h2d_bytes_per_step": NF * 9 * 8,
+                "d2h_bytes_per_step": NF * (n_obs * 8 + 4 + 4), "ms_per_step": ms_fe / K - flush_ms,
+                "api": "tfin_fom_affine(TFIN_MEM_HOST) on pinned host buffers (the call AffineROMFin makes)"},
+        "gpu_launches": launches_f,
+        "clocks": clocks,
+        "rom": {
+            "value": rom_rate, "unit": "solves/s", "ms_per_step": step_ms_r,
+            "e2e": {"value": rom_e2e_rate, "unit": "solves/s", "h2d_bytes_per_step": NR * 9 * 8,
+                    "d2h_bytes_per_step": NR * (n_obs * 8 + 4), "ms_per_step": ms_re / K - flush_ms},
+            "gpu_launches": launches_r,
+            "roofline": {"bound": "fp64", "achieved": rom_rate / world * rom_flops / 1e12,
+                         "peak": dgemm_tflops, "unit": "TFLOP/s",
+                         "frac": rom_rate / world * rom_flops / 1e12 / dgemm_tflops,
+                         "peak_source": "cuBLAS DGEMM 4096^3 measured in this run",
+                         "flops_per_sample": rom_flops},
+        },
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

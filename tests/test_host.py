@@ -1,0 +1,151 @@
+"""CPU tests of the host layer: mesh, marking, assembly (vs the independent oracle), C-ABI surface, sharding."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_mesh_sizes():
+    from bayesianinferencedl_b200 import get_space
+    for m in (1, 2, 3, 5):
+        V = get_space(40, m=m)
+        assert V.dim() == 144 * m * m + 100 * m + 1
+        assert V.mesh().num_cells() == 2 * 144 * m * m
+        x = V.tabulate_dof_coordinates()
+        assert x.min() == 0.0 and x[:, 0].max() == 6.0 and x[:, 1].max() == 4.0
+    assert get_space(40).dim() == 1597              # resolution 40 -> m = 3
+    # every rectangle corner of thermal_fin.py:7-15 is a vertex, bit-exactly
+    xs = {tuple(p) for p in get_space(40).tabulate_dof_coordinates()}
+    for c in [(2.5, 0.0), (3.5, 4.0), (0.0, 0.75), (2.5, 1.0), (6.0, 3.75), (3.5, 2.0), (0.0, 4.0)]:
+        assert c in xs
+
+
+def test_assembly_matches_oracle(space_m2, oracle_m2):
+    from bayesianinferencedl_b200.assembly import build_operators, nine_param_nodal, five_to_nine
+    ops = build_operators(space_m2)
+    o = oracle_m2
+    assert np.array_equal(ops.cell_markers, o.markers)
+    assert np.allclose(ops.rhs, o.B, atol=1e-16)
+    assert np.allclose(ops.B_obs, o.B_obs, atol=1e-15)
+    assert np.allclose(ops.C, o.C, atol=1e-15)
+    rng = np.random.default_rng(4)
+    theta = rng.uniform(0.1, 3.5, 9)
+    assert abs(ops.csr(ops.affine_values(theta)) - o.matrix_affine(theta)).max() < 1e-13
+    k = np.exp(rng.standard_normal(o.n))
+    kbar = k[ops.cells].mean(axis=1)
+    A = sum(kbar[e] * 0 for e in range(0)) if False else None
+    import scipy.sparse as sp
+    r = np.repeat(ops.cells, 3, axis=1).ravel(); c = np.tile(ops.cells, (1, 3)).ravel()
+    A = sp.coo_matrix(((ops.Ke * kbar[:, None, None]).ravel(), (r, c)), shape=(o.n, o.n)).tocsr() + ops.csr(ops.vals[0])
+    assert abs(A - o.matrix_nodal(k)).max() < 1e-12
+    assert np.array_equal(nine_param_nodal(ops.coords, theta), o.nine_param_to_function(theta))
+    assert np.array_equal(five_to_nine([1, 2, 3, 4, 5]), [1, 2, 3, 4, 5, 4, 3, 2, 1])
+    # batched nodal interpolation
+    th2 = rng.uniform(0.1, 3.5, (3, 9))
+    kn = nine_param_nodal(ops.coords, th2)
+    assert kn.shape == (3, o.n) and np.array_equal(kn[1], o.nine_param_to_function(th2[1]))
+    # pattern: sorted columns, diagonal present, symmetric values
+    for i in range(0, ops.n, 97):
+        cols = ops.col_idx[ops.row_ptr[i]:ops.row_ptr[i + 1]]
+        assert np.all(np.diff(cols) > 0) and i in cols
+
+
+def test_nonconforming_mesh_markers():
+    """SURVEY Q-1: cells straddling x = 2.5 / 3.5 keep marker 0 (SubDomain.mark semantics)."""
+    from bayesianinferencedl_b200.assembly import mark_cells
+    from oracle.thermal_fin_oracle import mark_cells as mark_ref
+    coords = np.array([[2.4, 0.8], [2.6, 0.8], [2.4, 0.95], [2.6, 0.95], [2.0, 0.8], [2.0, 0.95]])
+    cells = np.array([[0, 1, 2], [1, 3, 2], [4, 0, 5], [0, 2, 5]], dtype=np.int32)
+    got = mark_cells(coords, cells)
+    assert np.array_equal(got, mark_ref(coords, cells))
+    assert list(got) == [0, 0, 1, 1]
+
+
+def test_function_wrapper():
+    from bayesianinferencedl_b200 import Function, get_space
+    V = get_space(40, m=1)
+    f = Function(V)
+    assert f.shape == (V.dim(),) and np.all(f == 0)
+    f.vector().set_local(np.arange(V.dim(), dtype=float))
+    assert f.vector()[:][5] == 5.0 and f.vector().get_local().sum() == np.arange(V.dim()).sum()
+    g = Function(V)
+    g.assign(f)
+    assert np.array_equal(g, f)
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "tfin.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(tfin_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    """libtfin.so loads on a CPU-only box and exports every symbol include/tfin.h declares; the ctypes table
+    lists exactly the same set.  (No compute calls without a GPU.)"""
+    from bayesianinferencedl_b200 import _build, _cabi
+    _build.build()
+    lib = _cabi.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    assert sorted(_cabi.SIGNATURES) == declared
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tfin_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path fails loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from bayesianinferencedl_b200 import AffineROMFin, Fin, _cabi, get_space
+    V = get_space(40, m=1)
+    with pytest.raises(_cabi.TfinError, match="no CUDA device"):
+        Fin(V)
+    with pytest.raises(_cabi.TfinError):
+        AffineROMFin(V, None, np.eye(V.dim())[:, :4])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "bayesianinferencedl_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_rom_offline_tensors(space_m1, oracle_m1):
+    """Gram-tensor form of the LSPG system equals the literal psi^T psi of averaged_affine_ROM.py:292-304."""
+    from bayesianinferencedl_b200.assembly import build_operators
+    from bayesianinferencedl_b200.rom.averaged_affine_ROM import rom_offline_tensors
+    ops = build_operators(space_m1)
+    rng = np.random.default_rng(3)
+    phi = np.linalg.qr(rng.standard_normal((ops.n, 7)))[0]
+    S, G, obs_phi = rom_offline_tensors(ops, phi, ops.B_obs)
+    theta = rng.uniform(0.1, 3.5, 9)
+    th = np.concatenate([[1.0], theta])
+    coef = np.array([th[p] * th[q] for p in range(10) for q in range(p, 10)])
+    il = np.tril_indices(7)
+    A_r = np.zeros((7, 7)); A_r[il] = coef @ S; A_r = A_r + np.tril(A_r, -1).T
+    psi = oracle_m1.matrix_affine(theta) @ phi
+    assert np.allclose(A_r, psi.T @ psi, rtol=1e-11, atol=1e-13)
+    assert np.allclose(th @ G, psi.T @ oracle_m1.B, rtol=1e-11, atol=1e-14)
+    assert np.allclose(obs_phi, oracle_m1.B_obs @ phi)
+
+
+def test_shard_bounds():
+    from bayesianinferencedl_b200.dist import shard_bounds, shard_size
+    for n, w in [(10, 3), (8, 8), (5, 8), (0, 2), (1000001, 8)]:
+        cover = []
+        for r in range(w):
+            lo, hi = shard_bounds(n, w, r)
+            assert 0 <= lo <= hi <= n and hi - lo <= shard_size(n, w)
+            cover += list(range(lo, hi)) if n < 100 else []
+        if n < 100:
+            assert cover == list(range(n))
+        assert sum(shard_bounds(n, w, r)[1] - shard_bounds(n, w, r)[0] for r in range(w)) == n

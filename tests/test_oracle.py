@@ -1,0 +1,122 @@
+"""CPU tests of the oracle: pinned against everything the reference's shipped data pins, against its own
+committed golden outputs, and against the analytic invariants of the problem."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return np.load(os.path.join(GOLD, "reference_data.npz"))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "oracle_m1.npz"))
+
+
+def _shipped_B_obs(ref):
+    B = np.zeros(tuple(ref["B_obs_shape"]))
+    B[ref["B_obs_rows"], ref["B_obs_cols"]] = ref["B_obs_vals"]
+    return B
+
+
+def test_reference_B_obs_properties(ref, oracle_m3):
+    """data/B_obs.txt (observation_operator on the unshipped mshr mesh): 9 rows, each a partition of unity
+    average -> row sums 1, non-negative; the oracle's B_obs has the same properties."""
+    B = _shipped_B_obs(ref)
+    assert B.shape == (9, 1446)
+    assert np.allclose(B.sum(axis=1), 1.0, atol=1e-12)
+    assert B.min() >= 0
+    Bo = oracle_m3.B_obs
+    assert Bo.shape == (9, oracle_m3.n)
+    assert np.allclose(Bo.sum(axis=1), 1.0, atol=1e-13)
+    assert Bo.min() >= 0
+    # a dof belongs to at most two sub-domains (post / sub-fin interface) in both
+    assert (B > 0).sum(axis=0).max() <= 2 and (Bo > 0).sum(axis=0).max() <= 2
+
+
+def test_reference_B_obs_phi_identity(ref):
+    """averaged_affine_ROM.py:212: B_obs_phi = np.dot(B_obs, phi) on the shipped files (first 8 columns)."""
+    B = _shipped_B_obs(ref)
+    for name in ("five", "nine"):
+        assert tuple(ref[f"phi_{name}_shape"]) == (1446, 81)
+        got = np.dot(B, ref[f"phi_{name}_head"])
+        assert np.allclose(got, ref[f"B_obs_phi_{name}_head"], rtol=1e-13, atol=1e-16)
+
+
+def test_oracle_golden_regression(gold, oracle_m1):
+    o = oracle_m1
+    for s, t in enumerate(gold["theta"]):
+        assert relerr(o.qoi_operator(o.forward_nine_param(t)), gold["qoi_affine"][s]) < 1e-12
+        wr = o.forward_nine_param_reduced(t, gold["phi"])
+        assert relerr(o.qoi_reduced(wr, gold["phi"]), gold["qoi_rom"][s]) < 1e-9
+    assert np.allclose(o.forward_nine_param(gold["theta"][0]), gold["w_affine0"], rtol=1e-12, atol=1e-15)
+    for s, k in enumerate(gold["k5"]):
+        assert relerr(o.qoi_operator(o.forward_five_param_affine(k)), gold["qoi_five"][s]) < 1e-12
+    for s, k in enumerate(gold["k_nodal"]):
+        assert relerr(o.qoi_operator(o.forward(k)), gold["qoi_nodal"][s]) < 1e-12
+        assert relerr(o.subfin_avg_op(k), gold["theta_of_k"][s]) < 1e-13
+    assert np.array_equal(o.nine_param_to_function(gold["theta"][0]), gold["nine_to_fn"])
+
+
+def test_invariants(oracle_m2):
+    o = oracle_m2
+    ones = np.ones(o.n)
+    for K in o.K_q:                                   # stiffness annihilates constants, symmetric
+        assert np.abs(K @ ones).max() < 1e-12
+        assert abs(K - K.T).max() < 1e-14
+    assert abs(o.B.sum() - 1.0) < 1e-14               # |Gamma_root| = 1
+    rng = np.random.default_rng(0)
+    theta = rng.uniform(0.1, 3.5, 9)
+    w = o.forward_nine_param(theta)
+    assert abs(o.Bi * ones @ (o.M_robin @ w) - 1.0) < 1e-11     # energy balance
+    assert w.min() > 0
+    # five-parameter problem is mirror symmetric
+    q = o.qoi_operator(o.forward_five_param_affine([0.4, 0.6, 0.8, 1.0, 0.2]))
+    assert np.allclose(q[:4], q[:4:-1], rtol=1e-10)
+    # markers: conforming mesh -> no unmarked cell; areas of the nine rectangles
+    assert o.markers.min() == 1
+    assert np.allclose(o.fin_area, [0.625] * 4 + [4.0] + [0.625] * 4)
+    # C averages: sums to one
+    assert abs(o.C.sum() - 1.0) < 1e-13 and abs(o.domain_measure - 9.0) < 1e-12
+
+
+def test_f1_vs_f2(oracle_m2):
+    """SURVEY Q-2: nodal interpolation of a piecewise constant field (F1) differs from the affine model (F2), but
+    a CONSTANT field gives identical operators."""
+    o = oracle_m2
+    A1 = o.matrix_nodal(np.full(o.n, 1.7))
+    A2 = o.matrix_affine(np.full(9, 1.7))
+    assert abs(A1 - A2).max() < 1e-12
+    theta = np.array([0.5, 1.0, 1.5, 2.0, 2.5, 3.0, 0.3, 0.8, 1.2])
+    w1 = o.forward(o.nine_param_to_function(theta))
+    w2 = o.forward_nine_param(theta)
+    assert 1e-4 < np.abs(w1 - w2).max()
+
+
+def test_rom_reproduces_snapshots(oracle_m1):
+    """LSPG with a basis containing the exact solution returns it (residual zero)."""
+    o = oracle_m1
+    rng = np.random.default_rng(1)
+    theta = rng.uniform(0.5, 2.0, 9)
+    w = o.forward_nine_param(theta)
+    phi = np.column_stack([w, rng.standard_normal((o.n, 3))])
+    wr = o.forward_nine_param_reduced(theta, phi)
+    assert np.allclose(phi @ wr, w, rtol=1e-8, atol=1e-10)
+
+
+def test_cov_chol(oracle_m1):
+    from oracle.thermal_fin_oracle import make_cov_chol, sample_field
+    for kern in ("m52", "m32", "sq_exp"):
+        chol = make_cov_chol(oracle_m1.coords, kern, 1.6)
+        assert np.allclose(chol, np.triu(chol))                       # scipy returns the UPPER factor
+        cov = chol.T @ chol
+        assert np.allclose(np.diag(cov), 1.0 + (1e-5 if kern == "sq_exp" else 0.0), atol=1e-10)
+    k = sample_field(chol, np.zeros(oracle_m1.n))
+    assert np.array_equal(k, np.ones(oracle_m1.n))

@@ -16,8 +16,8 @@ theta = rng.uniform(0.1, 1.0, (N, 5)); theta = np.concatenate([theta, theta[:, 3
 th = torch.tensor(theta, device="cuda"); qoi = torch.empty((N, 9), device="cuda", dtype=torch.float64)
 it = torch.empty(N, device="cuda", dtype=torch.int32)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream; assert st != 0
-for R in (0, 3, 4, 5, 6, 8):
-    h.set_int("pcg_rows_per_thread", R)
+for R, WR in ((0, -1), (5, 0), (6, 0), (8, 0), (3, 1), (4, 1)):
+    h.set_int("pcg_rows_per_thread", R); h.set_int("pcg_reg_slots", WR)
     try:
         for rep in range(2):
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
@@ -25,10 +25,11 @@ for R in (0, 3, 4, 5, 6, 8):
             h.fom_affine_raw(th.data_ptr(), N, 0, 1, 1e-12, 20000, qoi=qoi.data_ptr(), iters=it.data_ptr(), stream=st)
             e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        print(f"K1 R={R} T={h.get_int('pcg_threads')} R_used={h.get_int('pcg_rows_per_thread')} occ={h.get_int('pcg_ctas_per_sm')} "
-              f"smem={h.get_int('pcg_smem_bytes')} W={h.get_int('ell_width')}: {ms:.2f} ms, {N/ms*1e3:.0f} solves/s, mean iters {it.float().mean().item():.1f}")
+        print(f"K1 R={R} WR={WR}: T={h.get_int('pcg_threads')} R_used={h.get_int('pcg_rows_per_thread')} occ={h.get_int('pcg_ctas_per_sm')} "
+              f"smem={h.get_int('pcg_smem_bytes')} W={h.get_int('ell_width')} WT={h.get_int('pcg_ell_width_compiled')} regslots={h.get_int('pcg_reg_slots')}: {ms:.2f} ms, {N/ms*1e3:.0f} solves/s, mean iters {it.float().mean().item():.1f}")
     except Exception as ex:
-        print("K1 R=", R, "failed:", ex)
+        print("K1 R=", R, WR, "failed:", ex)
+h.set_int("pcg_reg_slots", -1)
 h.set_int("pcg_rows_per_thread", 0)
 NR = int(os.environ.get("PROBE_NR", 200000))
 thr = torch.tensor(rng.uniform(0.1, 3.5, (NR, 9)), device="cuda"); qr = torch.empty((NR, 9), device="cuda", dtype=torch.float64)
