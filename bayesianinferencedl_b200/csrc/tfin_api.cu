@@ -9,6 +9,7 @@
 #include "pcg_small.cuh"
 #include "pcg_variants.h"
 #include "project.cuh"
+#include "pcg_stream.cuh"
 #include "rom.cuh"
 
 using namespace tfin;
@@ -41,6 +42,14 @@ struct tfin_ctx {
     std::vector<double> h_const;                  // vals[0] on the CSR pattern
     DevBuf<uint16_t> d_col;
     DevBuf<double> d_val, d_diag, d_rhs;
+    bool small_ok = false;                        // on-chip kernels usable (n <= 8191)
+    // ---- term-tagged CSR for the streaming kernel (K4)
+    DevBuf<int> d_srow, d_sdptr, d_sdterm;
+    DevBuf<int2> d_sent;
+    DevBuf<double> d_scoef, d_sdcoef, d_srhs, d_swork;
+    int pcg_path = 0;     // 0 auto, 1 on-chip, 2 streaming
+    int stream_tile = 0;  // 0 auto, else 8 / 16 / 32
+    int last_path = 0, last_tile = 0;
     // ---- observation / averaging
     int n_obs = 0, n_avg = 0;
     DevBuf<int> d_obs_ptr, d_obs_idx, d_avg_ptr, d_avg_idx;
@@ -104,6 +113,9 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
     for (auto* b : {&h->d_obs_ptr, &h->d_obs_idx, &h->d_avg_ptr, &h->d_avg_idx, &h->d_ncell, &h->d_dptr,
                     &h->d_dcell, &h->d_cells, &h->d_iters, &h->d_status})
         b->release();
+    for (auto* b : {&h->d_scoef, &h->d_sdcoef, &h->d_srhs, &h->d_swork}) b->release();
+    for (auto* b : {&h->d_srow, &h->d_sdptr, &h->d_sdterm}) b->release();
+    h->d_sent.release();
     h->d_col.release();
     h->d_ncol.release();
     h->d_counter.release();
@@ -125,7 +137,7 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
         return fail(TFIN_E_ARG, "tfin_set_operator: bad argument");
     if (n_terms < 1 || n_terms > TFIN_MAX_TERMS)
         return fail(TFIN_E_ARG, "tfin_set_operator: n_terms must be in [1, %d]", TFIN_MAX_TERMS);
-    if (n > 8191) return fail(TFIN_E_ARG, "tfin_set_operator: n = %d exceeds the on-chip PCG limit (8191)", n);
+    const bool small_ok = n <= 8191;  // uint16 byte offsets of the on-chip kernels
     if (row_ptr[0] != 0 || row_ptr[n] != nnz) return fail(TFIN_E_ARG, "tfin_set_operator: malformed row_ptr");
     const int ld = (n + 31) & ~31;
     // pass 1: diagonal positions, off-diagonal widths
@@ -170,10 +182,40 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
     h->h_row_ptr.assign(row_ptr, row_ptr + n + 1);
     h->h_col_idx.assign(col_idx, col_idx + nnz);
     h->h_const.assign(vals, vals + nnz);
-    if (int e = h->d_col.upload(col, h->stream)) return e;
-    if (int e = h->d_val.upload(val, h->stream)) return e;
-    if (int e = h->d_diag.upload(diag, h->stream)) return e;
+    h->small_ok = small_ok;
+    if (small_ok) {
+        if (int e = h->d_col.upload(col, h->stream)) return e;
+        if (int e = h->d_val.upload(val, h->stream)) return e;
+        if (int e = h->d_diag.upload(diag, h->stream)) return e;
+    }
     if (int e = h->d_rhs.upload(b, h->stream)) return e;
+    {   // term-tagged CSR (col, term, coef): only the non-zero (entry, term) pairs, diagonal included
+        std::vector<int> srow(n + 1, 0), sdptr(n + 1, 0), sdterm;
+        std::vector<int2> sent;
+        std::vector<double> scoef, sdcoef, srhs(rhs, rhs + n);
+        for (int i = 0; i < n; ++i) {
+            for (int j = row_ptr[i]; j < row_ptr[i + 1]; ++j)
+                for (int t = 0; t < n_terms; ++t) {
+                    const double v = vals[(size_t)t * nnz + j];
+                    if (v == 0.0) continue;
+                    sent.push_back(make_int2(col_idx[j], t));
+                    scoef.push_back(v);
+                    if (col_idx[j] == i) {
+                        sdterm.push_back(t);
+                        sdcoef.push_back(v);
+                    }
+                }
+            srow[i + 1] = (int)sent.size();
+            sdptr[i + 1] = (int)sdterm.size();
+        }
+        if (int e = h->d_srow.upload(srow, h->stream)) return e;
+        if (int e = h->d_sent.upload(sent, h->stream)) return e;
+        if (int e = h->d_scoef.upload(scoef, h->stream)) return e;
+        if (int e = h->d_sdptr.upload(sdptr, h->stream)) return e;
+        if (int e = h->d_sdterm.upload(sdterm, h->stream)) return e;
+        if (int e = h->d_sdcoef.upload(sdcoef, h->stream)) return e;
+        if (int e = h->d_srhs.upload(srhs, h->stream)) return e;
+    }
     TFIN_CUDA(cudaStreamSynchronize(h->stream));
     h->n_cells = 0;  // a new operator invalidates the nodal structures
     return 0;
@@ -221,6 +263,8 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
     CHECK_HANDLE(h);
     if (h->n <= 0) return fail(TFIN_E_STATE, "tfin_set_cells: call tfin_set_operator first");
     if (n_cells <= 0 || !cells || !Ke) return fail(TFIN_E_ARG, "tfin_set_cells: bad argument");
+    if (!h->small_ok)
+        return fail(TFIN_E_STATE, "tfin_set_cells: the nodal-conductivity kernel is on-chip only (n <= 8191), n = %d", h->n);
     const int n = h->n, ld = h->ld;
     const std::vector<int32_t>& rp = h->h_row_ptr;
     const std::vector<int32_t>& ci = h->h_col_idx;
@@ -409,6 +453,7 @@ static int launch_pcg(tfin_ctx* h, bool nodal, const double* d_in, int in_stride
     h->last_smem = best.smem;
     h->last_WT = best.v->WT;
     h->last_WR = best.v->WR;
+    h->last_path = 1;
 
     TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
     CsrRows obs{h->n_obs, h->d_obs_ptr.p, h->d_obs_idx.p, h->d_obs_val.p};
@@ -439,6 +484,31 @@ static int launch_pcg(tfin_ctx* h, bool nodal, const double* d_in, int in_stride
     void* args[] = {&op, &obs, &io};
     TFIN_CUDA(cudaLaunchKernel(best.v->func, dim3(grid), dim3(best.T), args, best.smem, st));
     h->launches += 1;
+    return 0;
+}
+
+static int launch_pcg_stream(tfin_ctx* h, const double* d_in, int in_stride, int64_t N, double tol, int maxit,
+                             double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres,
+                             cudaStream_t st) {
+    int S = h->stream_tile;
+    if (S == 0) S = N >= (int64_t)32 * h->sm_count ? 32 : (N >= (int64_t)16 * h->sm_count ? 16 : 8);
+    if (S != 8 && S != 16 && S != 32) return fail(TFIN_E_ARG, "stream_tile must be 8, 16 or 32");
+    const int64_t n_tiles = (N + S - 1) / S;
+    const int grid = (int)std::min<int64_t>(n_tiles, h->sm_count);
+    if (int e = h->d_swork.reserve((size_t)grid * 4 * h->n * S)) return e;
+    TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
+    StreamOp op{h->n, h->n_terms, h->d_srow.p, h->d_sent.p, h->d_scoef.p, h->d_sdptr.p, h->d_sdterm.p,
+                h->d_sdcoef.p, h->d_srhs.p};
+    CsrRows obs{h->n_obs, h->d_obs_ptr.p, h->d_obs_idx.p, h->d_obs_val.p};
+    PcgIO io{d_in, (long long)N, in_stride, tol * tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres,
+             h->d_counter.p};
+    if (S == 8) pcg_stream_kernel<8><<<grid, 1024, 0, st>>>(op, obs, io, h->d_swork.p);
+    else if (S == 16) pcg_stream_kernel<16><<<grid, 1024, 0, st>>>(op, obs, io, h->d_swork.p);
+    else pcg_stream_kernel<32><<<grid, 1024, 0, st>>>(op, obs, io, h->d_swork.p);
+    TFIN_CUDA(cudaGetLastError());
+    h->launches += 1;
+    h->last_path = 2;
+    h->last_tile = S;
     return 0;
 }
 
@@ -543,7 +613,12 @@ static int fom_common(tfin_handle_t h, bool nodal_op, const double* in, int64_t 
     if (int e = sg.out_alloc(iters_out, (size_t)N, h->d_iters, &d_iters)) return e;
     if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
     if (int e = sg.out_alloc(relres_out, (size_t)N, h->d_relres, &d_relres)) return e;
-    int rc = launch_pcg(h, nodal_op, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st);
+    const bool use_stream = !nodal_op && (h->pcg_path == 2 || (h->pcg_path == 0 && !h->small_ok));
+    if (!use_stream && !h->small_ok)
+        return fail(TFIN_E_STATE, "on-chip PCG needs n <= 8191 (n = %d); use the streaming path", h->n);
+    int rc = use_stream
+                 ? launch_pcg_stream(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st)
+                 : launch_pcg(h, nodal_op, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st);
     if (rc) return rc;
     if (int e = sg.out_copy(w_out, (size_t)N * h->n, d_w)) return e;
     if (int e = sg.out_copy(qoi_out, (size_t)N * h->n_obs, d_qoi)) return e;
@@ -649,6 +724,8 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
     if (k == "pcg_ell_width_compiled") return h->last_WT;
     if (k == "pcg_reg_slots") return h->last_WR;
     if (k == "rom_chunk") return h->rom_chunk;
+    if (k == "pcg_path") return h->last_path;
+    if (k == "stream_tile") return h->last_tile;
     return -1;
 }
 
@@ -665,6 +742,14 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
     }
     if (k == "pcg_reg_slots") {
         h->pcg_WR = (int)value;
+        return 0;
+    }
+    if (k == "pcg_path") {
+        h->pcg_path = (int)value;
+        return 0;
+    }
+    if (k == "stream_tile") {
+        h->stream_tile = (int)value;
         return 0;
     }
     return fail(TFIN_E_ARG, "tfin_set_int: unknown key '%s'", key);

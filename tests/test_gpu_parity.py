@@ -180,3 +180,52 @@ def test_other_mesh_sizes(m, request):
         assert relerr(qr[s], orc.qoi_reduced(orc.forward_nine_param_reduced(theta[s], phi), phi)) <= 1e-8
     for s in range(3):
         assert relerr(qn[s], orc.qoi_operator(orc.forward(k[s]))) <= RTOL_FOM
+
+
+@pytest.mark.parametrize("tile", [8, 16, 32])
+def test_stream_kernel_matches_onchip_and_oracle(rom_m3, oracle_m3, tile):
+    """K4 (HBM-streaming, matrix-free, interleaved tiles) forced on the small mesh: same observables as the on-chip
+    kernel and the oracle; 70 samples = partial last tile."""
+    rng = np.random.default_rng(31)
+    theta = rng.uniform(0.1, 10.0, (70, 9))
+    h = rom_m3.handle
+    ref = h.fom_affine(theta)
+    try:
+        h.set_int("pcg_path", 2)
+        h.set_int("stream_tile", tile)
+        out = h.fom_affine(theta, want_w=True)
+        assert h.get_int("pcg_path") == 2 and h.get_int("stream_tile") == tile
+    finally:
+        h.set_int("pcg_path", 0)
+        h.set_int("stream_tile", 0)
+    assert np.all(out["status"] == 0) and np.all(out["relres"] < 1e-10)
+    assert np.max(np.abs(out["iters"] - ref["iters"])) <= 3
+    assert relerr(out["qoi"], ref["qoi"]) <= 1e-10
+    for s in (0, 33, 69):
+        w_ref = oracle_m3.forward_nine_param(theta[s])
+        assert np.max(np.abs(out["w"][s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref))
+        assert relerr(out["qoi"][s], oracle_m3.qoi_operator(w_ref)) <= RTOL_FOM
+
+
+def test_stream_kernel_refined_mesh():
+    """n = 10 017 (m = 8) exceeds the on-chip limit -> the streaming kernel is selected automatically."""
+    from bayesianinferencedl_b200 import _cabi, get_space
+    from bayesianinferencedl_b200.assembly import build_operators
+    from oracle.thermal_fin_oracle import FinOracle
+    V = get_space(40, m=8)
+    ops = build_operators(V)
+    assert ops.n == 10017
+    h = _cabi.TfinHandle(0)
+    h.set_operator(ops.row_ptr, ops.col_idx, ops.vals, ops.rhs)
+    h.set_observation(*ops.obs_csr())
+    rng = np.random.default_rng(2)
+    theta = rng.uniform(0.1, 10.0, (12, 9))
+    out = h.fom_affine(theta, want_w=True)
+    assert h.get_int("pcg_path") == 2
+    assert np.all(out["status"] == 0)
+    orc = FinOracle(ops.coords, ops.cells)
+    for s in (0, 5, 11):
+        w_ref = orc.forward_nine_param(theta[s])
+        assert np.max(np.abs(out["w"][s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref))
+        assert relerr(out["qoi"][s], orc.qoi_operator(w_ref)) <= RTOL_FOM
+    h.close()
