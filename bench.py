@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "thermal-fin forward solves/sec (FOM & ROM) at 1/2/4/8 B200; % HBM roofline"
 RESOLUTION = 40                 # reference's get_space(40); structured m = 3 -> n = 1597
-FOM_SEED, ROM_SEED = 1, 0
+FOM_SEED, ROM_SEED, REF_SEED, NODAL_SEED = 1, 0, 2, 3
+REFINED_M = 26                  # n = 99 945
 TOL = 1e-12
 
 
@@ -39,6 +40,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--fom-batch", type=int, default=100_000, help="FOM samples per GPU per step")
     ap.add_argument("--rom-batch", type=int, default=1_000_000, help="ROM samples per GPU per step")
+    ap.add_argument("--refined-batch", type=int, default=1184,
+                    help="refined-mesh (m=26, n=99 945) FOM samples per GPU per step; 0 disables the leg")
+    ap.add_argument("--refined-steps", type=int, default=2)
+    ap.add_argument("--nodal-batch", type=int, default=100_000,
+                    help="nodal Gaussian-field FOM samples per GPU per step; 0 disables the leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-fom-sample", type=int, default=2048)
     ap.add_argument("--cpu-rom-sample", type=int, default=2048)
@@ -278,14 +284,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, hh=None):
         """W warm-up + EXACTLY K steps bracketed by barrier + synchronize; CUDA events on the launching stream;
         L2 flushed between steps; returns max-over-ranks milliseconds and this rank's launch count."""
         for _ in range(warmup):
             fn()
             flush.fill_(1)
         barrier()
-        l0 = h.kernel_launches()
+        hh = hh or h
+        l0 = hh.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -296,7 +303,7 @@ def run_b200(args):
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=f64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), h.kernel_launches() - l0
+        return float(ms.item()), hh.kernel_launches() - l0
 
     # flush cost (inside the bracket) measured once so it can be reported
     timed(lambda: None, 2, 1)
@@ -310,6 +317,101 @@ def run_b200(args):
     ms_r, launches_r = timed(rom_dev, K, Wm)
     ms_fe, launches_fe = timed(fom_e2e, K, Wm)
     ms_re, launches_re = timed(rom_e2e, K, Wm)
+
+    # ---- config[4] nodal Gaussian-field conductivity: k = exp(0.5 chol^T z), Matern-5/2, l = 1.6 (fields are
+    # generated on the device with torch -- input generation, not the measured path), in-kernel assembly + PCG
+    nodal = None
+    if args.nodal_batch > 0:
+        from bayesianinferencedl_b200 import Fin, make_cov_chol
+        NN = args.nodal_batch
+        fin = Fin(V, device=local_rank)
+        chol = torch.from_numpy(make_cov_chol(V, length=1.6)).to(dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(NODAL_SEED + rank)
+        k_dev = torch.empty((NN, n), dtype=f64, device=dev)
+        for lo in range(0, NN, 20000):
+            z = torch.randn((min(20000, NN - lo), n), dtype=f64, device=dev, generator=gen)
+            k_dev[lo:lo + len(z)] = torch.exp(0.5 * (z @ chol))
+        k_host = torch.empty((NN, n), dtype=f64).pin_memory()
+        k_host.copy_(k_dev)
+        q_n = torch.empty((NN, n_obs), dtype=f64, device=dev)
+        it_n = torch.empty(NN, dtype=torch.int32, device=dev)
+        st_n = torch.empty(NN, dtype=torch.int32, device=dev)
+        hn = fin.handle
+
+        def nodal_dev():
+            hn.fom_nodal_raw(k_dev.data_ptr(), NN, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_n.data_ptr(),
+                             iters=it_n.data_ptr(), status=st_n.data_ptr(), stream=sp)
+            return gather_rows(q_n, NN * world) if world > 1 else q_n
+
+        q_n_host = torch.empty((NN, n_obs), dtype=f64).pin_memory()
+        st_n_host = torch.empty(NN, dtype=torch.int32).pin_memory()
+
+        def nodal_e2e():
+            hn.fom_nodal_raw(k_host.data_ptr(), NN, _cabi.MEM_HOST, TOL, 20000, qoi=q_n_host.data_ptr(),
+                             status=st_n_host.data_ptr(), stream=sp)
+
+        ms_n, ln = timed(nodal_dev, K, Wm, hn)
+        ms_ne, _ = timed(nodal_e2e, K, Wm, hn)
+        it_sum_n = int(it_n.to(torch.int64).sum().item())
+        n_cells = fin.ops.n_cells
+        step_n = ms_n / K - flush_ms
+        nodal = {
+            "value": world * NN / (step_n * 1e-3), "unit": "solves/s", "ms_per_step": step_n,
+            "workload": f"config[4]: {NN} Matern-5/2 (l=1.6) nodal fields per GPU, per-sample in-kernel FEM assembly "
+                        f"+ PCG, mesh m=3",
+            "mean_pcg_iters": it_sum_n / NN, "all_converged": bool((st_n == 0).all().item()),
+            "e2e": {"value": world * NN / ((ms_ne / K - flush_ms) * 1e-3), "unit": "solves/s",
+                    "h2d_bytes_per_step": NN * n * 8, "d2h_bytes_per_step": NN * (n_obs * 8 + 4),
+                    "ms_per_step": ms_ne / K - flush_ms},
+            "gpu_launches": ln,
+            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": None,
+                         "achieved": ((88.0 * n + 8.0 * n_cells) * it_sum_n + NN * n * 8.0) / (step_n * 1e-3) / 1e9,
+                         "note": "algorithmic bytes (88 n + 8 n_cells) per iteration + the k field read once; "
+                                 "on-chip kernel, see roofline.note"},
+        }
+        del k_dev, k_host, chol
+        fin.handle.close()
+
+    # ---- config[3] refined mesh (m=26, n=99 945), nine-param FOM: the genuinely HBM-streaming PCG kernel
+    refined = None
+    if args.refined_batch > 0:
+        from bayesianinferencedl_b200.assembly import build_operators
+        NRf = args.refined_batch
+        Vr = get_space(RESOLUTION, m=REFINED_M)
+        opsr = build_operators(Vr)
+        hr = _cabi.TfinHandle(local_rank)
+        hr.set_operator(opsr.row_ptr, opsr.col_idx, opsr.vals, opsr.rhs)
+        hr.set_observation(*opsr.obs_csr())
+        th_ref_host = torch.from_numpy(np.random.default_rng(REF_SEED + rank).uniform(0.1, 10.0, (NRf, 9))).pin_memory()
+        th_ref = th_ref_host.to(dev)
+        q_ref = torch.empty((NRf, 9), dtype=f64, device=dev)
+        it_ref = torch.empty(NRf, dtype=torch.int32, device=dev)
+        st_ref = torch.empty(NRf, dtype=torch.int32, device=dev)
+
+        def ref_dev():
+            hr.fom_affine_raw(th_ref.data_ptr(), NRf, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, 50000,
+                              qoi=q_ref.data_ptr(), iters=it_ref.data_ptr(), status=st_ref.data_ptr(), stream=sp)
+            return gather_rows(q_ref, NRf * world) if world > 1 else q_ref
+
+        ms_ref, l_ref = timed(ref_dev, args.refined_steps, 1, hr)
+        step_ref = ms_ref / args.refined_steps - flush_ms
+        it_sum_ref = int(it_ref.to(torch.int64).sum().item())
+        bytes_ref = 88.0 * opsr.n * it_sum_ref
+        ach = bytes_ref / (step_ref * 1e-3) / 1e9
+        refined = {
+            "value": world * NRf / (step_ref * 1e-3), "unit": "solves/s", "ms_per_step": step_ref,
+            "steps": args.refined_steps, "warmup": 1,
+            "workload": f"config[3]: refined mesh m={REFINED_M}, n={opsr.n} dofs, nine-param theta~U(0.1,10), "
+                        f"{NRf} samples per GPU per step, streaming PCG kernel (tile {hr.get_int('stream_tile')})",
+            "mean_pcg_iters": it_sum_ref / NRf, "all_converged": bool((st_ref == 0).all().item()),
+            "gpu_launches": l_ref,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": None, "unit": "GB/s", "frac": None,
+                         "kernel": "pcg_stream_kernel", "algorithmic_bytes_per_launch": bytes_ref,
+                         "note": "88*n bytes per iteration per sample (SURVEY 8d), each sample counted with its own "
+                                 "iteration count; vectors stream from HBM every pass (working set >> L2)"},
+        }
+        hr.close()
     clocks = sampler.stop()
 
     # ---- kernel-only duration of the dominant kernel (PCG) for the roofline: one more step, events tight
@@ -353,15 +455,33 @@ def run_b200(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    traffic = None
+    traffic, traffic_note, ncu_t = None, None, {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("pcg_affine_kernel")
+        ncu_t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        t = ncu_t["pcg_kernel"]
+        # DRAM traffic of the on-chip kernel: operator arrays once + 152 B/sample, scaled to this launch's batch
+        traffic = t["dram_bytes"] + max(0, NF - t["launch_samples"]) * 152.0
+        traffic_note = (f"ncu --set full capture of a {t['launch_samples']}-sample launch: {t['dram_bytes']:.0f} B "
+                        f"(profiles/r1_ncu_summary.md), plus 152 B/sample of theta/qoi for the larger batch")
     except Exception:
         pass
 
     # algorithmic bytes of one PCG launch: 88 n bytes per iteration per sample + theta in, qoi out
     alg_bytes = 88.0 * n * iters_sum + NF * (9 * 8 + n_obs * 8 + 8)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    if refined is not None:
+        refined["roofline"]["peak"] = hbm_peak
+        refined["roofline"]["frac"] = refined["roofline"]["achieved"] / hbm_peak
+        refined["roofline"]["peak_source"] = peak_src
+        ts = ncu_t.get("pcg_stream_kernel")
+        refined["roofline"]["traffic"] = (ts["ratio_to_algorithmic"] * refined["roofline"]["algorithmic_bytes_per_launch"]
+                                          if ts else None)
+        refined["roofline"]["traffic_note"] = (
+            f"ncu capture ({ts['launch']}): dram bytes / algorithmic bytes = {ts['ratio_to_algorithmic']:.4f}, applied "
+            f"to this launch" if ts else None)
+    if nodal is not None:
+        nodal["roofline"]["peak"] = hbm_peak
+        nodal["roofline"]["frac"] = nodal["roofline"]["achieved"] / hbm_peak
     step_ms_f = (ms_f / K) - flush_ms
     step_ms_r = (ms_r / K) - flush_ms
     fom_rate = world * NF / (step_ms_f * 1e-3)
@@ -376,7 +496,7 @@ def run_b200(args):
         "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": "FOM leg (value): config[2] five-param batched FOM, QoI = subfin averages; ROM leg (rom): "
-                        "config[1] nine-param batched ROM",
+                        "config[1] nine-param batched ROM; fom_refined: config[3]; fom_nodal: config[4]",
             "fom_samples_per_gpu_per_step": NF, "rom_samples_per_gpu_per_step": NR,
             "mesh": f"structured conforming fin mesh m=3, n={n} dofs (reference mshr mesh is not shipped)",
             "n_r": n_r, "pcg_tol": TOL, "mean_pcg_iters": iters_sum / NF, "all_converged": ok_f and ok_r,
@@ -388,7 +508,7 @@ def run_b200(args):
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": traffic, "kernel": "pcg_affine_kernel", "kernel_ms": k_ms,
+            "traffic": traffic, "traffic_note": traffic_note, "kernel": "pcg_kernel<affine>", "kernel_ms": k_ms,
             "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
             "note": "algorithmic bytes = 88*n*iterations per solve (SURVEY 8d); at n=1597 the CG vectors and the "
                     "per-sample operator live in shared memory/registers, so achieved/peak is NOT bounded by 1 "
@@ -400,6 +520,8 @@ def run_b200(args):
                 "api": "tfin_fom_affine(TFIN_MEM_HOST) on pinned host buffers (the call AffineROMFin makes)"},
         "gpu_launches": launches_f,
         "clocks": clocks,
+        "fom_refined": refined,
+        "fom_nodal": nodal,
         "rom": {
             "value": rom_rate, "unit": "solves/s", "ms_per_step": step_ms_r,
             "e2e": {"value": rom_e2e_rate, "unit": "solves/s", "h2d_bytes_per_step": NR * 9 * 8,
