@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(256) rom_combine_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------- R2
-// One warp per sample: left-looking Cholesky of the augmented packed matrix in shared memory, back
-// substitution, observation projection.  Lane l owns rows j + l + 32 m of the current column.
+// One warp per sample: panel-blocked left-looking Cholesky of the augmented packed matrix in shared memory, back
+// substitution, observation projection.
 template <int MAXM /* ceil((n_r+1)/32) */>
 __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict__ C, long long s_begin,
                                                        long long s_end, int nr, int n_obs,
@@ -113,63 +113,101 @@ __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict_
         for (int e = lane; e < Taug; e += 32) A[e] = ldg_stream(src + e);
         __syncwarp();
         int status = TFIN_STATUS_CONVERGED;
-        for (int j = 0; j < nr; ++j) {
-            const int oj = rom_col_off(j, nr);
-            double c0[MAXM], c1[MAXM];
+        // Panel-blocked left-looking Cholesky, NB = 4 columns at a time.  Lane l holds rows j0 + l + 32 m of all four
+        // panel columns in registers; one pass over the previous columns k < j0 updates the whole panel (3 + 4 loads
+        // for 12 FMAs), then the panel is factored in registers with shuffles and written back once.
+        for (int j0 = 0; j0 < nr; j0 += 4) {
+            const int ncol = min(4, nr - j0);
+            double c[4][MAXM];
 #pragma unroll
-            for (int m = 0; m < MAXM; ++m) {
-                const int i = j + lane + 32 * m;
-                c0[m] = i < nrow ? A[oj + lane + 32 * m] : 0.0;
-                c1[m] = 0.0;
-            }
-            int k = 0;
-            for (; k + 1 < j; k += 2) {
-                const int ok0 = rom_col_off(k, nr) + (j - k), ok1 = rom_col_off(k + 1, nr) + (j - k - 1);
-                const double l0 = A[ok0], l1 = A[ok1];
+            for (int cc = 0; cc < 4; ++cc) {
+                const int oc = rom_col_off(j0 + cc, nr) - cc;  // + (i - j0) addresses row i of column j0+cc
 #pragma unroll
                 for (int m = 0; m < MAXM; ++m) {
-                    const int i = j + lane + 32 * m;
-                    if (i < nrow) {
-                        c0[m] = fma(-A[ok0 + lane + 32 * m], l0, c0[m]);
-                        c1[m] = fma(-A[ok1 + lane + 32 * m], l1, c1[m]);
+                    const int i = j0 + lane + 32 * m;
+                    c[cc][m] = (cc < ncol && i < nrow && i >= j0 + cc) ? A[oc + lane + 32 * m] : 0.0;
+                }
+            }
+            // number of 32-row slabs that still contain rows (warp-uniform): skips the empty slabs' loads and FMAs
+            const int mact = min(MAXM, (nrow - j0 + 31) >> 5);
+#pragma unroll 4
+            for (int k = 0; k < j0; ++k) {
+                const int ok = rom_col_off(k, nr) + (j0 - k);  // row j0 of column k
+                double lk[MAXM], lj[4];
+#pragma unroll
+                for (int m = 0; m < MAXM; ++m)
+                    if (m < mact) lk[m] = (j0 + lane + 32 * m < nrow) ? A[ok + lane + 32 * m] : 0.0;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) lj[cc] = A[ok + (cc < ncol ? cc : 0)];
+#pragma unroll
+                for (int m = 0; m < MAXM; ++m)
+                    if (m < mact) {
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) c[cc][m] = fma(-lk[m], lj[cc], c[cc][m]);
                     }
-                }
-            }
-            if (k < j) {
-                const int ok0 = rom_col_off(k, nr) + (j - k);
-                const double l0 = A[ok0];
-#pragma unroll
-                for (int m = 0; m < MAXM; ++m) {
-                    const int i = j + lane + 32 * m;
-                    if (i < nrow) c0[m] = fma(-A[ok0 + lane + 32 * m], l0, c0[m]);
-                }
             }
 #pragma unroll
-            for (int m = 0; m < MAXM; ++m) c0[m] += c1[m];
-            const double d = __shfl_sync(0xffffffffu, c0[0], 0);
-            if (!(d > 0.0)) status = TFIN_STATUS_BREAKDOWN;
-            const double inv = rsqrt(d);   // correctly rounded enough: refined below
-            const double ljj = sqrt(d);
-            const double invl = inv * (2.0 - ljj * inv) ;  // one Newton step on 1/ljj
+            for (int cc = 0; cc < 4; ++cc) {
+                if (cc < ncol) {
+                    // updates from the already finished columns of this panel
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) {
+                        if (c2 < cc) {
+                            const double ljc = __shfl_sync(0xffffffffu, c[c2][0], cc);  // L[j0+cc][j0+c2]
+#pragma unroll
+                            for (int m = 0; m < MAXM; ++m) c[cc][m] = fma(-c[c2][m], ljc, c[cc][m]);
+                        }
+                    }
+                    const double d = __shfl_sync(0xffffffffu, c[cc][0], cc);
+                    if (!(d > 0.0)) status = TFIN_STATUS_BREAKDOWN;
+                    const double ljj = sqrt(d);
+                    const double inv0 = rsqrt(d);
+                    const double invl = inv0 * (2.0 - ljj * inv0);  // one Newton step on 1 / ljj
+                    const int oc = rom_col_off(j0 + cc, nr) - cc;
+#pragma unroll
+                    for (int m = 0; m < MAXM; ++m) {
+                        const int i = j0 + lane + 32 * m;
+                        c[cc][m] = (i == j0 + cc) ? ljj : c[cc][m] * invl;
+                        if (i < nrow && i >= j0 + cc) A[oc + lane + 32 * m] = c[cc][m];
+                    }
+                    if (lane == 0) dinv[j0 + cc] = invl;
+                }
+            }
+            __syncwarp();
+        }
+        // y = last row of the factor; back substitution L^T w = y.  y is lane-distributed in registers (lane l holds
+        // entries l + 32 m); step j broadcasts w_j by shuffle and every lane updates its entries i < j with
+        // L[j][i] (column i of the packed factor, offset j - i), loaded ahead of the dependent chain.
+        double yv[MAXM];
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            const int i = lane + 32 * m;
+            yv[m] = i < nr ? A[rom_col_off(i, nr) + (nr - i)] : 0.0;
+        }
+        for (int j = nr - 1; j >= 0; --j) {
+            double lji[MAXM];
 #pragma unroll
             for (int m = 0; m < MAXM; ++m) {
-                const int i = j + lane + 32 * m;
-                if (i < nrow) A[oj + lane + 32 * m] = (i == j) ? ljj : c0[m] * invl;
+                const int i = lane + 32 * m;
+                lji[m] = i < j ? A[rom_col_off(i, nr) + (j - i)] : 0.0;
             }
-            if (lane == 0) dinv[j] = invl;
-            __syncwarp();
+            double yj = 0.0;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m)
+                if ((j >> 5) == m) yj = yv[m];
+            const double wj = __shfl_sync(0xffffffffu, yj, j & 31) * dinv[j];
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                const int i = lane + 32 * m;
+                yv[m] = (i == j) ? wj : fma(-lji[m], wj, yv[m]);
+            }
         }
-        // y = last row of the factor; back substitution L^T w = y (column j of L is contiguous)
-        for (int j = lane; j < nr; j += 32) wv[j] = A[rom_col_off(j, nr) + (nr - j)];
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            const int i = lane + 32 * m;
+            if (i < nr) wv[i] = yv[m];
+        }
         __syncwarp();
-        for (int j = nr - 1; j >= 0; --j) {
-            const double wj = wv[j] * dinv[j];
-            __syncwarp();
-            if (lane == 0) wv[j] = wj;
-            // y_i -= L[j][i] w_j for i < j   (L[j][i] sits in column i at offset j - i)
-            for (int i = lane; i < j; i += 32) wv[i] = fma(-A[rom_col_off(i, nr) + (j - i)], wj, wv[i]);
-            __syncwarp();
-        }
         if (status_out && lane == 0) status_out[s] = status;
         if (wr_out)
             for (int j = lane; j < nr; j += 32) wr_out[s * nr + j] = wv[j];

@@ -229,3 +229,37 @@ def test_stream_kernel_refined_mesh():
         assert np.max(np.abs(out["w"][s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref))
         assert relerr(out["qoi"][s], orc.qoi_operator(w_ref)) <= RTOL_FOM
     h.close()
+
+
+def test_unstructured_nonconforming_mesh():
+    """Stand-in for the reference's mshr mesh (tests/meshes.py): unstructured, vertex degree up to 9, cells straddling
+    x = 2.5 / 3.5 keep marker 0 and carry no conductivity in the affine model (SURVEY Q-1).  Affine FOM, nodal FOM and
+    ROM against the oracle."""
+    from meshes import unstructured_fin
+    from bayesianinferencedl_b200 import AffineROMFin, Fin, FinSpace
+    from oracle.thermal_fin_oracle import FinOracle, pod_basis
+    coords, cells = unstructured_fin()
+    V = FinSpace.from_mesh(coords, cells)
+    orc = FinOracle(coords, cells)
+    phi = pod_basis(orc, n_snapshots=60, basis_size=30, seed=3)
+    rom = AffineROMFin(V, None, phi)
+    fin = Fin(V)
+    assert rom.handle.get_int("ell_width") >= 8
+    rng = np.random.default_rng(9)
+    theta = rng.uniform(0.1, 3.5, (9, 9))
+    q = rom.forward_nine_param_qoi(theta)
+    qr = rom.forward_reduced_qoi(theta)
+    k = np.exp(0.4 * rng.standard_normal((4, orc.n)))
+    qn = fin.forward_qoi(k)
+    for s in range(len(theta)):
+        assert relerr(q[s], orc.qoi_operator(orc.forward_nine_param(theta[s]))) <= RTOL_FOM
+        assert relerr(qr[s], orc.qoi_reduced(orc.forward_nine_param_reduced(theta[s], phi), phi)) <= 1e-9
+    for s in range(len(k)):
+        assert relerr(qn[s], orc.qoi_operator(orc.forward(k[s]))) <= RTOL_FOM
+    # the streaming kernel on the same mesh
+    h = rom.handle
+    try:
+        h.set_int("pcg_path", 2)
+        assert relerr(h.fom_affine(theta)["qoi"], q) <= 1e-10
+    finally:
+        h.set_int("pcg_path", 0)
