@@ -29,6 +29,57 @@ const PcgVariant* pcg_variants(int group, int nodal, int* count) {
 }
 }  // namespace tfin
 
+// Reverse Cuthill-McKee ordering of the (symmetric) CSR pattern: order[new] = old.  Every connected component is
+// started from a pseudo-peripheral node (repeated BFS from the farthest minimum-degree node).
+static std::vector<int> rcm_order(int n, const int32_t* rp, const int32_t* ci) {
+    std::vector<int> order, level(n, -1), deg(n);
+    order.reserve(n);
+    for (int i = 0; i < n; ++i) deg[i] = rp[i + 1] - rp[i];
+    std::vector<char> done(n, 0);
+    std::vector<int> comp, nbr;
+    auto bfs = [&](int start, std::vector<int>& out) -> int {  // BFS over not-yet-ordered nodes; returns eccentricity
+        out.clear();
+        out.push_back(start);
+        level[start] = 0;
+        for (size_t h = 0; h < out.size(); ++h) {
+            const int u = out[h];
+            nbr.clear();
+            for (int j = rp[u]; j < rp[u + 1]; ++j) {
+                const int v = ci[j];
+                if (v != u && !done[v] && level[v] < 0) {
+                    level[v] = level[u] + 1;
+                    nbr.push_back(v);
+                }
+            }
+            std::sort(nbr.begin(), nbr.end(), [&](int a, int b) { return deg[a] != deg[b] ? deg[a] < deg[b] : a < b; });
+            out.insert(out.end(), nbr.begin(), nbr.end());
+        }
+        const int ecc = level[out.back()];
+        return ecc;
+    };
+    for (int seed = 0; seed < n; ++seed) {
+        if (done[seed]) continue;
+        int start = seed, ecc = -1;
+        for (int round = 0; round < 8; ++round) {
+            const int e = bfs(start, comp);
+            int far = comp.back();
+            for (int v : comp)
+                if (level[v] == e && deg[v] < deg[far]) far = v;
+            for (int v : comp) level[v] = -1;
+            if (e <= ecc) break;
+            ecc = e;
+            start = far;
+        }
+        bfs(start, comp);
+        for (int v : comp) {
+            done[v] = 1;
+            order.push_back(v);
+        }
+    }
+    std::reverse(order.begin(), order.end());
+    return order;
+}
+
 struct tfin_ctx {
     int device = 0;
     int sm_count = 0;
@@ -44,9 +95,18 @@ struct tfin_ctx {
     DevBuf<double> d_val, d_diag, d_rhs;
     bool small_ok = false;                        // on-chip kernels usable (n <= 8191)
     // ---- term-tagged CSR for the streaming kernel (K4)
-    DevBuf<int> d_srow, d_sdptr, d_sdterm;
-    DevBuf<int2> d_sent;
-    DevBuf<double> d_scoef, d_sdcoef, d_srhs, d_swork;
+    int s_ldr = 0, s_We = 0, s_bandwidth = 0;
+    bool stream_ok = false;
+    std::vector<int> h_sinv;       // caller's dof -> renumbered row of the streaming path
+    DevBuf<int> d_sperm, d_sobs_idx;
+    int stream_ring = -1;          // -1 auto (= direct gathers), 0 direct gathers, 1 shared-memory ring (opt-in)
+    int last_ring = 0;
+    DevBuf<uint32_t> d_scolterm;
+    DevBuf<unsigned char> d_scnt;
+    DevBuf<double> d_scoef, d_srhs, d_swork;
+    DevBuf<unsigned long long> d_sprof;  // CTA-0 clocks per pass (P1, P2, P3, iterations) when stream_prof is set
+    int stream_prof = 0;
+    int stream_pad_smem = 0;  // experiment knob: extra (unused) dynamic shared memory in KB
     int pcg_path = 0;     // 0 auto, 1 on-chip, 2 streaming
     int stream_tile = 0;  // 0 auto, else 8 / 16 / 32
     int last_path = 0, last_tile = 0;
@@ -113,9 +173,12 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
     for (auto* b : {&h->d_obs_ptr, &h->d_obs_idx, &h->d_avg_ptr, &h->d_avg_idx, &h->d_ncell, &h->d_dptr,
                     &h->d_dcell, &h->d_cells, &h->d_iters, &h->d_status})
         b->release();
-    for (auto* b : {&h->d_scoef, &h->d_sdcoef, &h->d_srhs, &h->d_swork}) b->release();
-    for (auto* b : {&h->d_srow, &h->d_sdptr, &h->d_sdterm}) b->release();
-    h->d_sent.release();
+    for (auto* b : {&h->d_scoef, &h->d_srhs, &h->d_swork}) b->release();
+    h->d_scolterm.release();
+    h->d_scnt.release();
+    h->d_sperm.release();
+    h->d_sobs_idx.release();
+    h->d_sprof.release();
     h->d_col.release();
     h->d_ncol.release();
     h->d_counter.release();
@@ -189,32 +252,66 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
         if (int e = h->d_diag.upload(diag, h->stream)) return e;
     }
     if (int e = h->d_rhs.upload(b, h->stream)) return e;
-    {   // term-tagged CSR (col, term, coef): only the non-zero (entry, term) pairs, diagonal included
-        std::vector<int> srow(n + 1, 0), sdptr(n + 1, 0), sdterm;
-        std::vector<int2> sent;
-        std::vector<double> scoef, sdcoef, srhs(rhs, rhs + n);
+    h->stream_ok = n < (1 << 24);
+    if (h->stream_ok) {  // term-tagged slot-major ELL for the streaming kernel: only non-zero (entry, term) pairs
+        struct Ent {
+            int col, term;
+            double coef;
+        };
+        // bandwidth-reducing renumbering (internal to the streaming path; callers keep their dof numbering)
+        const std::vector<int> perm = rcm_order(n, row_ptr, col_idx);  // new -> old
+        std::vector<int> inv(n);
+        for (int i = 0; i < n; ++i) inv[perm[i]] = i;
+        std::vector<std::vector<Ent>> rows(n);
+        int We = 1, bandwidth = 1;
         for (int i = 0; i < n; ++i) {
-            for (int j = row_ptr[i]; j < row_ptr[i + 1]; ++j)
-                for (int t = 0; t < n_terms; ++t) {
+            const int old = perm[i];
+            for (int t = 0; t < n_terms; ++t)  // sorted by term inside the row (theta is cached per term run)
+                for (int j = row_ptr[old]; j < row_ptr[old + 1]; ++j) {
                     const double v = vals[(size_t)t * nnz + j];
-                    if (v == 0.0) continue;
-                    sent.push_back(make_int2(col_idx[j], t));
-                    scoef.push_back(v);
-                    if (col_idx[j] == i) {
-                        sdterm.push_back(t);
-                        sdcoef.push_back(v);
-                    }
+                    if (v != 0.0) rows[i].push_back(Ent{inv[col_idx[j]], t, v});
                 }
-            srow[i + 1] = (int)sent.size();
-            sdptr[i + 1] = (int)sdterm.size();
+            std::stable_sort(rows[i].begin(), rows[i].end(),
+                             [](const Ent& a, const Ent& b) { return a.term != b.term ? a.term < b.term : a.col < b.col; });
+            for (const Ent& e : rows[i]) bandwidth = std::max(bandwidth, std::abs(e.col - i));
+            We = std::max(We, (int)rows[i].size());
         }
-        if (int e = h->d_srow.upload(srow, h->stream)) return e;
-        if (int e = h->d_sent.upload(sent, h->stream)) return e;
-        if (int e = h->d_scoef.upload(scoef, h->stream)) return e;
-        if (int e = h->d_sdptr.upload(sdptr, h->stream)) return e;
-        if (int e = h->d_sdterm.upload(sdterm, h->stream)) return e;
-        if (int e = h->d_sdcoef.upload(sdcoef, h->stream)) return e;
+        if (We > 255) return fail(TFIN_E_ARG, "tfin_set_operator: more than 255 term-tagged entries in one row");
+        We = (We + STREAM_KC - 1) / STREAM_KC * STREAM_KC;
+        const int ldr = (n + 511) & ~511;  // whole ring chunks for every tile width
+        std::vector<uint32_t> colterm((size_t)We * ldr);
+        std::vector<double> coef((size_t)We * ldr, 0.0);
+        std::vector<unsigned char> cnt(ldr, 1);
+        for (int i = 0; i < ldr; ++i) {
+            const int used = i < n ? (int)rows[i].size() : 0;
+            const uint32_t pad_term = used ? (uint32_t)rows[i][used - 1].term : 0u;
+            for (int k = 0; k < We; ++k) {
+                const size_t o = (size_t)k * ldr + i;
+                if (k < used) {
+                    colterm[o] = (uint32_t)rows[i][k].col | ((uint32_t)rows[i][k].term << 24);
+                    coef[o] = rows[i][k].coef;
+                } else {
+                    colterm[o] = (uint32_t)i | (pad_term << 24);  // own row: always inside the gather window
+                }
+            }
+            if (i < n) cnt[i] = (unsigned char)std::max(used, 1);
+        }
+        for (int b0 = 0; b0 < ldr; b0 += 32) {  // the kernel wants the max over the aligned 32-row block
+            unsigned char m = 1;
+            for (int i = b0; i < b0 + 32; ++i) m = std::max(m, cnt[i]);
+            for (int i = b0; i < b0 + 32; ++i) cnt[i] = m;
+        }
+        std::vector<double> srhs(n);
+        for (int i = 0; i < n; ++i) srhs[i] = rhs[perm[i]];
+        h->s_ldr = ldr;
+        h->s_We = We;
+        h->s_bandwidth = bandwidth;
+        h->h_sinv = inv;
+        if (int e = h->d_scolterm.upload(colterm, h->stream)) return e;
+        if (int e = h->d_scoef.upload(coef, h->stream)) return e;
+        if (int e = h->d_scnt.upload(cnt, h->stream)) return e;
         if (int e = h->d_srhs.upload(srhs, h->stream)) return e;
+        if (int e = h->d_sperm.upload(perm, h->stream)) return e;
     }
     TFIN_CUDA(cudaStreamSynchronize(h->stream));
     h->n_cells = 0;  // a new operator invalidates the nodal structures
@@ -246,6 +343,12 @@ extern "C" int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_
     if (int e = upload_csr(h, "tfin_set_observation", n_obs, ptr, idx, val, h->d_obs_ptr, h->d_obs_idx, h->d_obs_val))
         return e;
     h->n_obs = n_obs;
+    if (h->stream_ok) {  // the streaming path works in its own row numbering
+        std::vector<int> ix(ptr[n_obs]);
+        for (int j = 0; j < ptr[n_obs]; ++j) ix[j] = h->h_sinv[idx[j]];
+        if (int e = h->d_sobs_idx.upload(ix, h->stream)) return e;
+        TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    }
     return 0;
 }
 
@@ -490,21 +593,49 @@ static int launch_pcg(tfin_ctx* h, bool nodal, const double* d_in, int in_stride
 static int launch_pcg_stream(tfin_ctx* h, const double* d_in, int in_stride, int64_t N, double tol, int maxit,
                              double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres,
                              cudaStream_t st) {
+    if (!h->stream_ok) return fail(TFIN_E_STATE, "streaming PCG supports n < 2^24 rows (n = %d)", h->n);
     int S = h->stream_tile;
-    if (S == 0) S = N >= (int64_t)32 * h->sm_count ? 32 : (N >= (int64_t)16 * h->sm_count ? 16 : 8);
-    if (S != 8 && S != 16 && S != 32) return fail(TFIN_E_ARG, "stream_tile must be 8, 16 or 32");
+    if (S == 0) S = N <= (int64_t)4 * h->sm_count ? 4 : 8;
+    if (S != 4 && S != 8 && S != 16 && S != 32) return fail(TFIN_E_ARG, "stream_tile must be 4, 8, 16 or 32");
     const int64_t n_tiles = (N + S - 1) / S;
     const int grid = (int)std::min<int64_t>(n_tiles, h->sm_count);
-    if (int e = h->d_swork.reserve((size_t)grid * 4 * h->n * S)) return e;
+    if (int e = h->d_swork.reserve((size_t)grid * 5 * h->s_ldr * S)) return e;
     TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
-    StreamOp op{h->n, h->n_terms, h->d_srow.p, h->d_sent.p, h->d_scoef.p, h->d_sdptr.p, h->d_sdterm.p,
-                h->d_sdcoef.p, h->d_srhs.p};
-    CsrRows obs{h->n_obs, h->d_obs_ptr.p, h->d_obs_idx.p, h->d_obs_val.p};
+    // shared-memory ring for the gathered vector: chunk = 16 warps x 32/(S/4) rows, 8 chunks; needs
+    // 2 * halo + look-ahead + 2 <= 8 chunks
+    const int chunk_rows = 16 * (32 / (S / 4));
+    const int hb = (h->s_bandwidth + chunk_rows - 1) / chunk_rows, la = STREAM_RING_SLOTS - 2 * hb - 2;
+    const bool ring_possible = S == 8 && la >= 1;
+    if (h->stream_ring == 1 && !ring_possible)
+        return fail(TFIN_E_STATE, "stream_ring = 1 needs tile 8 and bandwidth <= %d rows (bandwidth %d, tile %d)",
+                    2 * chunk_rows, h->s_bandwidth, S);
+    // measured (tools/gpu_probe_stream.py, n = 99 945): the 128 KB ring shrinks L1 so much that the streaming pass B
+    // loses more than pass A gains (0.73 vs 0.85 of the HBM peak), so the ring is opt-in only
+    const bool ring = ring_possible && h->stream_ring == 1;
+    // per-warp double buffer for the operator slice of a row group: Ws slots x rows-per-warp x (4 + 8) bytes
+    const int rpw = 32 / (S / 4);
+    const size_t smem_avail = (size_t)h->max_smem_optin - 4096 - (ring ? STREAM_RING_BYTES : 0);
+    const int Ws = (int)std::min<size_t>(h->s_We, smem_avail / ((size_t)16 * 2 * rpw * 12));
+    if (Ws < 1) return fail(TFIN_E_STATE, "streaming PCG: no shared memory left for the operator stage");
+    StreamOp op{h->n, h->n_terms, h->s_ldr, h->s_We, h->d_scolterm.p, h->d_scoef.p, h->d_scnt.p, h->d_srhs.p,
+                h->d_sperm.p, hb, la, Ws};
+    unsigned long long* prof = nullptr;
+    if (h->stream_prof) {
+        if (int e = h->d_sprof.reserve(4)) return e;
+        TFIN_CUDA(cudaMemsetAsync(h->d_sprof.p, 0, 4 * sizeof(unsigned long long), st));
+        prof = h->d_sprof.p;
+    }
+    CsrRows obs{h->n_obs, h->d_obs_ptr.p, h->d_sobs_idx.p, h->d_obs_val.p};
     PcgIO io{d_in, (long long)N, in_stride, tol * tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres,
              h->d_counter.p};
-    if (S == 8) pcg_stream_kernel<8><<<grid, 1024, 0, st>>>(op, obs, io, h->d_swork.p);
-    else if (S == 16) pcg_stream_kernel<16><<<grid, 1024, 0, st>>>(op, obs, io, h->d_swork.p);
-    else pcg_stream_kernel<32><<<grid, 1024, 0, st>>>(op, obs, io, h->d_swork.p);
+    void (*kern)(StreamOp, CsrRows, PcgIO, double*, unsigned long long*) =
+        S == 4 ? pcg_stream_kernel<4, false>
+        : S == 8 ? (ring ? pcg_stream_kernel<8, true> : pcg_stream_kernel<8, false>)
+        : S == 16 ? pcg_stream_kernel<16, false> : pcg_stream_kernel<32, false>;
+    const size_t dyn = (ring ? STREAM_RING_BYTES : 0) + (size_t)16 * 2 * Ws * rpw * 12 + (size_t)h->stream_pad_smem * 1024;
+    if (dyn) TFIN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<grid, 512, dyn, st>>>(op, obs, io, h->d_swork.p, prof);
+    h->last_ring = ring ? 1 : 0;
     TFIN_CUDA(cudaGetLastError());
     h->launches += 1;
     h->last_path = 2;
@@ -726,6 +857,20 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
     if (k == "rom_chunk") return h->rom_chunk;
     if (k == "pcg_path") return h->last_path;
     if (k == "stream_tile") return h->last_tile;
+    if (k == "stream_ell_width") return h->s_We;
+    if (k == "stream_ld") return h->s_ldr;
+    if (k == "stream_bandwidth") return h->s_bandwidth;
+    if (k == "stream_ring") return h->last_ring;
+    if (k.rfind("stream_prof_", 0) == 0 && h->d_sprof.p) {  // stream_prof_0..3: P1, P2, P3 clocks, iterations (CTA 0)
+        const int slot = k.back() - '0';
+        if (slot < 0 || slot > 3) return -1;
+        unsigned long long v[4];
+        cudaSetDevice(h->device);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess ||
+            cudaMemcpy(v, h->d_sprof.p, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -1;
+        return (int64_t)v[slot];
+    }
     return -1;
 }
 
@@ -750,6 +895,18 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
     }
     if (k == "stream_tile") {
         h->stream_tile = (int)value;
+        return 0;
+    }
+    if (k == "stream_ring") {
+        h->stream_ring = (int)value;
+        return 0;
+    }
+    if (k == "stream_pad_smem") {
+        h->stream_pad_smem = (int)value;
+        return 0;
+    }
+    if (k == "stream_prof") {
+        h->stream_prof = (int)value;
         return 0;
     }
     return fail(TFIN_E_ARG, "tfin_set_int: unknown key '%s'", key);

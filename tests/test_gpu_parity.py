@@ -182,9 +182,9 @@ def test_other_mesh_sizes(m, request):
         assert relerr(qn[s], orc.qoi_operator(orc.forward(k[s]))) <= RTOL_FOM
 
 
-@pytest.mark.parametrize("tile", [8, 16, 32])
-def test_stream_kernel_matches_onchip_and_oracle(rom_m3, oracle_m3, tile):
-    """K4 (HBM-streaming, matrix-free, interleaved tiles) forced on the small mesh: same observables as the on-chip
+@pytest.mark.parametrize("tile,ring", [(4, 0), (8, 1), (8, 0), (16, 0), (32, 0)])
+def test_stream_kernel_matches_onchip_and_oracle(rom_m3, oracle_m3, tile, ring):
+    """K4 (HBM-streaming, matrix-free, sample-pair planes) forced on the small mesh: same observables as the on-chip
     kernel and the oracle; 70 samples = partial last tile."""
     rng = np.random.default_rng(31)
     theta = rng.uniform(0.1, 10.0, (70, 9))
@@ -193,11 +193,13 @@ def test_stream_kernel_matches_onchip_and_oracle(rom_m3, oracle_m3, tile):
     try:
         h.set_int("pcg_path", 2)
         h.set_int("stream_tile", tile)
+        h.set_int("stream_ring", ring)
         out = h.fom_affine(theta, want_w=True)
-        assert h.get_int("pcg_path") == 2 and h.get_int("stream_tile") == tile
+        assert h.get_int("pcg_path") == 2 and h.get_int("stream_tile") == tile and h.get_int("stream_ring") == ring
     finally:
         h.set_int("pcg_path", 0)
         h.set_int("stream_tile", 0)
+        h.set_int("stream_ring", -1)
     assert np.all(out["status"] == 0) and np.all(out["relres"] < 1e-10)
     assert np.max(np.abs(out["iters"] - ref["iters"])) <= 3
     assert relerr(out["qoi"], ref["qoi"]) <= 1e-10
