@@ -36,6 +36,11 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfin_rom": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p]),
+    "tfin_fom_nodal_gradient": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32,
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "tfin_fom_nodal_sensitivity": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfin_subfin_avg": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "tfin_kernel_launches": (C.c_int64, [_handle]),
     "tfin_get_int": (C.c_int64, [_handle, C.c_char_p]),
@@ -180,6 +185,37 @@ class TfinHandle:
                                            _ptr(w), _ptr(qoi), _ptr(iters), _ptr(status), _ptr(relres), None)
             _check(self._lib, rc, "tfin_fom_affine")
         return {"w": w, "qoi": qoi, "iters": iters, "status": status, "relres": relres}
+
+    def fom_nodal_gradient(self, k, data, tol=1e-12, maxit=20000):
+        """Batched Fin.gradient: k (N, n), data (n_obs,) or (N, n_obs) -> grad (N, n), cost (N), qoi (N, n_obs)."""
+        k, data = _f64(k), _f64(data)
+        if k.ndim != 2 or k.shape[1] != self.n:
+            raise ValueError(f"fom_nodal_gradient: expected (N, {self.n}) input, got {k.shape}")
+        N = k.shape[0]
+        if data.ndim == 1:
+            data = data[None, :]
+        if data.shape[1] != self.n_obs or data.shape[0] not in (1, N):
+            raise ValueError(f"fom_nodal_gradient: data must be ({self.n_obs},) or (N, {self.n_obs}), got {data.shape}")
+        grad, cost, qoi = np.empty((N, self.n)), np.empty(N), np.empty((N, self.n_obs))
+        iters, status = np.empty(N, dtype=np.int32), np.empty(N, dtype=np.int32)
+        rc = self._lib.tfin_fom_nodal_gradient(self._h, _ptr(k), N, MEM_HOST, float(tol), int(maxit), _ptr(data),
+                                               data.shape[0], _ptr(grad), _ptr(cost), _ptr(qoi), _ptr(iters),
+                                               _ptr(status), None)
+        _check(self._lib, rc, "tfin_fom_nodal_gradient")
+        return {"grad": grad, "cost": cost, "qoi": qoi, "iters": iters, "status": status, "relres": None}
+
+    def fom_nodal_sensitivity(self, k, tol=1e-12, maxit=20000):
+        """Batched Fin.sensitivity: k (N, n) -> jac (N, n_obs, n), qoi (N, n_obs)."""
+        k = _f64(k)
+        if k.ndim != 2 or k.shape[1] != self.n:
+            raise ValueError(f"fom_nodal_sensitivity: expected (N, {self.n}) input, got {k.shape}")
+        N = k.shape[0]
+        jac, qoi = np.empty((N, self.n_obs, self.n)), np.empty((N, self.n_obs))
+        iters, status = np.empty(N, dtype=np.int32), np.empty(N, dtype=np.int32)
+        rc = self._lib.tfin_fom_nodal_sensitivity(self._h, _ptr(k), N, MEM_HOST, float(tol), int(maxit), _ptr(jac),
+                                                  _ptr(qoi), _ptr(iters), _ptr(status), None)
+        _check(self._lib, rc, "tfin_fom_nodal_sensitivity")
+        return {"jac": jac, "qoi": qoi, "iters": iters, "status": status, "relres": None}
 
     def rom(self, batch, in_kind=IN_PARAMS, want_wr=True, want_qoi=True):
         batch = _f64(batch)

@@ -11,8 +11,14 @@
 
 namespace tfin {
 
-#define PCG_ROW(R, WT, WR, MAXT, MINB) \
-    {R, WT, WR, MAXT, MINB, PCG_NODAL, (const void*)&pcg_kernel<R, WT, WR, (PCG_NODAL != 0), MAXT, MINB>},
+#if PCG_NODAL
+#define PCG_ADJ_PTR(R, WT, WR, MAXT, MINB) (const void*)&pcg_kernel<R, WT, WR, true, MAXT, MINB, true>
+#else
+#define PCG_ADJ_PTR(R, WT, WR, MAXT, MINB) nullptr
+#endif
+#define PCG_ROW(R, WT, WR, MAXT, MINB)                                                                      \
+    {R, WT, WR, MAXT, MINB, PCG_NODAL, (const void*)&pcg_kernel<R, WT, WR, (PCG_NODAL != 0), MAXT, MINB>, \
+     PCG_ADJ_PTR(R, WT, WR, MAXT, MINB)},
 static const PcgVariant k_table[] = {PCG_LIST(PCG_ROW)};
 
 const PcgVariant* PCG_CAT(PCG_CAT(pcg_variants_g, PCG_GROUP), PCG_CAT(_n, PCG_NODAL))(int* count) {

@@ -15,6 +15,10 @@
 //     the residual r is published to shared memory for the SpMV gather
 //   * Chronopoulos-Gear CG: ONE fused block reduction (r.r, r.Ar) and two barriers per iteration
 //   * epilogue: true residual, B_obs projection (warp per observation row), optional w write-back
+//   * ADJ variants (nodal operator only) keep the assembled operator on chip and run the ADJOINT solves of
+//     Fin.gradient / Fin.sensitivity (forward_solve.py:293-342) right after the forward solve:
+//       A v = -B_obs^T (B_obs w - data)   (gradient)      or      A v_o = -B_obs[o,:]^T, o = 1..n_obs   (sensitivity)
+//     followed by the gradient form  g_i = sum_{e ni i} (1/3) w_e^T K_e v_e  (= assemble(k_hat grad w . grad v dx))
 //
 // Results do not depend on which CTA solves a sample (fixed reduction order) => bit-reproducible indexing.
 #pragma once
@@ -48,6 +52,17 @@ struct CsrRows {
     const double* val;
 };
 
+// adjoint outputs of the ADJ kernel variants (mode 0 = none)
+struct PcgAdj {
+    int mode;                // 1: gradient of 0.5 ||B_obs w - data||^2;  2: sensitivity d(B_obs w)/dk (n_obs solves)
+    const double* data;      // observations, row s at data + s * data_stride (data_stride = 0: one shared vector)
+    long long data_stride;
+    CsrRows obsT;            // B_obs^T: n rows over n_obs columns
+    const double* Ke;        // [n_cells][3][3]
+    double* grad_out;        // mode 1: (N, n);  mode 2: (N, n_obs, n)
+    double* cost_out;        // mode 1: (N) | NULL, 0.5 ||B_obs w - data||^2
+};
+
 struct PcgIO {
     const double* in;  // (N, in_stride)
     long long N;
@@ -64,13 +79,14 @@ struct PcgIO {
 
 // Shared-memory carve-up shared by host (size) and device (pointers).
 struct PcgSmem {
-    size_t r_off, part_off, misc_off, dsi_off, kbar_off, kbuf_off, val_off, total;
+    size_t r_off, part_off, misc_off, adj_off, dsi_off, kbar_off, kbuf_off, val_off, total;
     __host__ __device__ static PcgSmem make(int w_smem, int np, int n_cells /*0 = affine*/, int n) {
         PcgSmem s;
         size_t o = 0;
         s.r_off = o;    o += (size_t)np * sizeof(double);
         s.part_off = o; o += 64 * sizeof(double);
         s.misc_off = o; o += 32 * sizeof(double);      // theta[16] | next sample | mbarrier
+        s.adj_off = o;  o += 64 * sizeof(double);      // adjoint source coefficients (n_obs <= 64)
         s.dsi_off = o;  o += (size_t)np * sizeof(double);
         s.kbar_off = o; o += n_cells ? (((size_t)n_cells + 2 + 1) & ~size_t(1)) * sizeof(double) : 0;
         s.kbuf_off = o; o += n_cells ? (((size_t)n + 4 + 1) & ~size_t(1)) * sizeof(double) : 0;
@@ -103,8 +119,9 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* s_part,
 }
 
 // R rows per thread, WT padded ELL width (even), WR of the WT off-diagonal values per row in registers.
-template <int R, int WT, int WR, bool NODAL, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, PcgIO io) {
+template <int R, int WT, int WR, bool NODAL, int MAXT, int MINB, bool ADJ = false>
+__global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, PcgIO io, PcgAdj adj) {
+    static_assert(!ADJ || NODAL, "adjoint variants exist for the nodal operator only");
     static_assert(WT % 2 == 0 && WR <= WT, "bad ELL template widths");
     constexpr int WS = WT - WR;  // slots whose values live in shared memory
     extern __shared__ __align__(16) unsigned char smem[];
@@ -116,6 +133,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, 
     double* s_theta = reinterpret_cast<double*>(smem + L.misc_off);
     long long* s_next = reinterpret_cast<long long*>(smem + L.misc_off) + 16;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.misc_off) + 20;
+    double* s_adj = reinterpret_cast<double*>(smem + L.adj_off);
     double* s_dsi = reinterpret_cast<double*>(smem + L.dsi_off);
     double* s_kbar = reinterpret_cast<double*>(smem + L.kbar_off);
     double* s_kbuf = reinterpret_cast<double*>(smem + L.kbuf_off);
@@ -249,27 +267,30 @@ __global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, 
                 }
             }
         };
-        double x[R], r[R], p[R], q[R], s[R];
+        // CG on the scaled system for the scaled right-hand side rin (registers); returns the scaled solution in x
+        auto cg_solve = [&](const double (&rin)[R], double (&x)[R], int& it, int& status) {
+            double r[R], p[R], q[R], s[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const int i = tid + k * T;
-            x[k] = 0.0;
-            r[k] = (i < n ? op.rhs[i] : 0.0) * dsi[k];
-            s_r[i] = r[k];
-        }
-        __syncthreads();
-        spmv(r, s);
-        double gam = 0.0, del = 0.0;
+            for (int k = 0; k < R; ++k) {
+                x[k] = 0.0;
+                r[k] = rin[k];
+                s_r[tid + k * T] = r[k];
+            }
+            __syncthreads();
+            spmv(r, s);
+            double gam = 0.0, del = 0.0;
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            gam = fma(r[k], r[k], gam);
-            del = fma(r[k], s[k], del);
-        }
-        block_sum2(gam, del, s_part, lane, warp, nwarps);
-        int status = TFIN_STATUS_MAXIT, it = 0;
-        if (!(gam > 0.0) || !(del > 0.0)) {  // b == 0 (x = 0 is exact) or not SPD / NaN
-            status = (gam == 0.0) ? TFIN_STATUS_CONVERGED : TFIN_STATUS_BREAKDOWN;
-        } else {
+            for (int k = 0; k < R; ++k) {
+                gam = fma(r[k], r[k], gam);
+                del = fma(r[k], s[k], del);
+            }
+            block_sum2(gam, del, s_part, lane, warp, nwarps);
+            status = TFIN_STATUS_MAXIT;
+            it = 0;
+            if (!(gam > 0.0) || !(del > 0.0)) {  // b == 0 (x = 0 is exact) or not SPD / NaN
+                status = (gam == 0.0) ? TFIN_STATUS_CONVERGED : TFIN_STATUS_BREAKDOWN;
+                return;
+            }
             const double thresh = io.tol2 * gam;
             double alpha = gam / del, denom = del;
 #pragma unroll
@@ -312,6 +333,17 @@ __global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, 
                     q[k] = fma(beta, q[k], s[k]);
                 }
             }
+        };
+        double x[R], s[R];
+        int status, it;
+        {
+            double b0[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int i = tid + k * T;
+                b0[k] = (i < n ? op.rhs[i] : 0.0) * dsi[k];
+            }
+            cg_solve(b0, x, it, status);
         }
 
         // ================= epilogue =================
@@ -336,7 +368,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, 
             if (tid == 0 && io.relres_out) io.relres_out[sample] = relres;
             __syncthreads();
         }
-        if (tid == 0) {
+        if (!ADJ && tid == 0) {
             if (io.iters_out) io.iters_out[sample] = it;
             if (io.status_out) io.status_out[sample] = status;
         }
@@ -361,6 +393,82 @@ __global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, 
             for (int k = 0; k < R; ++k) {
                 const int i = tid + k * T;
                 if (i < n) io.w_out[sample * (long long)n + i] = x[k];
+            }
+        }
+        if (ADJ) {
+            // ================= adjoint solves + gradient form (operator still on chip) =================
+            double* s_w = s_kbuf;  // the nodal field is no longer needed: keep the state w here
+            const int n_adj = adj.mode == 2 ? obs.rows : 1;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int i = tid + k * T;
+                if (i < n) s_w[i] = x[k];
+            }
+            if (adj.mode == 1) {  // source coefficients c_o = (B_obs w)_o - data_o
+                const double* d = adj.data + sample * adj.data_stride;
+                for (int o = warp; o < obs.rows; o += nwarps) {
+                    double acc = 0.0;
+                    for (int j = obs.ptr[o] + lane; j < obs.ptr[o + 1]; j += 32)
+                        acc = fma(obs.val[j], s_r[obs.idx[j]], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0) s_adj[o] = acc - d[o];
+                }
+            }
+            __syncthreads();
+            if (adj.mode == 1 && adj.cost_out && tid == 0) {
+                double c = 0.0;
+                for (int o = 0; o < obs.rows; ++o) c = fma(s_adj[o], s_adj[o], c);
+                adj.cost_out[sample] = 0.5 * c;
+            }
+            for (int a = 0; a < n_adj; ++a) {
+                double rhs[R], v[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int i = tid + k * T;
+                    double rr = 0.0;
+                    if (i < n)
+                        for (int j = adj.obsT.ptr[i]; j < adj.obsT.ptr[i + 1]; ++j) {
+                            const int o = adj.obsT.idx[j];
+                            const double c = adj.mode == 1 ? s_adj[o] : (o == a ? 1.0 : 0.0);
+                            rr = fma(-adj.obsT.val[j], c, rr);
+                        }
+                    rhs[k] = rr * s_dsi[i];
+                }
+                int it_a, st_a;
+                cg_solve(rhs, v, it_a, st_a);
+                if (st_a > status) status = st_a;
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int i = tid + k * T;
+                    s_r[i] = v[k] * s_dsi[i];  // adjoint state
+                }
+                __syncthreads();
+                for (int e = tid; e < nc; e += T) {  // (1/3) w_e^T K_e v_e per cell
+                    const int ca = op.cells[3 * e], cb = op.cells[3 * e + 1], cc = op.cells[3 * e + 2];
+                    const double* K = adj.Ke + 9 * (size_t)e;
+                    const double va = s_r[ca], vb = s_r[cb], vc = s_r[cc];
+                    const double t0 = fma(K[0], va, fma(K[1], vb, K[2] * vc));
+                    const double t1 = fma(K[3], va, fma(K[4], vb, K[5] * vc));
+                    const double t2 = fma(K[6], va, fma(K[7], vb, K[8] * vc));
+                    s_kbar[e] = fma(s_w[ca], t0, fma(s_w[cb], t1, s_w[cc] * t2)) * (1.0 / 3.0);
+                }
+                __syncthreads();
+                double* g = adj.grad_out + (sample * n_adj + a) * (long long)n;
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int i = tid + k * T;
+                    if (i < n) {
+                        double acc = 0.0;
+                        for (int j = op.dptr[i]; j < op.dptr[i + 1]; ++j) acc += s_kbar[op.dcell[j]];
+                        g[i] = acc;
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                if (io.iters_out) io.iters_out[sample] = it;
+                if (io.status_out) io.status_out[sample] = status;
             }
         }
     }

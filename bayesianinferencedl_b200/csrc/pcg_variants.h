@@ -6,7 +6,8 @@ namespace tfin {
 
 struct PcgVariant {
     int R, WT, WR, maxT, minB, nodal;
-    const void* func;  // host stub of pcg_kernel<R, WT, WR, nodal, maxT, minB>
+    const void* func;      // host stub of pcg_kernel<R, WT, WR, nodal, maxT, minB>
+    const void* func_adj;  // ... with the adjoint solves compiled in (nodal variants only, else nullptr)
 };
 
 //        X(R, WT, WR, MAXT, MINB)

@@ -118,7 +118,10 @@ struct tfin_ctx {
     int n_cells = 0, Wn = 0;
     DevBuf<uint16_t> d_ncol;
     DevBuf<int> d_ncell, d_dptr, d_dcell, d_cells;
-    DevBuf<double> d_ncoef, d_ncst, d_dcoef, d_dcst;
+    DevBuf<double> d_ncoef, d_ncst, d_dcoef, d_dcst, d_Ke;
+    // ---- transpose of the observation operator (adjoint right-hand sides)
+    DevBuf<int> d_obsT_ptr, d_obsT_idx;
+    DevBuf<double> d_obsT_val, d_data, d_grad, d_cost;
     // ---- ROM (K3)
     int n_r = 0, rom_terms = 0, rom_obs = 0;
     DevBuf<double> d_S, d_obs_phi, d_romC;
@@ -173,7 +176,10 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
     for (auto* b : {&h->d_obs_ptr, &h->d_obs_idx, &h->d_avg_ptr, &h->d_avg_idx, &h->d_ncell, &h->d_dptr,
                     &h->d_dcell, &h->d_cells, &h->d_iters, &h->d_status})
         b->release();
-    for (auto* b : {&h->d_scoef, &h->d_srhs, &h->d_swork}) b->release();
+    for (auto* b : {&h->d_scoef, &h->d_srhs, &h->d_swork, &h->d_Ke, &h->d_obsT_val, &h->d_data, &h->d_grad, &h->d_cost})
+        b->release();
+    h->d_obsT_ptr.release();
+    h->d_obsT_idx.release();
     h->d_scolterm.release();
     h->d_scnt.release();
     h->d_sperm.release();
@@ -343,6 +349,24 @@ extern "C" int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_
     if (int e = upload_csr(h, "tfin_set_observation", n_obs, ptr, idx, val, h->d_obs_ptr, h->d_obs_idx, h->d_obs_val))
         return e;
     h->n_obs = n_obs;
+    {   // B_obs^T as CSR over the n dofs: right-hand sides of the adjoint solves
+        const int n = h->n, nnz = ptr[n_obs];
+        std::vector<int> tp(n + 1, 0), ti(nnz);
+        std::vector<double> tv(nnz);
+        for (int j = 0; j < nnz; ++j) tp[idx[j] + 1]++;
+        for (int i = 0; i < n; ++i) tp[i + 1] += tp[i];
+        std::vector<int> fill(tp.begin(), tp.end() - 1);
+        for (int o = 0; o < n_obs; ++o)
+            for (int j = ptr[o]; j < ptr[o + 1]; ++j) {
+                const int dst = fill[idx[j]]++;
+                ti[dst] = o;
+                tv[dst] = val[j];
+            }
+        if (int e = h->d_obsT_ptr.upload(tp, h->stream)) return e;
+        if (int e = h->d_obsT_idx.upload(ti, h->stream)) return e;
+        if (int e = h->d_obsT_val.upload(tv, h->stream)) return e;
+        TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    }
     if (h->stream_ok) {  // the streaming path works in its own row numbering
         std::vector<int> ix(ptr[n_obs]);
         for (int j = 0; j < ptr[n_obs]; ++j) ix[j] = h->h_sinv[idx[j]];
@@ -447,6 +471,10 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
     if (int e = h->d_dcoef.upload(dcoef, h->stream)) return e;
     if (int e = h->d_dcst.upload(dcst, h->stream)) return e;
     if (int e = h->d_cells.upload(cl, h->stream)) return e;
+    {
+        std::vector<double> ke(Ke, Ke + 9 * (size_t)n_cells);
+        if (int e = h->d_Ke.upload(ke, h->stream)) return e;
+    }
     TFIN_CUDA(cudaStreamSynchronize(h->stream));
     h->n_cells = n_cells;
     return 0;
@@ -489,18 +517,20 @@ struct PcgGeom {
     size_t smem;
 };
 
-static bool pcg_geom_for(tfin_ctx* h, const PcgVariant* v, int n_cells, PcgGeom* g) {
+static bool pcg_geom_for(tfin_ctx* h, const PcgVariant* v, int n_cells, PcgGeom* g, bool adjoint = false) {
     const int n = h->n, R = v->R;
+    const void* func = adjoint ? v->func_adj : v->func;
+    if (!func) return false;
     const int T = ((n + R - 1) / R + 31) & ~31;
     if (T > v->maxT || T > 1024 || R * T > 8192) return false;
     const PcgSmem L = PcgSmem::make(v->WT - v->WR, R * T, n_cells, n);
     if (L.total > (size_t)h->max_smem_optin) return false;
-    if (cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, T, L.total) != cudaSuccess || occ < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, T, L.total) != cudaSuccess || occ < 1) {
         cudaGetLastError();
         return false;
     }
@@ -512,7 +542,8 @@ static bool pcg_geom_for(tfin_ctx* h, const PcgVariant* v, int n_cells, PcgGeom*
 }
 
 static int launch_pcg(tfin_ctx* h, bool nodal, const double* d_in, int in_stride, int64_t N, double tol, int maxit,
-                      double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres, cudaStream_t st) {
+                      double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres, cudaStream_t st,
+                      const PcgAdj* adjoint = nullptr) {
     const int W = nodal ? h->Wn : h->W;
     const int nc = nodal ? h->n_cells : 0;
     // candidates: variants with the smallest compiled ELL width >= W; user knobs filter further
@@ -534,7 +565,7 @@ static int launch_pcg(tfin_ctx* h, bool nodal, const double* d_in, int in_stride
             if (h->pcg_R > 0 && v->R != h->pcg_R) continue;
             if (h->pcg_WR >= 0 && (v->WR > 0) != (h->pcg_WR > 0)) continue;
             PcgGeom geo{};
-            if (!pcg_geom_for(h, v, nc, &geo)) continue;
+            if (!pcg_geom_for(h, v, nc, &geo, adjoint != nullptr)) continue;
             // score: resident rows per SM that do useful work, two CTAs per SM preferred (barrier latency of one
             // CTA overlaps the SpMV of the other), narrower compiled width preferred
             const double pad = (double)h->n / (v->R * geo.T);
@@ -584,8 +615,10 @@ static int launch_pcg(tfin_ctx* h, bool nodal, const double* d_in, int in_stride
         op.val = h->d_val.p;
         op.diag = h->d_diag.p;
     }
-    void* args[] = {&op, &obs, &io};
-    TFIN_CUDA(cudaLaunchKernel(best.v->func, dim3(grid), dim3(best.T), args, best.smem, st));
+    PcgAdj adj{};
+    if (adjoint) adj = *adjoint;
+    void* args[] = {&op, &obs, &io, &adj};
+    TFIN_CUDA(cudaLaunchKernel(adjoint ? best.v->func_adj : best.v->func, dim3(grid), dim3(best.T), args, best.smem, st));
     h->launches += 1;
     return 0;
 }
@@ -832,6 +865,66 @@ extern "C" int tfin_rom(tfin_handle_t h, const double* in, int64_t N, int32_t in
     if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
     if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ adjoints
+static int fom_adjoint(tfin_handle_t h, int mode, const double* k, int64_t N, int32_t mem, double tol, int32_t maxit,
+                       const double* data, int64_t data_rows, double* grad_out, double* cost_out, double* qoi_out,
+                       int32_t* iters_out, int32_t* status_out, void* stream) {
+    if (h->n_cells <= 0) return fail(TFIN_E_STATE, "adjoint solve: call tfin_set_cells first");
+    if (h->n_obs <= 0 || h->n_obs > 64) return fail(TFIN_E_STATE, "adjoint solve: needs an observation operator with <= 64 rows");
+    if (N < 0 || (N > 0 && (!k || !grad_out))) return fail(TFIN_E_ARG, "adjoint solve: bad batch argument");
+    if (!(tol > 0.0) || maxit < 1) return fail(TFIN_E_ARG, "adjoint solve: tol must be > 0 and maxit >= 1");
+    if (mode == 1 && (!data || (data_rows != 1 && data_rows != N)))
+        return fail(TFIN_E_ARG, "tfin_fom_nodal_gradient: data must have 1 or N rows");
+    if (N == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    Staged sg{h, st, mem == TFIN_MEM_HOST};
+    const int n = h->n, nobs = h->n_obs;
+    const int64_t grad_rows = mode == 2 ? N * nobs : N;
+    const double *d_k, *d_data = nullptr;
+    if (int e = sg.in(k, (size_t)N * n, h->d_in, &d_k)) return e;
+    if (mode == 1)
+        if (int e = sg.in(data, (size_t)data_rows * nobs, h->d_data, &d_data)) return e;
+    double *d_grad, *d_cost, *d_qoi;
+    int *d_iters, *d_status;
+    if (int e = sg.out_alloc(grad_out, (size_t)grad_rows * n, h->d_grad, &d_grad)) return e;
+    if (int e = sg.out_alloc(cost_out, (size_t)N, h->d_cost, &d_cost)) return e;
+    if (int e = sg.out_alloc(qoi_out, (size_t)N * nobs, h->d_qoi, &d_qoi)) return e;
+    if (int e = sg.out_alloc(iters_out, (size_t)N, h->d_iters, &d_iters)) return e;
+    if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
+    PcgAdj adj{};
+    adj.mode = mode;
+    adj.data = d_data;
+    adj.data_stride = data_rows == 1 ? 0 : nobs;
+    adj.obsT = CsrRows{n, h->d_obsT_ptr.p, h->d_obsT_idx.p, h->d_obsT_val.p};
+    adj.Ke = h->d_Ke.p;
+    adj.grad_out = d_grad;
+    adj.cost_out = d_cost;
+    if (int e = launch_pcg(h, true, d_k, n, N, tol, maxit, nullptr, d_qoi, d_iters, d_status, nullptr, st, &adj)) return e;
+    if (int e = sg.out_copy(grad_out, (size_t)grad_rows * n, d_grad)) return e;
+    if (int e = sg.out_copy(cost_out, (size_t)N, d_cost)) return e;
+    if (int e = sg.out_copy(qoi_out, (size_t)N * nobs, d_qoi)) return e;
+    if (int e = sg.out_copy(iters_out, (size_t)N, d_iters)) return e;
+    if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
+    if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int tfin_fom_nodal_gradient(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double tol,
+                                       int32_t maxit, const double* data, int64_t data_rows, double* grad_out,
+                                       double* cost_out, double* qoi_out, int32_t* iters_out, int32_t* status_out,
+                                       void* stream) {
+    CHECK_HANDLE(h);
+    return fom_adjoint(h, 1, k, N, mem, tol, maxit, data, data_rows, grad_out, cost_out, qoi_out, iters_out, status_out,
+                       stream);
+}
+
+extern "C" int tfin_fom_nodal_sensitivity(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double tol,
+                                          int32_t maxit, double* jac_out, double* qoi_out, int32_t* iters_out,
+                                          int32_t* status_out, void* stream) {
+    CHECK_HANDLE(h);
+    return fom_adjoint(h, 2, k, N, mem, tol, maxit, nullptr, 0, jac_out, nullptr, qoi_out, iters_out, status_out, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ introspection

@@ -126,8 +126,33 @@ class Fin:
         st = out["status"]
         if st is not None and np.any(st != _cabi.STATUS_CONVERGED):
             bad = np.nonzero(st != _cabi.STATUS_CONVERGED)[0]
+            rr = "" if out.get("relres") is None else f", relres {out['relres'][bad[0]]:.3e}"
             raise RuntimeError(f"PCG did not converge for {len(bad)} sample(s) (first: {bad[0]}, status "
-                               f"{int(st[bad[0]])}, relres {out['relres'][bad[0]]:.3e}); is k > 0 everywhere?")
+                               f"{int(st[bad[0]])}{rr}); is k > 0 everywhere?")
+
+    # ------------------------------------------------------------------ adjoint gradients
+    def gradient(self, k, data, return_cost=False):
+        """forward_solve.py:293-322: gradient of ``0.5 * ||B_obs w(k) - data||^2`` w.r.t. the nodal conductivity by
+        the adjoint method.  ``k``: (n,) or (N, n); ``data``: (n_obs,) shared or (N, n_obs).  Forward solve, adjoint
+        solve and the gradient form run in one kernel per sample (the reference's dense ``np.linalg.solve`` of
+        :310 is the same PCG here, A being symmetric).  ``return_cost=True`` also returns the cost(s)."""
+        kb, single = _as_batch(k, self.dofs, "Fin.gradient")
+        out = self._h.fom_nodal_gradient(kb, data, tol=self.tol, maxit=self.maxit)
+        self._last = out
+        self._raise_on_failure(out)
+        g = out["grad"][0] if single else out["grad"]
+        if return_cost:
+            return g, (out["cost"][0] if single else out["cost"])
+        return g
+
+    def sensitivity(self, k):
+        """forward_solve.py:324-342: Jacobian of the observables w.r.t. the nodal conductivity,
+        (n_obs, n) for one field, (N, n_obs, n) for a batch (n_obs adjoint solves per sample, on chip)."""
+        kb, single = _as_batch(k, self.dofs, "Fin.sensitivity")
+        out = self._h.fom_nodal_sensitivity(kb, tol=self.tol, maxit=self.maxit)
+        self._last = out
+        self._raise_on_failure(out)
+        return out["jac"][0] if single else out["jac"]
 
     # ------------------------------------------------------------------ observation
     def qoi_operator(self, x):
@@ -160,9 +185,3 @@ class Fin:
 
     def r_fwd_no_full(self, k, phi):
         raise NotImplementedError("nodal-conductivity LSPG (forward_solve.py:454-464) is a 'next' row in DESIGN.md")
-
-    def gradient(self, k, data):
-        raise NotImplementedError("adjoint gradient (forward_solve.py:293-322) is a 'next' row in DESIGN.md")
-
-    def sensitivity(self, k):
-        raise NotImplementedError("sensitivity (forward_solve.py:324-342) is a 'next' row in DESIGN.md")

@@ -127,6 +127,28 @@ int tfin_fom_nodal(tfin_handle_t h, const double* k, int64_t N, int32_t mem, dou
 int tfin_rom(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int32_t mem, double* wr_out,
              double* qoi_out, int32_t* status_out, void* stream);
 
+/*
+ * Batched adjoint gradient of J_s = 0.5 ||B_obs w_s - data_s||^2 with respect to the nodal conductivity:
+ * = Fin.gradient(k, data) (fom/forward_solve.py:293-322) for N samples.  The forward solve, the adjoint solve
+ * A v = -B_obs^T (B_obs w - data) (the reference's dense np.linalg.solve, :310) and the gradient form
+ * assemble(k_hat * inner(grad w, grad v) * dx) (:313-314) run in one kernel on the same on-chip operator.
+ *   data: (data_rows, n_obs) with data_rows == 1 (one observation vector for all samples) or N
+ *   grad_out (N, n), cost_out (N) | NULL = J_s, qoi_out (N, n_obs) | NULL, iters_out (forward solve) | NULL,
+ *   status_out | NULL (worst of the forward and adjoint solves)
+ */
+int tfin_fom_nodal_gradient(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double tol, int32_t maxit,
+                            const double* data, int64_t data_rows, double* grad_out, double* cost_out,
+                            double* qoi_out, int32_t* iters_out, int32_t* status_out, void* stream);
+
+/*
+ * Batched Jacobian of the observables with respect to the nodal conductivity:
+ * = Fin.sensitivity(k) (fom/forward_solve.py:324-342): n_obs adjoint solves A v_o = -B_obs[o,:]^T per sample.
+ *   jac_out (N, n_obs, n)
+ */
+int tfin_fom_nodal_sensitivity(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double tol, int32_t maxit,
+                               double* jac_out, double* qoi_out, int32_t* iters_out, int32_t* status_out,
+                               void* stream);
+
 /* theta = averaging(k) for N nodal fields (subfin_avg_op batched); out (N, n_rows). */
 int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double* theta_out,
                     void* stream);

@@ -248,6 +248,64 @@ class FinOracle:
         return A_r, B_r, C_r, x_r, float(C_r @ x_r)
 
 
+    # ---------------- adjoint gradients ----------------
+    def grad_form(self, z, v):
+        """assemble(k_hat * inner(grad z, grad v) * dx) for the P1 test function k_hat (forward_solve.py:313-314,
+        180): entry i = sum over cells containing vertex i of (|e|/3) grad z . grad v = (1/3) z_e^T K_e v_e."""
+        ge = np.einsum("ea,eab,eb->e", z[self.cells], self.Ke, v[self.cells]) / 3.0
+        out = np.zeros(self.n)
+        for a in range(3):
+            np.add.at(out, self.cells[:, a], ge)
+        return out
+
+    def gradient(self, k, data):
+        """``Fin.gradient(k, data)`` (forward_solve.py:293-322): forward solve, adjoint solve with
+        rhs = -(B_obs z - data)^T B_obs (the reference uses a DENSE np.linalg.solve, :310), gradient form."""
+        A = self.matrix_nodal(k)
+        lu = spla.splu(A)
+        z = lu.solve(self.B)
+        pred = self.B_obs @ z
+        adj_rhs = -np.dot((pred - data).T, self.B_obs)
+        v = np.linalg.solve(A.toarray(), adj_rhs) if self.n <= 2000 else lu.solve(adj_rhs)
+        return self.grad_form(z, v)
+
+    def sensitivity(self, k):
+        """``Fin.sensitivity(k)`` (forward_solve.py:324-342): Jacobian of the observables w.r.t. the nodal
+        conductivity, (n_obs, n): adjoint solves with rhs = -B_obs^T, then grad_assembled @ v."""
+        A = self.matrix_nodal(k)
+        lu = spla.splu(A)
+        z = lu.solve(self.B)
+        V = lu.solve(np.ascontiguousarray(-self.B_obs.T))
+        return np.stack([self.grad_form(z, V[:, o]) for o in range(self.B_obs.shape[0])])
+
+    def grad_reduced(self, k, data, phi):
+        """``AffineROMFin.grad_reduced(k)`` (averaged_affine_ROM.py:335-356), literally, with
+        dA_dsigmak_phi[q] = K_q phi (:215-220) and dsigma_dk = B_obs (:210).  Returns (dJ_dk, J)."""
+        theta = self.subfin_avg_op(k)
+        A = self.matrix_affine(theta).tocsr()
+        psi = A @ phi
+        A_r = psi.T @ psi
+        w_r = np.linalg.solve(A_r, psi.T @ self.B)
+        B_obs_phi = self.B_obs @ phi
+        reduced_fwd_obs = B_obs_phi @ w_r
+        reduced_adj_rhs = B_obs_phi.T @ (data - reduced_fwd_obs)
+        v_r = np.linalg.solve(A_r.T, reduced_adj_rhs)
+        psi_v_r = psi @ v_r
+        A_phi_w_r = np.stack([(Kq @ phi) @ w_r for Kq in self.K_q]).T      # (n, 9)
+        g_theta = psi_v_r @ A_phi_w_r                                       # (9,)  = dJ / d theta
+        dJ_dk = g_theta @ self.B_obs                                        # psi_v_r^T (A_phi_w_r dsigma_dk)
+        J = 0.5 * np.linalg.norm(data - reduced_fwd_obs) ** 2
+        return dJ_dk, J, g_theta
+
+    def reduced_forward(self, A, B, C, psi, phi):
+        """``Fin.reduced_forward`` (forward_solve.py:421-452), literally (dense A)."""
+        A_r = np.dot(psi.T, np.dot(A, phi))
+        B_r = np.dot(psi.T, B)
+        C_r = np.dot(C, phi)
+        x_r = np.linalg.solve(A_r, B_r)
+        return A_r, B_r, C_r, x_r, np.dot(C_r, x_r)
+
+
 def five_param_to_nine(k5):
     """forward_solve_petsc.py:243-260: k1..k4 are the y-bands 0.75/1.75/2.75/3.75 on BOTH sides, k5 the
     post.  In the numbering of forward_solve.py:125-133 (right fins counted top-down) this is
