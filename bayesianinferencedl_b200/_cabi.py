@@ -36,6 +36,10 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfin_rom": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p]),
+    "tfin_set_rom_gradient": (C.c_int, [_handle, C.c_int32, C.c_int32, C.c_void_p]),
+    "tfin_rom_gradient": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "tfin_fom_nodal_gradient": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32,
                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
@@ -154,6 +158,14 @@ class TfinHandle:
                "tfin_set_rom")
         self.n_r, self.rom_terms, self.rom_obs = n_r, n_terms, n_obs
 
+    def set_rom_gradient(self, gram):
+        """gram[t][q-1] = Psi_t^T Psi_q, shape (n_terms, n_terms-1, n_r, n_r)."""
+        gram = _f64(gram)
+        if gram.shape != (self.rom_terms, self.rom_terms - 1, self.n_r, self.n_r):
+            raise ValueError("set_rom_gradient: gram must be (n_terms, n_terms-1, n_r, n_r)")
+        _check(self._lib, self._lib.tfin_set_rom_gradient(self._h, self.n_r, self.rom_terms, _ptr(gram)),
+               "tfin_set_rom_gradient")
+
     # ---- host-memory batch calls (numpy in, numpy out)
     def fom_affine(self, batch, in_kind=IN_PARAMS, tol=1e-12, maxit=20000, want_w=False, want_qoi=True,
                    want_stats=True):
@@ -230,6 +242,27 @@ class TfinHandle:
                                 None)
         _check(self._lib, rc, "tfin_rom")
         return {"w_r": wr, "qoi": qoi, "status": status}
+
+    def rom_gradient(self, batch, data, in_kind=IN_PARAMS, grad_kind=IN_PARAMS, want_wr=False):
+        """Batched AffineROMFin.grad_reduced: -> grad (N, n_terms-1 | n), cost (N), qoi (N, n_obs)."""
+        batch, data = _f64(batch), _f64(data)
+        cols = self.n if in_kind == IN_NODAL else self.rom_terms - 1
+        if batch.ndim != 2 or batch.shape[1] != cols:
+            raise ValueError(f"rom_gradient: expected (N, {cols}) input, got {batch.shape}")
+        N = batch.shape[0]
+        if data.ndim == 1:
+            data = data[None, :]
+        if data.shape[1] != self.rom_obs or data.shape[0] not in (1, N):
+            raise ValueError(f"rom_gradient: data must be ({self.rom_obs},) or (N, {self.rom_obs}), got {data.shape}")
+        gcols = self.n if grad_kind == IN_NODAL else self.rom_terms - 1
+        grad, cost, qoi = np.empty((N, gcols)), np.empty(N), np.empty((N, self.rom_obs))
+        wr = np.empty((N, self.n_r)) if want_wr else None
+        status = np.empty(N, dtype=np.int32)
+        rc = self._lib.tfin_rom_gradient(self._h, _ptr(batch), N, int(in_kind), MEM_HOST, _ptr(data), data.shape[0],
+                                         int(grad_kind), _ptr(grad), _ptr(cost), _ptr(qoi), _ptr(wr), _ptr(status),
+                                         None)
+        _check(self._lib, rc, "tfin_rom_gradient")
+        return {"grad": grad, "cost": cost, "qoi": qoi, "w_r": wr, "status": status}
 
     def subfin_avg(self, k):
         k = _f64(k)

@@ -120,6 +120,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// ---- Ampere-style 16-byte asynchronous copies (LDGSTS) for multi-stage shared-memory rings
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 #endif  // __CUDACC__
 
 }  // namespace tfin

@@ -48,14 +48,6 @@ struct StreamOp {
 #define STREAM_RING_BYTES (128 * 1024)  // shared-memory ring of the gathered vector (ring mode)
 #define STREAM_RING_SLOTS 8             // chunks in the ring
 
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 // streaming 16-byte load of read-write data that is touched once per pass: do not allocate an L1 line
 __device__ __forceinline__ double2 ld_stream2(const double2* p) {
     double2 v;

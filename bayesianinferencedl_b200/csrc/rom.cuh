@@ -12,6 +12,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "pcg_small.cuh"  // CsrRows
 
 namespace tfin {
 
@@ -92,12 +93,71 @@ __global__ void __launch_bounds__(256) rom_combine_kernel(const double* __restri
 // ------------------------------------------------------------------------------------------- R2
 // One warp per sample: panel-blocked left-looking Cholesky of the augmented packed matrix in shared memory, back
 // substitution, observation projection.
-template <int MAXM /* ceil((n_r+1)/32) */>
+// Adjoint outputs of the reduced gradient (averaged_affine_ROM.py:335-346): v_r = A_r^{-T} (B_obs phi)^T (data - qoi).
+struct RomAdj {
+    const double* data;   // (1 | N, n_obs)
+    long long data_stride;  // 0 = one observation vector for every sample
+    double* vr_out;       // (N, n_r)
+    double* cost_out;     // (N) | nullptr: J = 0.5 ||data - qoi||^2
+};
+
+// Back substitution L^T w = y on the packed factor.  y is lane-distributed in registers (lane l holds entries
+// l + 32 m); step j broadcasts w_j by shuffle and every lane updates its entries i < j with L[j][i] (column i of
+// the packed factor, offset j - i), loaded ahead of the dependent chain.
+template <int MAXM>
+__device__ __forceinline__ void rom_back_subst(const double* __restrict__ A, const double* __restrict__ dinv, int nr,
+                                               int lane, double (&yv)[MAXM]) {
+    // the slab index of the pivot is a compile-time constant inside the unrolled mb loop, so yv stays in registers
+#pragma unroll
+    for (int mb = MAXM - 1; mb >= 0; --mb) {
+        for (int j = min(nr, 32 * mb + 32) - 1; j >= 32 * mb; --j) {
+            double lji[MAXM];
+#pragma unroll
+            for (int m = 0; m <= mb; ++m) {
+                const int i = lane + 32 * m;
+                lji[m] = i < j ? A[rom_col_off(i, nr) + (j - i)] : 0.0;
+            }
+            const double wj = __shfl_sync(0xffffffffu, yv[mb], j & 31) * dinv[j];
+#pragma unroll
+            for (int m = 0; m <= mb; ++m) {
+                const int i = lane + 32 * m;
+                yv[m] = (i == j) ? wj : fma(-lji[m], wj, yv[m]);
+            }
+        }
+    }
+}
+
+// Forward substitution L z = y (column sweep: column j of the packed factor is contiguous, so the lanes read
+// consecutive words); same register distribution as rom_back_subst.
+template <int MAXM>
+__device__ __forceinline__ void rom_fwd_subst(const double* __restrict__ A, const double* __restrict__ dinv, int nr,
+                                              int lane, double (&yv)[MAXM]) {
+#pragma unroll
+    for (int mb = 0; mb < MAXM; ++mb) {
+        for (int j = 32 * mb; j < min(nr, 32 * mb + 32); ++j) {
+            const int oj = rom_col_off(j, nr) - j;  // + i addresses L[i][j]
+            double lij[MAXM];
+#pragma unroll
+            for (int m = mb; m < MAXM; ++m) {
+                const int i = lane + 32 * m;
+                lij[m] = (i > j && i < nr) ? A[oj + i] : 0.0;
+            }
+            const double zj = __shfl_sync(0xffffffffu, yv[mb], j & 31) * dinv[j];
+#pragma unroll
+            for (int m = mb; m < MAXM; ++m) {
+                const int i = lane + 32 * m;
+                yv[m] = (i == j) ? zj : fma(-lij[m], zj, yv[m]);
+            }
+        }
+    }
+}
+
+template <int MAXM /* ceil((n_r+1)/32) */, bool ADJ = false>
 __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict__ C, long long s_begin,
                                                        long long s_end, int nr, int n_obs,
                                                        const double* __restrict__ obs_phi,  // [n_obs][nr]
                                                        double* __restrict__ wr_out, double* __restrict__ qoi_out,
-                                                       int* __restrict__ status_out) {
+                                                       int* __restrict__ status_out, RomAdj adj) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int Taug = rom_taug(nr);
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -175,33 +235,14 @@ __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict_
             }
             __syncwarp();
         }
-        // y = last row of the factor; back substitution L^T w = y.  y is lane-distributed in registers (lane l holds
-        // entries l + 32 m); step j broadcasts w_j by shuffle and every lane updates its entries i < j with
-        // L[j][i] (column i of the packed factor, offset j - i), loaded ahead of the dependent chain.
+        // y = last row of the factor (the forward substitution rode along with the factorisation)
         double yv[MAXM];
 #pragma unroll
         for (int m = 0; m < MAXM; ++m) {
             const int i = lane + 32 * m;
             yv[m] = i < nr ? A[rom_col_off(i, nr) + (nr - i)] : 0.0;
         }
-        for (int j = nr - 1; j >= 0; --j) {
-            double lji[MAXM];
-#pragma unroll
-            for (int m = 0; m < MAXM; ++m) {
-                const int i = lane + 32 * m;
-                lji[m] = i < j ? A[rom_col_off(i, nr) + (j - i)] : 0.0;
-            }
-            double yj = 0.0;
-#pragma unroll
-            for (int m = 0; m < MAXM; ++m)
-                if ((j >> 5) == m) yj = yv[m];
-            const double wj = __shfl_sync(0xffffffffu, yj, j & 31) * dinv[j];
-#pragma unroll
-            for (int m = 0; m < MAXM; ++m) {
-                const int i = lane + 32 * m;
-                yv[m] = (i == j) ? wj : fma(-lji[m], wj, yv[m]);
-            }
-        }
+        rom_back_subst<MAXM>(A, dinv, nr, lane, yv);
 #pragma unroll
         for (int m = 0; m < MAXM; ++m) {
             const int i = lane + 32 * m;
@@ -211,15 +252,172 @@ __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict_
         if (status_out && lane == 0) status_out[s] = status;
         if (wr_out)
             for (int j = lane; j < nr; j += 32) wr_out[s * nr + j] = wv[j];
-        if (qoi_out) {
+        if (qoi_out || ADJ) {
+            double rv[MAXM], cost = 0.0;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) rv[m] = 0.0;
             for (int o = 0; o < n_obs; ++o) {
                 double acc = 0.0;
                 for (int j = lane; j < nr; j += 32) acc = fma(obs_phi[o * nr + j], wv[j], acc);
                 acc = warp_sum(acc);
-                if (lane == 0) qoi_out[s * n_obs + o] = acc;
+                if (qoi_out && lane == 0) qoi_out[s * n_obs + o] = acc;
+                if (ADJ) {  // reduced adjoint right-hand side (B_obs phi)^T (data - qoi), :338-339
+                    const double res = adj.data[s * adj.data_stride + o] - acc;
+                    cost = fma(res, res, cost);
+#pragma unroll
+                    for (int m = 0; m < MAXM; ++m) {
+                        const int j = lane + 32 * m;
+                        if (j < nr) rv[m] = fma(obs_phi[o * nr + j], res, rv[m]);
+                    }
+                }
+            }
+            if (ADJ) {  // v_r = A_r^{-T} rhs = L^{-T} L^{-1} rhs (A_r symmetric), :345
+                rom_fwd_subst<MAXM>(A, dinv, nr, lane, rv);
+                rom_back_subst<MAXM>(A, dinv, nr, lane, rv);
+#pragma unroll
+                for (int m = 0; m < MAXM; ++m) {
+                    const int j = lane + 32 * m;
+                    if (j < nr) adj.vr_out[s * nr + j] = rv[m];
+                }
+                if (adj.cost_out && lane == 0) adj.cost_out[s] = 0.5 * cost;
             }
         }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------- R3
+// Reduced gradient contraction (averaged_affine_ROM.py:347-351 rewritten with offline Gram blocks):
+//     g_q = (psi v_r)^T (K_q phi) w_r = sum_t th_t  v_r^T N_tq w_r,     N_tq = Psi_t^T Psi_q   (n_r x n_r)
+// as a batched GEMM  c[s][o] = sum_{i,j} (v_i w_j) NG[(i,j)][o],  o = (t, q), followed by the th_t fold.
+// CTA = 64 samples x one block of 96 outputs at a time; warp = 8 samples, lane = outputs lane + 32 m.  Two-stage
+// accumulation keeps the FP64 pipe on pure FMAs:  d += w_j * NG[i][j][.] over j, then c += v_i * d once per i.
+// NG streams from L2 through a 4-stage cp.async ring of 16-row chunks; w and v sit transposed in shared memory.
+constexpr int RG_BM = 64, RG_OB = 96, RG_KC = 16, RG_STAGES = 4;
+
+__host__ __device__ inline size_t rom_grad_smem(int nr, int n_par) {
+    return ((size_t)2 * nr * RG_BM + (size_t)RG_STAGES * RG_KC * RG_OB + (size_t)RG_BM * n_par) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(256, 1) rom_grad_kernel(const double* __restrict__ theta,  // (N, n_terms-1)
+                                                          const double* __restrict__ wr,     // (N, nr)
+                                                          const double* __restrict__ vr,     // (N, nr)
+                                                          long long N, int nr, int n_terms,
+                                                          const double* __restrict__ NG,  // [n_ob][nr*nr][RG_OB]
+                                                          int n_ob, double* __restrict__ g_out /* (N, n_terms-1) */) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n_par = n_terms - 1, O = n_terms * n_par, K = nr * nr;
+    double* s_w = reinterpret_cast<double*>(smem);     // [nr][BM]
+    double* s_v = s_w + (size_t)nr * RG_BM;             // [nr][BM]
+    double* s_ring = s_v + (size_t)nr * RG_BM;          // [STAGES][KC][OB]; reused as c[BM][OB] in the epilogue
+    double* s_g = s_ring + (size_t)RG_STAGES * RG_KC * RG_OB;  // [BM][n_par]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_chunks = (K + RG_KC - 1) / RG_KC;
+
+    for (long long s0 = (long long)blockIdx.x * RG_BM; s0 < N; s0 += (long long)gridDim.x * RG_BM) {
+        __syncthreads();  // previous tile's epilogue is done with s_ring / s_g
+        for (int e = tid; e < RG_BM * nr; e += 256) {
+            const int sl = e / nr, j = e - sl * nr;
+            const long long s = s0 + sl;
+            s_w[j * RG_BM + sl] = s < N ? wr[s * nr + j] : 0.0;
+            s_v[j * RG_BM + sl] = s < N ? vr[s * nr + j] : 0.0;
+        }
+        for (int e = tid; e < RG_BM * n_par; e += 256) s_g[e] = 0.0;
+        for (int ob = 0; ob < n_ob; ++ob) {
+            const double* src = NG + (size_t)ob * K * RG_OB;
+            auto issue = [&](int chunk) {
+                if (chunk < n_chunks) {
+                    const int rows = min(RG_KC, K - chunk * RG_KC);
+                    const double* g = src + (size_t)chunk * RG_KC * RG_OB;
+                    double* d = s_ring + (size_t)(chunk % RG_STAGES) * RG_KC * RG_OB;
+                    for (int e = tid; e < rows * (RG_OB / 2); e += 256) cp_async16(d + 2 * e, g + 2 * e);
+                }
+                cp_async_commit();
+            };
+            __syncthreads();  // s_w / s_v visible; ring free
+            for (int c = 0; c < RG_STAGES - 1; ++c) issue(c);
+            double acc[8][3], d[8][3];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int m = 0; m < 3; ++m) acc[a][m] = 0.0, d[a][m] = 0.0;
+            int i = 0, j = 0;
+            for (int chunk = 0; chunk < n_chunks; ++chunk) {
+                cp_async_wait<RG_STAGES - 2>();
+                __syncthreads();             // chunk landed for everyone; the stage refilled below was consumed
+                issue(chunk + RG_STAGES - 1);
+                const double* st = s_ring + (size_t)(chunk % RG_STAGES) * RG_KC * RG_OB;
+                const int rows = min(RG_KC, K - chunk * RG_KC);
+#pragma unroll 4
+                for (int r = 0; r < rows; ++r) {
+                    const double4 w0 = *reinterpret_cast<const double4*>(&s_w[j * RG_BM + 8 * warp]);
+                    const double4 w1 = *reinterpret_cast<const double4*>(&s_w[j * RG_BM + 8 * warp + 4]);
+                    const double wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    double nv[3];
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) nv[m] = st[r * RG_OB + lane + 32 * m];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) d[a][m] = fma(wv[a], nv[m], d[a][m]);
+                    if (++j == nr) {  // row i of the outer product is complete: c += v_i * d
+                        const double4 v0 = *reinterpret_cast<const double4*>(&s_v[i * RG_BM + 8 * warp]);
+                        const double4 v1 = *reinterpret_cast<const double4*>(&s_v[i * RG_BM + 8 * warp + 4]);
+                        const double vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                        for (int a = 0; a < 8; ++a)
+#pragma unroll
+                            for (int m = 0; m < 3; ++m) {
+                                acc[a][m] = fma(vv[a], d[a][m], acc[a][m]);
+                                d[a][m] = 0.0;
+                            }
+                        j = 0;
+                        ++i;
+                    }
+                }
+            }
+            cp_async_wait<0>();
+            __syncthreads();  // everyone is done with the ring: reuse it for c[BM][OB]
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int m = 0; m < 3; ++m) s_ring[(8 * warp + a) * RG_OB + lane + 32 * m] = acc[a][m];
+            __syncthreads();
+            for (int e = tid; e < RG_BM * n_par; e += 256) {
+                const int sl = e / n_par, q = e - sl * n_par;
+                const long long s = s0 + sl;
+                if (s >= N) continue;
+                double g = 0.0;
+                // outputs of this block: o = ob*OB + ol = t * n_par + q
+                for (int t = 0; t < n_terms; ++t) {
+                    const int ol = t * n_par + q - ob * RG_OB;
+                    if (ol < 0 || ol >= RG_OB || t * n_par + q >= O) continue;
+                    const double th = t == 0 ? 1.0 : theta[s * n_par + t - 1];
+                    g = fma(th, s_ring[sl * RG_OB + ol], g);
+                }
+                s_g[e] += g;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < RG_BM * n_par; e += 256) {
+            const long long s = s0 + e / n_par;
+            if (s < N) g_out[s0 * n_par + e] = s_g[e];
+        }
+    }
+}
+
+// dJ/dk = g^T dsigma_dk (averaged_affine_ROM.py:350-351): out[s][i] = sum_q g[s][q] Avg[q][i], through the transposed
+// averaging operator (CSR over the n dofs).  One thread per (sample, dof), coalesced stores.
+__global__ void __launch_bounds__(256) rom_grad_lift_kernel(CsrRows avgT, const double* __restrict__ g, long long N,
+                                                            int n_par, double* __restrict__ out) {
+    const long long total = N * avgT.rows;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long s = e / avgT.rows;
+        const int i = (int)(e - s * avgT.rows);
+        double acc = 0.0;
+        for (int j = avgT.ptr[i]; j < avgT.ptr[i + 1]; ++j) acc = fma(avgT.val[j], g[s * n_par + avgT.idx[j]], acc);
+        out[e] = acc;
     }
 }
 

@@ -126,6 +126,10 @@ struct tfin_ctx {
     int n_r = 0, rom_terms = 0, rom_obs = 0;
     DevBuf<double> d_S, d_obs_phi, d_romC;
     int64_t rom_chunk = 0;  // 0 = auto
+    // ---- ROM gradient (R3): Gram blocks Psi_t^T Psi_q, transposed averaging operator
+    int rg_ob = 0;
+    DevBuf<double> d_NG, d_vr, d_gtheta, d_avgT_val;
+    DevBuf<int> d_avgT_ptr, d_avgT_idx;
     // ---- batch staging / scratch
     DevBuf<double> d_in, d_theta, d_w, d_qoi, d_relres, d_wr;
     DevBuf<int> d_iters, d_status;
@@ -180,6 +184,9 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
         b->release();
     h->d_obsT_ptr.release();
     h->d_obsT_idx.release();
+    for (auto* b : {&h->d_NG, &h->d_vr, &h->d_gtheta, &h->d_avgT_val}) b->release();
+    h->d_avgT_ptr.release();
+    h->d_avgT_idx.release();
     h->d_scolterm.release();
     h->d_scnt.release();
     h->d_sperm.release();
@@ -343,30 +350,36 @@ static int upload_csr(tfin_ctx* h, const char* who, int rows, const int32_t* ptr
     return 0;
 }
 
+// Transpose of a (rows x n) CSR operator as CSR over the n dofs.
+static int upload_csr_transpose(tfin_ctx* h, int rows, const int32_t* ptr, const int32_t* idx, const double* val,
+                                DevBuf<int>& dptr, DevBuf<int>& didx, DevBuf<double>& dval) {
+    const int n = h->n, nnz = ptr[rows];
+    std::vector<int> tp(n + 1, 0), ti(nnz);
+    std::vector<double> tv(nnz);
+    for (int j = 0; j < nnz; ++j) tp[idx[j] + 1]++;
+    for (int i = 0; i < n; ++i) tp[i + 1] += tp[i];
+    std::vector<int> fill(tp.begin(), tp.end() - 1);
+    for (int o = 0; o < rows; ++o)
+        for (int j = ptr[o]; j < ptr[o + 1]; ++j) {
+            const int dst = fill[idx[j]]++;
+            ti[dst] = o;
+            tv[dst] = val[j];
+        }
+    if (int e = dptr.upload(tp, h->stream)) return e;
+    if (int e = didx.upload(ti, h->stream)) return e;
+    if (int e = dval.upload(tv, h->stream)) return e;
+    TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_t* ptr, const int32_t* idx,
                                     const double* val) {
     CHECK_HANDLE(h);
     if (int e = upload_csr(h, "tfin_set_observation", n_obs, ptr, idx, val, h->d_obs_ptr, h->d_obs_idx, h->d_obs_val))
         return e;
     h->n_obs = n_obs;
-    {   // B_obs^T as CSR over the n dofs: right-hand sides of the adjoint solves
-        const int n = h->n, nnz = ptr[n_obs];
-        std::vector<int> tp(n + 1, 0), ti(nnz);
-        std::vector<double> tv(nnz);
-        for (int j = 0; j < nnz; ++j) tp[idx[j] + 1]++;
-        for (int i = 0; i < n; ++i) tp[i + 1] += tp[i];
-        std::vector<int> fill(tp.begin(), tp.end() - 1);
-        for (int o = 0; o < n_obs; ++o)
-            for (int j = ptr[o]; j < ptr[o + 1]; ++j) {
-                const int dst = fill[idx[j]]++;
-                ti[dst] = o;
-                tv[dst] = val[j];
-            }
-        if (int e = h->d_obsT_ptr.upload(tp, h->stream)) return e;
-        if (int e = h->d_obsT_idx.upload(ti, h->stream)) return e;
-        if (int e = h->d_obsT_val.upload(tv, h->stream)) return e;
-        TFIN_CUDA(cudaStreamSynchronize(h->stream));
-    }
+    // B_obs^T as CSR over the n dofs: right-hand sides of the adjoint solves
+    if (int e = upload_csr_transpose(h, n_obs, ptr, idx, val, h->d_obsT_ptr, h->d_obsT_idx, h->d_obsT_val)) return e;
     if (h->stream_ok) {  // the streaming path works in its own row numbering
         std::vector<int> ix(ptr[n_obs]);
         for (int j = 0; j < ptr[n_obs]; ++j) ix[j] = h->h_sinv[idx[j]];
@@ -382,7 +395,8 @@ extern "C" int tfin_set_averaging(tfin_handle_t h, int32_t n_rows, const int32_t
     if (int e = upload_csr(h, "tfin_set_averaging", n_rows, ptr, idx, val, h->d_avg_ptr, h->d_avg_idx, h->d_avg_val))
         return e;
     h->n_avg = n_rows;
-    return 0;
+    // Avg^T over the dofs: lifts d/d theta to d/d k (dsigma_dk, averaged_affine_ROM.py:210, 350)
+    return upload_csr_transpose(h, n_rows, ptr, idx, val, h->d_avgT_ptr, h->d_avgT_idx, h->d_avgT_val);
 }
 
 extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* cells, const double* Ke,
@@ -507,6 +521,27 @@ extern "C" int tfin_set_rom(tfin_handle_t h, int32_t n_r, int32_t n_terms, int32
     h->n_r = n_r;
     h->rom_terms = n_terms;
     h->rom_obs = n_obs;
+    h->rg_ob = 0;  // a new basis invalidates the gradient tensors
+    return 0;
+}
+
+extern "C" int tfin_set_rom_gradient(tfin_handle_t h, int32_t n_r, int32_t n_terms, const double* gram) {
+    CHECK_HANDLE(h);
+    if (h->n_r <= 0) return fail(TFIN_E_STATE, "tfin_set_rom_gradient: call tfin_set_rom first");
+    if (!gram || n_r != h->n_r || n_terms != h->rom_terms)
+        return fail(TFIN_E_ARG, "tfin_set_rom_gradient: n_r / n_terms must match tfin_set_rom (%d, %d)", h->n_r,
+                    h->rom_terms);
+    // gram[t][q-1][i][j] = (Psi_t^T Psi_q)[i][j]  ->  NG[ob][i*n_r + j][96] with output o = t (n_terms-1) + (q-1)
+    const int n_par = n_terms - 1, O = n_terms * n_par, K = n_r * n_r, n_ob = (O + RG_OB - 1) / RG_OB;
+    std::vector<double> ng((size_t)n_ob * K * RG_OB, 0.0);
+    for (int o = 0; o < O; ++o) {
+        const double* src = gram + (size_t)o * K;
+        double* dst = ng.data() + (size_t)(o / RG_OB) * K * RG_OB + (o % RG_OB);
+        for (int k = 0; k < K; ++k) dst[(size_t)k * RG_OB] = src[k];
+    }
+    if (int e = h->d_NG.upload(ng, h->stream)) return e;
+    TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    h->rg_ob = n_ob;
     return 0;
 }
 
@@ -810,6 +845,38 @@ extern "C" int tfin_fom_nodal(tfin_handle_t h, const double* k, int64_t N, int32
                       relres_out, stream);
 }
 
+// Combine + Cholesky over chunks of samples (R1 + R2); with `adj` the Cholesky kernel also solves the reduced adjoint.
+static int rom_run(tfin_ctx* h, const double* d_par, int64_t N, cudaStream_t st, double* d_wr, double* d_qoi,
+                   int* d_status, const RomAdj* adj) {
+    const int nt = h->rom_terms, nr = h->n_r, nobs = h->rom_obs;
+    const int Taug = rom_taug(nr), P2 = nt * (nt + 1) / 2;
+    const int per_warp = ((Taug + 2 * nr + 2) + 1) & ~1;
+    int wpb = std::min<int>(8, (int)((size_t)(h->max_smem_optin - 1024) / ((size_t)per_warp * 8)));
+    if (wpb < 1) return fail(TFIN_E_STATE, "tfin_rom: n_r = %d does not fit shared memory", nr);
+    const size_t chol_smem = (size_t)wpb * per_warp * 8;
+    const size_t comb_smem = ((size_t)P2 * (ROM_BM + ROM_BN) + (size_t)ROM_BM * nt) * 8;
+    const int64_t chunk = h->rom_chunk > 0 ? h->rom_chunk : (int64_t)h->sm_count * wpb * 8;
+    if (int e = h->d_romC.reserve((size_t)std::min<int64_t>(chunk, N) * Taug)) return e;
+    TFIN_CUDA(cudaFuncSetAttribute(rom_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comb_smem));
+    const int maxm = (nr + 1 + 31) / 32;
+    auto chol = adj ? (maxm == 1 ? rom_chol_kernel<1, true> : maxm == 2 ? rom_chol_kernel<2, true>
+                       : maxm == 3 ? rom_chol_kernel<3, true> : rom_chol_kernel<4, true>)
+                    : (maxm == 1 ? rom_chol_kernel<1, false> : maxm == 2 ? rom_chol_kernel<2, false>
+                       : maxm == 3 ? rom_chol_kernel<3, false> : rom_chol_kernel<4, false>);
+    TFIN_CUDA(cudaFuncSetAttribute(chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+    const RomAdj a = adj ? *adj : RomAdj{};
+    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
+        const int64_t s1 = std::min<int64_t>(N, s0 + chunk);
+        dim3 g1((unsigned)((s1 - s0 + ROM_BM - 1) / ROM_BM), (unsigned)((Taug + ROM_BN - 1) / ROM_BN));
+        rom_combine_kernel<<<g1, 256, comb_smem, st>>>(d_par, s0, s1, nt, h->d_S.p, Taug, h->d_romC.p);
+        const int g2 = (int)std::min<int64_t>((s1 - s0 + wpb - 1) / wpb, (int64_t)h->sm_count * 4);
+        chol<<<g2, wpb * 32, chol_smem, st>>>(h->d_romC.p, s0, s1, nr, nobs, h->d_obs_phi.p, d_wr, d_qoi, d_status, a);
+        h->launches += 2;
+    }
+    TFIN_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int tfin_rom(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int32_t mem, double* wr_out,
                         double* qoi_out, int32_t* status_out, void* stream) {
     CHECK_HANDLE(h);
@@ -839,29 +906,79 @@ extern "C" int tfin_rom(tfin_handle_t h, const double* in, int64_t N, int32_t in
     if (int e = sg.out_alloc(qoi_out, (size_t)N * nobs, h->d_qoi, &d_qoi)) return e;
     if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
 
-    const int Taug = rom_taug(nr), P2 = nt * (nt + 1) / 2;
-    const int per_warp = ((Taug + 2 * nr + 2) + 1) & ~1;
-    int wpb = std::min<int>(8, (int)((size_t)(h->max_smem_optin - 1024) / ((size_t)per_warp * 8)));
-    if (wpb < 1) return fail(TFIN_E_STATE, "tfin_rom: n_r = %d does not fit shared memory", nr);
-    const size_t chol_smem = (size_t)wpb * per_warp * 8;
-    const size_t comb_smem = ((size_t)P2 * (ROM_BM + ROM_BN) + (size_t)ROM_BM * nt) * 8;
-    const int64_t chunk = h->rom_chunk > 0 ? h->rom_chunk : (int64_t)h->sm_count * wpb * 8;
-    if (int e = h->d_romC.reserve((size_t)std::min<int64_t>(chunk, N) * Taug)) return e;
-    TFIN_CUDA(cudaFuncSetAttribute(rom_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comb_smem));
-    const int maxm = (nr + 1 + 31) / 32;
-    auto chol = maxm == 1 ? rom_chol_kernel<1> : maxm == 2 ? rom_chol_kernel<2> : maxm == 3 ? rom_chol_kernel<3> : rom_chol_kernel<4>;
-    TFIN_CUDA(cudaFuncSetAttribute(chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
-    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
-        const int64_t s1 = std::min<int64_t>(N, s0 + chunk);
-        dim3 g1((unsigned)((s1 - s0 + ROM_BM - 1) / ROM_BM), (unsigned)((Taug + ROM_BN - 1) / ROM_BN));
-        rom_combine_kernel<<<g1, 256, comb_smem, st>>>(d_par, s0, s1, nt, h->d_S.p, Taug, h->d_romC.p);
-        const int g2 = (int)std::min<int64_t>((s1 - s0 + wpb - 1) / wpb, (int64_t)h->sm_count * 4);
-        chol<<<g2, wpb * 32, chol_smem, st>>>(h->d_romC.p, s0, s1, nr, nobs, h->d_obs_phi.p, d_wr, d_qoi, d_status);
-        h->launches += 2;
-    }
+    if (int e = rom_run(h, d_par, N, st, d_wr, d_qoi, d_status, nullptr)) return e;
     TFIN_CUDA(cudaGetLastError());
     if (int e = sg.out_copy(wr_out, (size_t)N * nr, d_wr)) return e;
     if (int e = sg.out_copy(qoi_out, (size_t)N * nobs, d_qoi)) return e;
+    if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
+    if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int tfin_rom_gradient(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int32_t mem,
+                                 const double* data, int64_t data_rows, int32_t grad_kind, double* grad_out,
+                                 double* cost_out, double* qoi_out, double* wr_out, int32_t* status_out,
+                                 void* stream) {
+    CHECK_HANDLE(h);
+    if (h->n_r <= 0 || h->rg_ob <= 0)
+        return fail(TFIN_E_STATE, "tfin_rom_gradient: call tfin_set_rom and tfin_set_rom_gradient first");
+    if ((in_kind != TFIN_IN_PARAMS && in_kind != TFIN_IN_NODAL) || (grad_kind != TFIN_IN_PARAMS && grad_kind != TFIN_IN_NODAL))
+        return fail(TFIN_E_ARG, "tfin_rom_gradient: bad in_kind / grad_kind");
+    if (N < 0 || (N > 0 && (!in || !grad_out || !data || (data_rows != 1 && data_rows != N))))
+        return fail(TFIN_E_ARG, "tfin_rom_gradient: bad batch argument (data must have 1 or N rows)");
+    if (N == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    Staged sg{h, st, mem == TFIN_MEM_HOST};
+    const int nt = h->rom_terms, nparam = nt - 1, nr = h->n_r, nobs = h->rom_obs;
+    const bool nodal_in = in_kind == TFIN_IN_NODAL, nodal_out = grad_kind == TFIN_IN_NODAL;
+    if ((nodal_in || nodal_out) && (h->n <= 0 || h->n_avg != nparam))
+        return fail(TFIN_E_STATE, "tfin_rom_gradient: nodal input/output needs tfin_set_operator and tfin_set_averaging with %d rows", nparam);
+    const int in_cols = nodal_in ? h->n : nparam;
+    const double *d_in, *d_data;
+    if (int e = sg.in(in, (size_t)N * in_cols, h->d_in, &d_in)) return e;
+    if (int e = sg.in(data, (size_t)data_rows * nobs, h->d_data, &d_data)) return e;
+    const double* d_par = d_in;
+    if (nodal_in) {  // grad_reduced(k) starts with forward_reduced(k): theta = subfin_avg_op(k), :336, :274
+        if (int e = h->d_theta.reserve((size_t)N * nparam)) return e;
+        CsrRows avg{h->n_avg, h->d_avg_ptr.p, h->d_avg_idx.p, h->d_avg_val.p};
+        if (int e = launch_project(h, avg, d_in, N, h->d_theta.p, st)) return e;
+        d_par = h->d_theta.p;
+    }
+    const int grad_cols = nodal_out ? h->n : nparam;
+    double *d_wr, *d_qoi, *d_cost, *d_grad;
+    int* d_status;
+    if (int e = h->d_wr.reserve((size_t)N * nr)) return e;   // w_r is always needed by the contraction
+    d_wr = (!sg.host && wr_out) ? wr_out : h->d_wr.p;
+    if (int e = h->d_vr.reserve((size_t)N * nr)) return e;
+    if (int e = sg.out_alloc(qoi_out, (size_t)N * nobs, h->d_qoi, &d_qoi)) return e;
+    if (int e = sg.out_alloc(cost_out, (size_t)N, h->d_cost, &d_cost)) return e;
+    if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
+    if (int e = sg.out_alloc(grad_out, (size_t)N * grad_cols, h->d_grad, &d_grad)) return e;
+    double* d_g = d_grad;
+    if (nodal_out) {
+        if (int e = h->d_gtheta.reserve((size_t)N * nparam)) return e;
+        d_g = h->d_gtheta.p;
+    }
+    RomAdj adj{d_data, data_rows == 1 ? 0 : (long long)nobs, h->d_vr.p, d_cost};
+    if (int e = rom_run(h, d_par, N, st, d_wr, d_qoi, d_status, &adj)) return e;
+    const size_t gsm = rom_grad_smem(nr, nparam);
+    if (gsm > (size_t)h->max_smem_optin) return fail(TFIN_E_STATE, "tfin_rom_gradient: n_r = %d does not fit shared memory", nr);
+    TFIN_CUDA(cudaFuncSetAttribute(rom_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    const int gg = (int)std::min<int64_t>((N + RG_BM - 1) / RG_BM, h->sm_count);
+    rom_grad_kernel<<<gg, 256, gsm, st>>>(d_par, d_wr, h->d_vr.p, (long long)N, nr, nt, h->d_NG.p, h->rg_ob, d_g);
+    h->launches += 1;
+    if (nodal_out) {
+        CsrRows avgT{h->n, h->d_avgT_ptr.p, h->d_avgT_idx.p, h->d_avgT_val.p};
+        const int64_t total = N * h->n;
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+        rom_grad_lift_kernel<<<blocks, 256, 0, st>>>(avgT, d_g, (long long)N, nparam, d_grad);
+        h->launches += 1;
+    }
+    TFIN_CUDA(cudaGetLastError());
+    if (int e = sg.out_copy(grad_out, (size_t)N * grad_cols, d_grad)) return e;
+    if (int e = sg.out_copy(cost_out, (size_t)N, d_cost)) return e;
+    if (int e = sg.out_copy(qoi_out, (size_t)N * nobs, d_qoi)) return e;
+    if (int e = sg.out_copy(wr_out, (size_t)N * nr, (const double*)d_wr)) return e;
     if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
     if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
     return 0;

@@ -19,7 +19,7 @@ from ..assembly import BIOT, build_operators, five_to_nine
 from ..fom.forward_solve import DEFAULT_MAXIT, DEFAULT_TOL, _as_batch
 from ..fom.thermal_fin import FinSpace, Function
 
-__all__ = ["AffineROMFin", "rom_offline_tensors"]
+__all__ = ["AffineROMFin", "rom_offline_tensors", "rom_gradient_tensors"]
 
 
 def rom_offline_tensors(ops, phi, B_obs):
@@ -42,6 +42,15 @@ def rom_offline_tensors(ops, phi, B_obs):
             pq += 1
     G = np.stack([P.T @ ops.rhs for P in Psi])
     return S, G, B_obs @ phi
+
+
+def rom_gradient_tensors(ops, phi):
+    """Offline Gram blocks of the reduced gradient: gram[t][q-1] = Psi_t^T Psi_q with Psi_t = V_t phi, so that
+    psi^T dA_dsigmak_phi[q-1] = sum_t theta_t gram[t][q-1] (averaged_affine_ROM.py:215-220, 343-348)."""
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    n_terms = ops.vals.shape[0]
+    Psi = [ops.csr(ops.vals[t]) @ phi for t in range(n_terms)]
+    return np.stack([np.stack([Psi[t].T @ Psi[q] for q in range(1, n_terms)]) for t in range(n_terms)])
 
 
 class AffineROMFin:
@@ -90,6 +99,7 @@ class AffineROMFin:
         self._h.set_observation(*self.ops.obs_csr(self.B_obs))
         self._h.set_averaging(*self.ops.obs_csr(self.ops.B_obs))
         self._h.set_rom(S, G, obs_phi)
+        self._grad_ready = False
 
     @property
     def handle(self):
@@ -187,8 +197,32 @@ class AffineROMFin:
         self.dl_model = model
 
     # ------------------------------------------------------------------ 'next' rows
-    def grad_reduced(self, k):
-        raise NotImplementedError("ROM adjoint gradient (averaged_affine_ROM.py:335-356) is a 'next' row in DESIGN.md")
+    def _rom_gradient(self, batch, in_kind, grad_kind, data):
+        data = self.data if data is None else data
+        if data is None:
+            raise ValueError("grad_reduced: call set_data(data) first (averaged_affine_ROM.py:398)")
+        if not self._grad_ready:   # 90 Gram blocks of n_r x n_r, built on first use
+            self._h.set_rom_gradient(rom_gradient_tensors(self.ops, self.phi))
+            self._grad_ready = True
+        t_i = time.time()
+        out = self._h.rom_gradient(batch, data, in_kind, grad_kind)
+        self._check(out)
+        self.rom_grad_time += time.time() - t_i
+        return out
+
+    def grad_reduced(self, k, data=None):
+        """:335-356.  ``k`` nodal field (n,) | (N, n) -> ``(dJ_dk, J)`` with dJ_dk (n,) | (N, n); the observation
+        vector is ``set_data``'s (one for all samples) unless ``data`` (n_obs,) | (N, n_obs) is given."""
+        kb, single = _as_batch(k, self.dofs, "AffineROMFin.grad_reduced")
+        out = self._rom_gradient(kb, _cabi.IN_NODAL, _cabi.IN_NODAL, data)
+        return (out["grad"][0], float(out["cost"][0])) if single else (out["grad"], out["cost"])
+
+    def grad_reduced_nine_param(self, k_s, data=None):
+        """The same gradient with respect to the nine sub-fin conductivities (the factor ``psi_v_r^T A_phi_w_r`` of
+        :349-351 before it is multiplied by ``dsigma_dk``): (9,) | (N, 9) -> ``(g, J)``."""
+        tb, single = _as_batch(k_s, self.num_params, "AffineROMFin.grad_reduced_nine_param")
+        out = self._rom_gradient(tb, _cabi.IN_PARAMS, _cabi.IN_PARAMS, data)
+        return (out["grad"][0], float(out["cost"][0])) if single else (out["grad"], out["cost"])
 
     def grad_romml(self, k):
         raise NotImplementedError("ROM+NN gradient (averaged_affine_ROM.py:358-396) is out of scope (TensorFlow model)")

@@ -128,6 +128,28 @@ int tfin_rom(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int3
              double* qoi_out, int32_t* status_out, void* stream);
 
 /*
+ * Offline Gram blocks for the reduced gradient: gram[t][q-1] = Psi_t^T Psi_q (n_r x n_r, row-major) for
+ * t = 0..n_terms-1, q = 1..n_terms-1 with Psi_t = vals[t] phi, i.e. psi^T (dA_dsigmak_phi[q-1]) =
+ * sum_t theta_t gram[t][q-1]  (rom/averaged_affine_ROM.py:215-220, 343-348).  Requires tfin_set_rom first.
+ */
+int tfin_set_rom_gradient(tfin_handle_t h, int32_t n_r, int32_t n_terms, const double* gram);
+
+/*
+ * Batched reduced-model gradient of J_s = 0.5 ||data_s - (B_obs phi) w_r,s||^2, exactly the reference's formula
+ * = AffineROMFin.grad_reduced(k) (rom/averaged_affine_ROM.py:335-356) for N samples:
+ *   w_r = A_r^{-1} B_r;  v_r = A_r^{-T} (B_obs phi)^T (data - (B_obs phi) w_r);
+ *   g_q = (psi v_r)^T (K_q phi) w_r  (q = 1..n_terms-1);   dJ_dk = g^T dsigma_dk.
+ *   in: (N, n_terms-1) conductivities (TFIN_IN_PARAMS) or (N, n) nodal fields averaged first (TFIN_IN_NODAL)
+ *   data: (data_rows, n_obs) with data_rows == 1 or N
+ *   grad_kind: TFIN_IN_PARAMS -> grad_out (N, n_terms-1) = g;  TFIN_IN_NODAL -> grad_out (N, n) = dJ_dk
+ *              (needs tfin_set_averaging: dsigma_dk = the sub-fin averaging operator, :210)
+ *   cost_out (N) | NULL, qoi_out (N, n_obs) | NULL, wr_out (N, n_r) | NULL, status_out (N) | NULL
+ */
+int tfin_rom_gradient(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int32_t mem,
+                      const double* data, int64_t data_rows, int32_t grad_kind, double* grad_out, double* cost_out,
+                      double* qoi_out, double* wr_out, int32_t* status_out, void* stream);
+
+/*
  * Batched adjoint gradient of J_s = 0.5 ||B_obs w_s - data_s||^2 with respect to the nodal conductivity:
  * = Fin.gradient(k, data) (fom/forward_solve.py:293-322) for N samples.  The forward solve, the adjoint solve
  * A v = -B_obs^T (B_obs w - data) (the reference's dense np.linalg.solve, :310) and the gradient form
