@@ -36,6 +36,9 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfin_rom": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p]),
+    "tfin_set_basis": (C.c_int, [_handle, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "tfin_rom_nodal": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfin_set_rom_gradient": (C.c_int, [_handle, C.c_int32, C.c_int32, C.c_void_p]),
     "tfin_rom_gradient": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -158,6 +161,15 @@ class TfinHandle:
                "tfin_set_rom")
         self.n_r, self.rom_terms, self.rom_obs = n_r, n_terms, n_obs
 
+    def set_basis(self, phi, out_phi):
+        """phi (n, n_r); out_phi (n_out, n_r): rows projected onto the reduced solution by rom_nodal."""
+        phi, out_phi = _f64(phi), _f64(out_phi)
+        if phi.ndim != 2 or phi.shape[0] != self.n or out_phi.ndim != 2 or out_phi.shape[1] != phi.shape[1]:
+            raise ValueError("set_basis: phi must be (n, n_r) and out_phi (n_out, n_r)")
+        _check(self._lib, self._lib.tfin_set_basis(self._h, self.n, phi.shape[1], _ptr(phi), out_phi.shape[0],
+                                                   _ptr(out_phi)), "tfin_set_basis")
+        self.basis_n_r, self.basis_n_out = phi.shape[1], out_phi.shape[0]
+
     def set_rom_gradient(self, gram):
         """gram[t][q-1] = Psi_t^T Psi_q, shape (n_terms, n_terms-1, n_r, n_r)."""
         gram = _f64(gram)
@@ -242,6 +254,21 @@ class TfinHandle:
                                 None)
         _check(self._lib, rc, "tfin_rom")
         return {"w_r": wr, "qoi": qoi, "status": status}
+
+    def rom_nodal(self, k, want_system=True):
+        """Batched Fin.r_fwd_no_full: k (N, n) -> A_r (N, n_r, n_r), B_r, x_r (N, n_r), y (N, n_out)."""
+        k = _f64(k)
+        if k.ndim != 2 or k.shape[1] != self.n:
+            raise ValueError(f"rom_nodal: expected (N, {self.n}) input, got {k.shape}")
+        N, nr = k.shape[0], self.basis_n_r
+        Ar = np.empty((N, nr, nr)) if want_system else None
+        Br = np.empty((N, nr)) if want_system else None
+        xr, y = np.empty((N, nr)), np.empty((N, self.basis_n_out))
+        status = np.empty(N, dtype=np.int32)
+        rc = self._lib.tfin_rom_nodal(self._h, _ptr(k), N, MEM_HOST, _ptr(Ar), _ptr(Br), _ptr(xr), _ptr(y),
+                                      _ptr(status), None)
+        _check(self._lib, rc, "tfin_rom_nodal")
+        return {"A_r": Ar, "B_r": Br, "x_r": xr, "y": y, "status": status}
 
     def rom_gradient(self, batch, data, in_kind=IN_PARAMS, grad_kind=IN_PARAMS, want_wr=False):
         """Batched AffineROMFin.grad_reduced: -> grad (N, n_terms-1 | n), cost (N), qoi (N, n_obs)."""

@@ -11,6 +11,7 @@
 #include "project.cuh"
 #include "pcg_stream.cuh"
 #include "rom.cuh"
+#include "rom_nodal.cuh"
 
 using namespace tfin;
 
@@ -126,6 +127,9 @@ struct tfin_ctx {
     int n_r = 0, rom_terms = 0, rom_obs = 0;
     DevBuf<double> d_S, d_obs_phi, d_romC;
     int64_t rom_chunk = 0;  // 0 = auto
+    // ---- nodal LSPG (R4): padded basis [n][6 TT], projection rows
+    int b_nr = 0, b_nout = 0, b_TT = 0;
+    DevBuf<double> d_bphi, d_bout, d_Ar, d_Br, d_y;
     // ---- ROM gradient (R3): Gram blocks Psi_t^T Psi_q, transposed averaging operator
     int rg_ob = 0;
     DevBuf<double> d_NG, d_vr, d_gtheta, d_avgT_val;
@@ -184,7 +188,8 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
         b->release();
     h->d_obsT_ptr.release();
     h->d_obsT_idx.release();
-    for (auto* b : {&h->d_NG, &h->d_vr, &h->d_gtheta, &h->d_avgT_val}) b->release();
+    for (auto* b : {&h->d_NG, &h->d_vr, &h->d_gtheta, &h->d_avgT_val, &h->d_bphi, &h->d_bout, &h->d_Ar, &h->d_Br, &h->d_y})
+        b->release();
     h->d_avgT_ptr.release();
     h->d_avgT_idx.release();
     h->d_scolterm.release();
@@ -845,19 +850,42 @@ extern "C" int tfin_fom_nodal(tfin_handle_t h, const double* k, int64_t N, int32
                       relres_out, stream);
 }
 
-// Combine + Cholesky over chunks of samples (R1 + R2); with `adj` the Cholesky kernel also solves the reduced adjoint.
-static int rom_run(tfin_ctx* h, const double* d_par, int64_t N, cudaStream_t st, double* d_wr, double* d_qoi,
-                   int* d_status, const RomAdj* adj) {
-    const int nt = h->rom_terms, nr = h->n_r, nobs = h->rom_obs;
+// Producer of the packed reduced systems of a chunk: the affine Gram combination (R1, theta input) or the per-sample
+// nodal assembly + Gram kernel (R4, nodal k input).
+struct RomSrc {
+    bool nodal = false;
+    const double* d_in = nullptr;   // theta (N, n_terms-1) | k (N, n)
+    double* d_Ar = nullptr;         // nodal only: dense A_r / B_r outputs (optional)
+    double* d_Br = nullptr;
+};
+
+// Reduced systems + Cholesky over chunks of samples (R1|R4 + R2); with `adj` the Cholesky kernel also solves the
+// reduced adjoint.
+static int rom_run(tfin_ctx* h, const RomSrc& src, int nr, int nobs, const double* d_obs_phi, int64_t N,
+                   cudaStream_t st, double* d_wr, double* d_qoi, int* d_status, const RomAdj* adj) {
+    const int nt = h->rom_terms;
     const int Taug = rom_taug(nr), P2 = nt * (nt + 1) / 2;
     const int per_warp = ((Taug + 2 * nr + 2) + 1) & ~1;
     int wpb = std::min<int>(8, (int)((size_t)(h->max_smem_optin - 1024) / ((size_t)per_warp * 8)));
     if (wpb < 1) return fail(TFIN_E_STATE, "tfin_rom: n_r = %d does not fit shared memory", nr);
     const size_t chol_smem = (size_t)wpb * per_warp * 8;
-    const size_t comb_smem = ((size_t)P2 * (ROM_BM + ROM_BN) + (size_t)ROM_BM * nt) * 8;
     const int64_t chunk = h->rom_chunk > 0 ? h->rom_chunk : (int64_t)h->sm_count * wpb * 8;
     if (int e = h->d_romC.reserve((size_t)std::min<int64_t>(chunk, N) * Taug)) return e;
-    TFIN_CUDA(cudaFuncSetAttribute(rom_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comb_smem));
+    size_t comb_smem = 0, gram_smem = 0;
+    int gram_threads = 0, gram_occ = 1;
+    if (!src.nodal) {
+        comb_smem = ((size_t)P2 * (ROM_BM + ROM_BN) + (size_t)ROM_BM * nt) * 8;
+        TFIN_CUDA(cudaFuncSetAttribute(rom_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comb_smem));
+    } else {
+        const int TT = h->b_TT;
+        gram_smem = RomNodalSmem::make(h->n_cells, 6 * TT, h->Wn).total;
+        gram_threads = (TT * (TT + 1) / 2 + 31) & ~31;
+        if (gram_smem > (size_t)h->max_smem_optin || gram_threads > 256)
+            return fail(TFIN_E_STATE, "nodal LSPG: n_r = %d / n_cells = %d do not fit one CTA", nr, h->n_cells);
+        TFIN_CUDA(cudaFuncSetAttribute(rom_nodal_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem));
+        TFIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gram_occ, rom_nodal_gram_kernel, gram_threads, gram_smem));
+        if (gram_occ < 1) return fail(TFIN_E_STATE, "nodal LSPG: kernel does not fit an SM");
+    }
     const int maxm = (nr + 1 + 31) / 32;
     auto chol = adj ? (maxm == 1 ? rom_chol_kernel<1, true> : maxm == 2 ? rom_chol_kernel<2, true>
                        : maxm == 3 ? rom_chol_kernel<3, true> : rom_chol_kernel<4, true>)
@@ -867,10 +895,27 @@ static int rom_run(tfin_ctx* h, const double* d_par, int64_t N, cudaStream_t st,
     const RomAdj a = adj ? *adj : RomAdj{};
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
         const int64_t s1 = std::min<int64_t>(N, s0 + chunk);
-        dim3 g1((unsigned)((s1 - s0 + ROM_BM - 1) / ROM_BM), (unsigned)((Taug + ROM_BN - 1) / ROM_BN));
-        rom_combine_kernel<<<g1, 256, comb_smem, st>>>(d_par, s0, s1, nt, h->d_S.p, Taug, h->d_romC.p);
+        if (!src.nodal) {
+            dim3 g1((unsigned)((s1 - s0 + ROM_BM - 1) / ROM_BM), (unsigned)((Taug + ROM_BN - 1) / ROM_BN));
+            rom_combine_kernel<<<g1, 256, comb_smem, st>>>(src.d_in, s0, s1, nt, h->d_S.p, Taug, h->d_romC.p);
+        } else {
+            PcgOp op{};
+            op.n = h->n; op.ld = h->ld; op.W = h->Wn; op.n_cells = h->n_cells; op.rhs = h->d_rhs.p;
+            op.col = h->d_ncol.p; op.cell = h->d_ncell.p; op.coef = h->d_ncoef.p; op.cst = h->d_ncst.p;
+            op.dptr = h->d_dptr.p; op.dcell = h->d_dcell.p; op.dcoef = h->d_dcoef.p; op.dcst = h->d_dcst.p;
+            op.cells = h->d_cells.p;
+            const int g1 = (int)std::min<int64_t>(s1 - s0, (int64_t)h->sm_count * gram_occ);
+            rom_nodal_gram_kernel<<<g1, gram_threads, gram_smem, st>>>(op, src.d_in, s0, s1, h->d_bphi.p, nr, h->b_TT,
+                                                                       h->d_romC.p);
+            if (src.d_Ar || src.d_Br) {
+                const int64_t total = (s1 - s0) * (int64_t)nr * (nr + 1);
+                const int gb = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+                rom_unpack_kernel<<<gb, 256, 0, st>>>(h->d_romC.p, s0, s1, nr, src.d_Ar, src.d_Br);
+                h->launches += 1;
+            }
+        }
         const int g2 = (int)std::min<int64_t>((s1 - s0 + wpb - 1) / wpb, (int64_t)h->sm_count * 4);
-        chol<<<g2, wpb * 32, chol_smem, st>>>(h->d_romC.p, s0, s1, nr, nobs, h->d_obs_phi.p, d_wr, d_qoi, d_status, a);
+        chol<<<g2, wpb * 32, chol_smem, st>>>(h->d_romC.p, s0, s1, nr, nobs, d_obs_phi, d_wr, d_qoi, d_status, a);
         h->launches += 2;
     }
     TFIN_CUDA(cudaGetLastError());
@@ -906,10 +951,65 @@ extern "C" int tfin_rom(tfin_handle_t h, const double* in, int64_t N, int32_t in
     if (int e = sg.out_alloc(qoi_out, (size_t)N * nobs, h->d_qoi, &d_qoi)) return e;
     if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
 
-    if (int e = rom_run(h, d_par, N, st, d_wr, d_qoi, d_status, nullptr)) return e;
+    RomSrc src;
+    src.d_in = d_par;
+    if (int e = rom_run(h, src, nr, nobs, h->d_obs_phi.p, N, st, d_wr, d_qoi, d_status, nullptr)) return e;
     TFIN_CUDA(cudaGetLastError());
     if (int e = sg.out_copy(wr_out, (size_t)N * nr, d_wr)) return e;
     if (int e = sg.out_copy(qoi_out, (size_t)N * nobs, d_qoi)) return e;
+    if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
+    if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int tfin_set_basis(tfin_handle_t h, int32_t n, int32_t n_r, const double* phi, int32_t n_out,
+                              const double* out_phi) {
+    CHECK_HANDLE(h);
+    if (h->n <= 0) return fail(TFIN_E_STATE, "tfin_set_basis: call tfin_set_operator first");
+    if (!phi || n != h->n || n_r <= 0 || n_r > 127 || n_out <= 0 || !out_phi)
+        return fail(TFIN_E_ARG, "tfin_set_basis: bad argument (n must match the operator, n_r in [1,127])");
+    const int TT = (n_r + 1 + 5) / 6, nrp = 6 * TT;  // one spare column for the right-hand side
+    std::vector<double> pad((size_t)n * nrp, 0.0);
+    for (int i = 0; i < n; ++i) std::copy(phi + (size_t)i * n_r, phi + (size_t)(i + 1) * n_r, pad.begin() + (size_t)i * nrp);
+    std::vector<double> op(out_phi, out_phi + (size_t)n_out * n_r);
+    if (int e = h->d_bphi.upload(pad, h->stream)) return e;
+    if (int e = h->d_bout.upload(op, h->stream)) return e;
+    TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    h->b_nr = n_r;
+    h->b_nout = n_out;
+    h->b_TT = TT;
+    return 0;
+}
+
+extern "C" int tfin_rom_nodal(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double* Ar_out,
+                              double* Br_out, double* xr_out, double* y_out, int32_t* status_out, void* stream) {
+    CHECK_HANDLE(h);
+    if (h->b_nr <= 0) return fail(TFIN_E_STATE, "tfin_rom_nodal: call tfin_set_basis first");
+    if (h->n_cells <= 0) return fail(TFIN_E_STATE, "tfin_rom_nodal: call tfin_set_cells first");
+    if (N < 0 || (N > 0 && !k)) return fail(TFIN_E_ARG, "tfin_rom_nodal: bad batch argument");
+    if (N == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    Staged sg{h, st, mem == TFIN_MEM_HOST};
+    const int nr = h->b_nr, nout = h->b_nout;
+    const double* d_k;
+    if (int e = sg.in(k, (size_t)N * h->n, h->d_in, &d_k)) return e;
+    double *d_Ar, *d_Br, *d_xr, *d_y;
+    int* d_status;
+    if (int e = sg.out_alloc(Ar_out, (size_t)N * nr * nr, h->d_Ar, &d_Ar)) return e;
+    if (int e = sg.out_alloc(Br_out, (size_t)N * nr, h->d_Br, &d_Br)) return e;
+    if (int e = sg.out_alloc(xr_out, (size_t)N * nr, h->d_wr, &d_xr)) return e;
+    if (int e = sg.out_alloc(y_out, (size_t)N * nout, h->d_y, &d_y)) return e;
+    if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
+    RomSrc src;
+    src.nodal = true;
+    src.d_in = d_k;
+    src.d_Ar = d_Ar;
+    src.d_Br = d_Br;
+    if (int e = rom_run(h, src, nr, nout, h->d_bout.p, N, st, d_xr, d_y, d_status, nullptr)) return e;
+    if (int e = sg.out_copy(Ar_out, (size_t)N * nr * nr, d_Ar)) return e;
+    if (int e = sg.out_copy(Br_out, (size_t)N * nr, d_Br)) return e;
+    if (int e = sg.out_copy(xr_out, (size_t)N * nr, d_xr)) return e;
+    if (int e = sg.out_copy(y_out, (size_t)N * nout, d_y)) return e;
     if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
     if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -960,7 +1060,9 @@ extern "C" int tfin_rom_gradient(tfin_handle_t h, const double* in, int64_t N, i
         d_g = h->d_gtheta.p;
     }
     RomAdj adj{d_data, data_rows == 1 ? 0 : (long long)nobs, h->d_vr.p, d_cost};
-    if (int e = rom_run(h, d_par, N, st, d_wr, d_qoi, d_status, &adj)) return e;
+    RomSrc src;
+    src.d_in = d_par;
+    if (int e = rom_run(h, src, nr, nobs, h->d_obs_phi.p, N, st, d_wr, d_qoi, d_status, &adj)) return e;
     const size_t gsm = rom_grad_smem(nr, nparam);
     if (gsm > (size_t)h->max_smem_optin) return fail(TFIN_E_STATE, "tfin_rom_gradient: n_r = %d does not fit shared memory", nr);
     TFIN_CUDA(cudaFuncSetAttribute(rom_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));

@@ -42,6 +42,7 @@ class Fin:
     def __init__(self, V: FinSpace, external_obs=False, *, device=0, tol=DEFAULT_TOL, maxit=DEFAULT_MAXIT,
                  prune_zeros=True):
         self.phi = None
+        self._basis_on_device = None
         self.V = V
         self.ops = build_operators(V)
         self.dofs = self.ops.n
@@ -178,10 +179,55 @@ class Fin:
         """forward_solve.py:396-406."""
         return self.ops.C.copy(), self.ops.domain_measure
 
-    # ------------------------------------------------------------------ not on the batched path (yet)
+    # ------------------------------------------------------------------ generic / nodal LSPG reduction
     def reduced_forward(self, A, B, C, psi, phi):
-        raise NotImplementedError("dense generic LSPG (forward_solve.py:421-452) is not part of the batched "
-                                  "path; use AffineROMFin.forward_reduced (DESIGN.md, 'next').")
+        """forward_solve.py:421-452: dense LSPG reduction ``A_r = psi^T A phi, B_r = psi^T B, C_r = C phi,
+        x_r = solve(A_r, B_r), y_r = C_r x_r`` for caller-supplied dense operators.  Plain dense linear algebra:
+        run as library GEMMs + LU on the handle's device (torch -> cuBLAS/cuSOLVER, fp64); no CPU path."""
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("Fin.reduced_forward needs a CUDA device (there is no CPU fallback)")
+        dev = torch.device("cuda", self._h.device)
+        t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev)
+        self.phi = np.asarray(phi, dtype=np.float64)                     # :446
+        A_d, B_d, C_d, psi_d, phi_d = t(A), t(B), t(C), t(psi), t(phi)
+        A_r = psi_d.T @ (A_d @ phi_d)
+        B_r = psi_d.T @ B_d
+        C_r = C_d @ phi_d
+        x_r = torch.linalg.solve(A_r, B_r)
+        y_r = C_r @ x_r
+        return A_r.cpu().numpy(), B_r.cpu().numpy(), C_r.cpu().numpy(), x_r.cpu().numpy(), y_r.cpu().numpy()[()]
 
     def r_fwd_no_full(self, k, phi):
-        raise NotImplementedError("nodal-conductivity LSPG (forward_solve.py:454-464) is a 'next' row in DESIGN.md")
+        """forward_solve.py:454-464: LSPG reduction of the nodal-conductivity operator with ``psi = A(k) phi``,
+        without forming the full solution.  ``k`` (n,) | (N, n); returns ``(A_r, B_r, C_r, x_r, y_r)`` with a leading
+        batch axis on A_r, B_r, x_r, y_r for batched input.  A(k) is assembled per sample inside the Gram kernel."""
+        kb, single = _as_batch(k, self.dofs, "Fin.r_fwd_no_full")
+        out = self._r_fwd(kb, phi, want_system=True)
+        C_r = np.dot(self.C, self.phi)                                   # :442
+        if single:
+            return out["A_r"][0], out["B_r"][0], C_r, out["x_r"][0], float(out["y"][0, 0])
+        return out["A_r"], out["B_r"], C_r, out["x_r"], out["y"][:, 0]
+
+    def r_fwd_no_full_qoi(self, k, phi):
+        """Fused ``reduced_qoi_operator(r_fwd_no_full(k, phi)[3])`` (:415-419): (n,)|(N,n) -> (n_obs,)|(N,n_obs)."""
+        kb, single = _as_batch(k, self.dofs, "Fin.r_fwd_no_full_qoi")
+        out = self._r_fwd(kb, phi, want_system=False)
+        return out["y"][0, 1:] if single else out["y"][:, 1:]
+
+    def _r_fwd(self, kb, phi, want_system):
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        if phi.ndim != 2 or phi.shape[0] != self.dofs:
+            raise ValueError(f"phi must be ({self.dofs}, n_r), got {phi.shape}")
+        cached = self._basis_on_device
+        if cached is None or cached.shape != phi.shape or not np.array_equal(cached, phi):
+            # projection rows: the legacy scalar QoI C_r = C phi (:442), then B_obs phi (reduced_qoi_operator)
+            self._h.set_basis(phi, np.vstack([np.dot(self.C, phi)[None, :], np.dot(self.B_obs, phi)]))
+            self._basis_on_device = phi.copy()
+        self.phi = phi                                                   # :446
+        out = self._h.rom_nodal(kb, want_system=want_system)
+        st = out["status"]
+        if np.any(st != _cabi.STATUS_CONVERGED):
+            bad = np.nonzero(st != _cabi.STATUS_CONVERGED)[0]
+            raise RuntimeError(f"reduced system not SPD for {len(bad)} sample(s) (first: {bad[0]}); is k > 0?")
+        return out

@@ -128,6 +128,23 @@ int tfin_rom(tfin_handle_t h, const double* in, int64_t N, int32_t in_kind, int3
              double* qoi_out, int32_t* status_out, void* stream);
 
 /*
+ * Reduced basis for the nodal-conductivity LSPG model (Fin.reduced_forward / r_fwd_no_full,
+ * fom/forward_solve.py:421-464): phi (n, n_r) row-major and the rows projected onto the reduced solution,
+ * out_phi (n_out, n_r), e.g. C_r = C phi (:442) and B_obs phi (:415-419).  Requires tfin_set_operator.
+ */
+int tfin_set_basis(tfin_handle_t h, int32_t n, int32_t n_r, const double* phi, int32_t n_out, const double* out_phi);
+
+/*
+ * Batched nodal-conductivity LSPG reduced solve = Fin.r_fwd_no_full(k, phi) (fom/forward_solve.py:454-464) for N fields:
+ *   psi = A(k) phi (A assembled per sample in-kernel), A_r = psi^T A phi, B_r = psi^T b, x_r = A_r^{-1} B_r,
+ *   y = out_phi x_r.   Requires tfin_set_cells and tfin_set_basis.
+ *   Ar_out (N, n_r, n_r) | NULL, Br_out (N, n_r) | NULL, xr_out (N, n_r) | NULL, y_out (N, n_out) | NULL,
+ *   status_out (N) | NULL
+ */
+int tfin_rom_nodal(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double* Ar_out, double* Br_out,
+                   double* xr_out, double* y_out, int32_t* status_out, void* stream);
+
+/*
  * Offline Gram blocks for the reduced gradient: gram[t][q-1] = Psi_t^T Psi_q (n_r x n_r, row-major) for
  * t = 0..n_terms-1, q = 1..n_terms-1 with Psi_t = vals[t] phi, i.e. psi^T (dA_dsigmak_phi[q-1]) =
  * sum_t theta_t gram[t][q-1]  (rom/averaged_affine_ROM.py:215-220, 343-348).  Requires tfin_set_rom first.

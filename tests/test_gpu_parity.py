@@ -334,3 +334,38 @@ def test_rom_grad_reduced(rom_m3, oracle_m3, pod_m3):
     assert np.allclose(g9 @ rom_m3.dsigma_dk, dJ_each, rtol=1e-13, atol=1e-300)
     for s in (5, 40):
         assert relerr(g9[s], orc.grad_reduced(k[s], data[s], pod_m3)[2]) <= 1e-8
+
+
+def test_r_fwd_no_full_and_reduced_forward(fin_m3, oracle_m3, pod_m3):
+    """Fin.r_fwd_no_full / reduced_forward (forward_solve.py:421-464): nodal-conductivity LSPG with in-kernel
+    assembly of A(k), psi = A phi and the Gram matrix, against the oracle's dense restatement."""
+    orc = oracle_m3
+    rng = np.random.default_rng(29)
+    k = np.exp(0.4 * rng.standard_normal((6, orc.n)))
+    A_r, B_r, C_r, x_r, y_r = fin_m3.r_fwd_no_full(k, pod_m3)
+    assert A_r.shape == (6, 81, 81) and B_r.shape == (6, 81) and x_r.shape == (6, 81) and y_r.shape == (6,)
+    q_r = fin_m3.r_fwd_no_full_qoi(k, pod_m3)
+    for s in range(6):
+        A_ref, B_ref, C_ref, x_ref, y_ref = orc.r_fwd_no_full(k[s], pod_m3)
+        assert np.max(np.abs(A_r[s] - A_ref)) <= 1e-12 * np.max(np.abs(A_ref))
+        assert np.max(np.abs(B_r[s] - B_ref)) <= 1e-12 * np.max(np.abs(B_ref))
+        assert np.allclose(C_r, C_ref, rtol=1e-12, atol=0)
+        assert abs(y_r[s] - y_ref) <= 1e-9 * abs(y_ref)                  # cond(A_r) ~ 1e10: observables, not x_r
+        assert relerr(q_r[s], orc.B_obs @ (pod_m3 @ x_ref)) <= 1e-8
+        assert np.array_equal(A_r[s], A_r[s].T)
+    one = fin_m3.r_fwd_no_full(k[2], pod_m3)                             # single-sample signature
+    assert one[0].shape == (81, 81) and isinstance(one[4], float) and one[4] == y_r[2]
+    assert relerr(fin_m3.reduced_qoi_operator(one[3]), q_r[2]) <= 1e-12
+    # a smaller basis (n_r not a multiple of 6, one 32-lane slab) re-uploads transparently
+    phi20 = np.ascontiguousarray(pod_m3[:, :20])
+    out20 = fin_m3.r_fwd_no_full(k[:2], phi20)
+    for s in range(2):
+        ref = orc.r_fwd_no_full(k[s], phi20)
+        assert np.max(np.abs(out20[0][s] - ref[0])) <= 1e-12 * np.max(np.abs(ref[0]))
+        assert abs(out20[4][s] - ref[4]) <= 1e-10 * abs(ref[4])
+    # generic dense reduction with caller-supplied operators
+    A = orc.matrix_nodal(k[0]).toarray()
+    got = fin_m3.reduced_forward(A, orc.B, orc.C, A @ pod_m3, pod_m3)
+    ref = orc.reduced_forward(A, orc.B, orc.C, A @ pod_m3, pod_m3)
+    assert np.max(np.abs(got[0] - ref[0])) <= 1e-12 * np.max(np.abs(ref[0]))
+    assert abs(got[4] - ref[4]) <= 1e-8 * abs(ref[4])
