@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtfin.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
+KERN_SQ_EXP, KERN_M52, KERN_M32 = 0, 1, 2
 IN_PARAMS, IN_NODAL = 0, 1
 STATUS_CONVERGED, STATUS_MAXIT, STATUS_BREAKDOWN = 0, 1, 2
 
@@ -48,6 +49,10 @@ SIGNATURES = {
                                           C.c_void_p, C.c_void_p]),
     "tfin_fom_nodal_sensitivity": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tfin_field_set_cov": (C.c_int, [_handle, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
+    "tfin_field_set_chol": (C.c_int, [_handle, C.c_int32, C.c_void_p]),
+    "tfin_field_sample": (C.c_int, [_handle, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "tfin_subfin_avg": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "tfin_kernel_launches": (C.c_int64, [_handle]),
     "tfin_get_int": (C.c_int64, [_handle, C.c_char_p]),
@@ -290,6 +295,42 @@ class TfinHandle:
                                          None)
         _check(self._lib, rc, "tfin_rom_gradient")
         return {"grad": grad, "cost": cost, "qoi": qoi, "w_r": wr, "status": status}
+
+    # ---- Gaussian-field sampler
+    def field_set_cov(self, coords, kern_type=KERN_M52, length=1.6, want_chol=True):
+        """Covariance + Cholesky on the device; returns the upper factor (n, n) like scipy.linalg.cholesky."""
+        coords = _f64(coords)
+        if coords.ndim != 2 or coords.shape[1] != 2:
+            raise ValueError("field_set_cov: coords must be (n, 2)")
+        n = coords.shape[0]
+        chol = np.empty((n, n)) if want_chol else None
+        _check(self._lib, self._lib.tfin_field_set_cov(self._h, n, _ptr(coords), int(kern_type), float(length),
+                                                       _ptr(chol)), "tfin_field_set_cov")
+        self.field_n = n
+        return chol
+
+    def field_set_chol(self, chol):
+        chol = _f64(chol)
+        if chol.ndim != 2 or chol.shape[0] != chol.shape[1]:
+            raise ValueError("field_set_chol: chol must be square")
+        _check(self._lib, self._lib.tfin_field_set_chol(self._h, chol.shape[0], _ptr(chol)), "tfin_field_set_chol")
+        self.field_n = chol.shape[0]
+
+    def field_sample(self, N=None, z=None, seed=0, subsequence=0, want_z=False):
+        """k = exp(0.5 chol^T z): from given normals z (N, n) or from the device generator (N, seed)."""
+        n = self.field_n
+        if z is not None:
+            z = _f64(z)
+            if z.ndim != 2 or z.shape[1] != n:
+                raise ValueError(f"field_sample: z must be (N, {n})")
+            N = z.shape[0]
+        elif N is None:
+            raise ValueError("field_sample: give N or z")
+        k = np.empty((int(N), n))
+        z_out = np.empty((int(N), n)) if want_z else None
+        _check(self._lib, self._lib.tfin_field_sample(self._h, _ptr(z), int(seed), int(subsequence), int(N), MEM_HOST, _ptr(k),
+                                                      _ptr(z_out), None), "tfin_field_sample")
+        return (k, z_out) if want_z else k
 
     def subfin_avg(self, k):
         k = _f64(k)

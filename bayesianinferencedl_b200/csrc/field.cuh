@@ -1,0 +1,221 @@
+// F: Gaussian-random-field conductivity sampler on the device.
+//   covariance over the dof coordinates + Cholesky factor  = make_cov_chol (bayesian_inference/gaussian_field.py:9-31)
+//   k_s = exp(0.5 * chol^T z_s), z_s ~ N(0, I_n)             = deep_learning/generate_fin_dataset.py:87-88
+// The factor is kept as the LOWER triangle L (cov = L L^T, row-major), i.e. chol = L^T, so that
+// (chol^T z)_j = sum_{i <= j} L[j][i] z_i is an "NT" product with both operands contiguous along the contraction.
+#pragma once
+
+#include "common.cuh"
+
+namespace tfin {
+
+// ------------------------------------------------------------------------------------------- F1 covariance
+__global__ void __launch_bounds__(256) field_cov_kernel(const double* __restrict__ xy, int n, int kern, double length,
+                                                        double* __restrict__ cov /* [n][n] */) {
+    const long long total = (long long)n * n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n), j = (int)(e - (long long)i * n);
+        const double dx = xy[2 * i] - xy[2 * j], dy = xy[2 * i + 1] - xy[2 * j + 1];
+        const double d = sqrt(dx * dx + dy * dy);
+        double c;
+        if (kern == TFIN_KERN_SQ_EXP) {
+            c = exp(-(1.0 / (2.0 * length * length)) * (d * d)) + (i == j ? 1e-5 : 0.0);
+        } else if (kern == TFIN_KERN_M52) {
+            const double t = sqrt(5.0) * d / length;
+            c = (1.0 + t + t * t / 3.0) * exp(-t);
+        } else {
+            const double t = sqrt(3.0) * d / length;
+            c = (1.0 + t) * exp(-t);
+        }
+        cov[e] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- F2 blocked Cholesky
+// Right-looking, panel width 32, in place on the lower triangle of a row-major n x n matrix (one-time set-up work).
+constexpr int FC_NB = 32;
+
+// Diagonal block: one warp, lane = row, unblocked left-looking in registers/shared memory.
+__global__ void __launch_bounds__(32) field_potf2_kernel(double* __restrict__ A, int n, int p0, int* __restrict__ info) {
+    __shared__ double L[FC_NB][FC_NB + 1];
+    const int lane = threadIdx.x, nb = min(FC_NB, n - p0);
+    for (int j = 0; j < nb; ++j) L[lane][j] = (lane < nb && j <= lane) ? A[(size_t)(p0 + lane) * n + p0 + j] : 0.0;
+    __syncwarp();
+    for (int j = 0; j < nb; ++j) {
+        double s = L[lane][j];
+        for (int k = 0; k < j; ++k) s = fma(-L[lane][k], L[j][k], s);
+        const double d = __shfl_sync(0xffffffffu, s, j);
+        if (!(d > 0.0)) {
+            if (lane == 0) atomicCAS(info, 0, p0 + j + 1);
+            return;
+        }
+        const double ljj = sqrt(d);
+        __syncwarp();
+        if (lane >= j) L[lane][j] = (lane == j) ? ljj : s / ljj;
+        __syncwarp();
+    }
+    for (int j = 0; j < nb; ++j)
+        if (lane < nb) A[(size_t)(p0 + lane) * n + p0 + j] = (j <= lane) ? L[lane][j] : 0.0;  // zero the upper part
+}
+
+// Panel below the diagonal block: X L_pp^T = A_panel, one thread per row (forward substitution along the row).
+__global__ void __launch_bounds__(128) field_trsm_kernel(double* __restrict__ A, int n, int p0) {
+    __shared__ double L[FC_NB][FC_NB + 1];
+    const int nb = min(FC_NB, n - p0);
+    for (int e = threadIdx.x; e < FC_NB * FC_NB; e += blockDim.x) {
+        const int r = e / FC_NB, c = e - r * FC_NB;
+        L[r][c] = (r < nb && c <= r) ? A[(size_t)(p0 + r) * n + p0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int i = p0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x[FC_NB];
+#pragma unroll
+    for (int j = 0; j < FC_NB; ++j) x[j] = j < nb ? A[(size_t)i * n + p0 + j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < FC_NB; ++j) {
+        if (j < nb) {
+            double s = x[j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = fma(-x[k], L[j][k], s);
+            x[j] = s / L[j][j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < FC_NB; ++j)
+        if (j < nb) A[(size_t)i * n + p0 + j] = x[j];
+}
+
+// Trailing update A[i][j] -= sum_k P[i][k] P[j][k] for i >= j > panel; 32 x 32 tiles, lower tiles only.
+__global__ void __launch_bounds__(256) field_syrk_kernel(double* __restrict__ A, int n, int p0) {
+    __shared__ double Pi[FC_NB][FC_NB + 1], Pj[FC_NB][FC_NB + 1];
+    const int t0 = p0 + FC_NB;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const int i0 = t0 + bi * FC_NB, j0 = t0 + bj * FC_NB;
+    for (int e = threadIdx.x; e < FC_NB * FC_NB; e += 256) {
+        const int r = e / FC_NB, c = e - r * FC_NB;
+        Pi[r][c] = (i0 + r < n) ? A[(size_t)(i0 + r) * n + p0 + c] : 0.0;
+        Pj[r][c] = (j0 + r < n) ? A[(size_t)(j0 + r) * n + p0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // column tx, rows ty + 8 m
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int r = ty + 8 * m, i = i0 + r, j = j0 + tx;
+        if (i >= n || j >= n || j > i) continue;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < FC_NB; ++k) s = fma(Pi[r][k], Pj[tx][k], s);
+        A[(size_t)i * n + j] -= s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- F3 normals
+// Philox4x32-10 counter RNG + Box-Muller.  Element pair e (two consecutive doubles of the row-major (N, n) array) uses
+// counter (e_lo, e_hi, sub_lo, sub_hi) and key (seed_lo, seed_hi), `sub` being the caller's subsequence id (e.g. the
+// index of the first sample of a chunk); the four 32-bit outputs give two 53-bit uniforms.
+__host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        c[1] = (uint32_t)p1;
+        c[3] = (uint32_t)p0;
+        c[0] = n0;
+        c[2] = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+__global__ void __launch_bounds__(256) field_normal_kernel(unsigned long long seed, unsigned long long sub,
+                                                           long long count /* doubles */,
+                                                           double* __restrict__ z) {
+    const long long pairs = (count + 1) / 2;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < pairs;
+         e += (long long)gridDim.x * blockDim.x) {
+        uint32_t c[4] = {(uint32_t)e, (uint32_t)((unsigned long long)e >> 32), (uint32_t)sub, (uint32_t)(sub >> 32)};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double two53 = 1.0 / 9007199254740992.0;
+        const double u1 = ((double)((((uint64_t)c[0] << 32) | c[1]) >> 11) + 1.0) * two53;  // (0, 1]
+        const double u2 = ((double)((((uint64_t)c[2] << 32) | c[3]) >> 11)) * two53;        // [0, 1)
+        const double r = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        z[2 * e] = r * cs;
+        if (2 * e + 1 < count) z[2 * e + 1] = r * sn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- F4 sampler
+// K[s][j] = exp(0.5 * sum_{i <= j} Z[s][i] L[j][i]):  fp64 "NT" GEMM restricted to the lower triangle, exp fused in
+// the epilogue.  64 x 64 tile, BK = 16, 256 threads x (4 x 4); operands are stored k-major in shared memory and the
+// next k-slab is prefetched into registers while the current one is consumed.
+constexpr int FS_BM = 64, FS_BN = 64, FS_BK = 16;
+
+__global__ void __launch_bounds__(256) field_sample_kernel(const double* __restrict__ Z, long long N, int n,
+                                                           const double* __restrict__ L, double* __restrict__ K) {
+    __shared__ __align__(16) double As[2][FS_BK][FS_BM + 4], Bs[2][FS_BK][FS_BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long s0 = (long long)blockIdx.y * FS_BM;
+    const int j0 = blockIdx.x * FS_BN;
+    const int kmax = min(n, j0 + FS_BN);  // L[j][i] = 0 for i > j
+    const int nslab = (kmax + FS_BK - 1) / FS_BK;
+    // loader mapping: row lr = tid / 4 (0..63), k quad lk = (tid % 4) * 4
+    const int lr = tid >> 2, lk = (tid & 3) * 4;
+    double ra[4], rb[4];
+    auto fetch = [&](int slab) {
+        const int k0 = slab * FS_BK + lk;
+        const long long s = s0 + lr;
+        const int j = j0 + lr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ra[q] = (s < N && k0 + q < kmax) ? Z[s * n + k0 + q] : 0.0;
+            rb[q] = (j < n && k0 + q <= j) ? L[(size_t)j * n + k0 + q] : 0.0;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            As[buf][lk + q][lr] = ra[q];
+            Bs[buf][lk + q][lr] = rb[q];
+        }
+    };
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int slab = 0; slab < nslab; ++slab) {
+        const int buf = slab & 1;
+        if (slab + 1 < nslab) fetch(slab + 1);
+#pragma unroll
+        for (int k = 0; k < FS_BK; ++k) {
+            const double4 a4 = *reinterpret_cast<const double4*>(&As[buf][k][4 * ty]);
+            const double4 b4 = *reinterpret_cast<const double4*>(&Bs[buf][k][4 * tx]);
+            const double av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+        if (slab + 1 < nslab) stash(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const long long s = s0 + 4 * ty + a;
+        if (s >= N) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = j0 + 4 * tx + b;
+            if (j < n) K[s * n + j] = exp(0.5 * acc[a][b]);
+        }
+    }
+}
+
+}  // namespace tfin

@@ -12,6 +12,7 @@
 #include "pcg_stream.cuh"
 #include "rom.cuh"
 #include "rom_nodal.cuh"
+#include "field.cuh"
 
 using namespace tfin;
 
@@ -127,6 +128,10 @@ struct tfin_ctx {
     int n_r = 0, rom_terms = 0, rom_obs = 0;
     DevBuf<double> d_S, d_obs_phi, d_romC;
     int64_t rom_chunk = 0;  // 0 = auto
+    // ---- Gaussian-field sampler (F): lower Cholesky factor of the covariance, normals
+    int f_n = 0;
+    DevBuf<double> d_fL, d_fz, d_fk, d_fxy;
+    DevBuf<int> d_finfo;
     // ---- nodal LSPG (R4): padded basis [n][6 TT], projection rows
     int b_nr = 0, b_nout = 0, b_TT = 0;
     DevBuf<double> d_bphi, d_bout, d_Ar, d_Br, d_y;
@@ -188,6 +193,8 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
         b->release();
     h->d_obsT_ptr.release();
     h->d_obsT_idx.release();
+    for (auto* b : {&h->d_fL, &h->d_fz, &h->d_fk, &h->d_fxy}) b->release();
+    h->d_finfo.release();
     for (auto* b : {&h->d_NG, &h->d_vr, &h->d_gtheta, &h->d_avgT_val, &h->d_bphi, &h->d_bout, &h->d_Ar, &h->d_Br, &h->d_y})
         b->release();
     h->d_avgT_ptr.release();
@@ -1144,6 +1151,111 @@ extern "C" int tfin_fom_nodal_sensitivity(tfin_handle_t h, const double* k, int6
                                           int32_t* status_out, void* stream) {
     CHECK_HANDLE(h);
     return fom_adjoint(h, 2, k, N, mem, tol, maxit, nullptr, 0, jac_out, nullptr, qoi_out, iters_out, status_out, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ field sampler
+extern "C" int tfin_field_set_cov(tfin_handle_t h, int32_t n_pts, const double* coords, int32_t kern_type,
+                                  double length, double* chol_out) {
+    CHECK_HANDLE(h);
+    if (n_pts <= 0 || !coords || !(length > 0.0) || kern_type < TFIN_KERN_SQ_EXP || kern_type > TFIN_KERN_M32)
+        return fail(TFIN_E_ARG, "tfin_field_set_cov: bad argument");
+    const int n = n_pts;
+    cudaStream_t st = h->stream;
+    std::vector<double> xy(coords, coords + 2 * (size_t)n);
+    if (int e = h->d_fxy.upload(xy, st)) return e;
+    if (int e = h->d_fL.reserve((size_t)n * n)) return e;
+    if (int e = h->d_finfo.reserve(1)) return e;
+    TFIN_CUDA(cudaMemsetAsync(h->d_finfo.p, 0, sizeof(int), st));
+    const long long total = (long long)n * n;
+    field_cov_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16), 256, 0, st>>>(
+        h->d_fxy.p, n, kern_type, length, h->d_fL.p);
+    h->launches += 1;
+    for (int p0 = 0; p0 < n; p0 += FC_NB) {
+        field_potf2_kernel<<<1, 32, 0, st>>>(h->d_fL.p, n, p0, h->d_finfo.p);
+        h->launches += 1;
+        const int rest = n - p0 - FC_NB;
+        if (rest > 0) {
+            field_trsm_kernel<<<(rest + 127) / 128, 128, 0, st>>>(h->d_fL.p, n, p0);
+            const int T = (rest + FC_NB - 1) / FC_NB;
+            field_syrk_kernel<<<dim3(T, T), 256, 0, st>>>(h->d_fL.p, n, p0);
+            h->launches += 2;
+        }
+    }
+    TFIN_CUDA(cudaGetLastError());
+    int info = 0;
+    TFIN_CUDA(cudaMemcpyAsync(&info, h->d_finfo.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TFIN_CUDA(cudaStreamSynchronize(st));
+    if (info != 0) {
+        h->f_n = 0;
+        return fail(TFIN_E_STATE, "tfin_field_set_cov: covariance is not positive definite (pivot %d)", info);
+    }
+    h->f_n = n;
+    if (chol_out) {  // upper factor chol = L^T, row-major: element (i, j) = L[j][i]
+        std::vector<double> L((size_t)n * n);
+        TFIN_CUDA(cudaMemcpy(L.data(), h->d_fL.p, L.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) chol_out[(size_t)i * n + j] = j >= i ? L[(size_t)j * n + i] : 0.0;
+    }
+    return 0;
+}
+
+extern "C" int tfin_field_set_chol(tfin_handle_t h, int32_t n_pts, const double* chol) {
+    CHECK_HANDLE(h);
+    if (n_pts <= 0 || !chol) return fail(TFIN_E_ARG, "tfin_field_set_chol: bad argument");
+    const int n = n_pts;
+    std::vector<double> L((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = i; j < n; ++j) L[(size_t)j * n + i] = chol[(size_t)i * n + j];
+    if (int e = h->d_fL.upload(L, h->stream)) return e;
+    TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    h->f_n = n;
+    return 0;
+}
+
+extern "C" int tfin_field_sample(tfin_handle_t h, const double* z, uint64_t seed, uint64_t subsequence, int64_t N,
+                                 int32_t mem,
+                                 double* k_out, double* z_out, void* stream) {
+    CHECK_HANDLE(h);
+    if (h->f_n <= 0) return fail(TFIN_E_STATE, "tfin_field_sample: call tfin_field_set_cov or tfin_field_set_chol first");
+    if (N < 0 || (N > 0 && !k_out)) return fail(TFIN_E_ARG, "tfin_field_sample: bad batch argument");
+    if (N == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    Staged sg{h, st, mem == TFIN_MEM_HOST};
+    const int n = h->f_n;
+    const size_t cnt = (size_t)N * n;
+    const double* d_z;
+    double* d_k;
+    if (z) {
+        if (int e = sg.in(z, cnt, h->d_fz, &d_z)) return e;
+    } else {
+        double* d_zw;
+        if (!sg.host && z_out) d_zw = z_out;
+        else {
+            if (int e = h->d_fz.reserve(cnt)) return e;
+            d_zw = h->d_fz.p;
+        }
+        const long long pairs = ((long long)cnt + 1) / 2;
+        field_normal_kernel<<<(int)std::min<long long>((pairs + 255) / 256, (long long)h->sm_count * 16), 256, 0, st>>>(
+            (unsigned long long)seed, (unsigned long long)subsequence, (long long)cnt, d_zw);
+        h->launches += 1;
+        d_z = d_zw;
+    }
+    if (int e = sg.out_alloc(k_out, cnt, h->d_fk, &d_k)) return e;
+    dim3 grid((unsigned)((n + FS_BN - 1) / FS_BN), (unsigned)((N + FS_BM - 1) / FS_BM));
+    if (grid.y > 65535) return fail(TFIN_E_ARG, "tfin_field_sample: at most %d samples per call", 65535 * FS_BM);
+    field_sample_kernel<<<grid, 256, 0, st>>>(d_z, (long long)N, n, h->d_fL.p, d_k);
+    h->launches += 1;
+    TFIN_CUDA(cudaGetLastError());
+    if (int e = sg.out_copy(k_out, cnt, (const double*)d_k)) return e;
+    if (z_out && d_z != z_out) {
+        if (sg.host) {
+            if (int e = sg.out_copy(z_out, cnt, d_z)) return e;
+        } else {
+            TFIN_CUDA(cudaMemcpyAsync(z_out, d_z, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ introspection

@@ -1,0 +1,100 @@
+"""Batched generator of the ROM-error training set, device-resident end to end.
+
+Reference: ``deep_learning/generate_fin_dataset.py:62-112`` (``gen_affine_avg_rom_dataset``): for every sample draw
+a log-normal Matern conductivity field, solve the nodal full-order model and the sub-fin-averaged affine ROM, and
+store ``z_s`` (the fields), ``qois`` and ``qoi_errors = qoi - qoi_r``; the ``.npy`` names depend on the set size.
+
+The reference loops one sample at a time through FEniCS.  Here each chunk of samples is ONE pass of four kernels
+over device buffers -- field sampler (csrc/field.cuh) -> nodal FOM PCG + B_obs (K2) -> sub-fin averages + ROM
+(K0, R1, R2) -- and only the finished arrays cross PCIe.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .. import _cabi
+from ..bayesian_inference.gaussian_field import FieldSampler
+from ..fom.forward_solve import Fin
+from ..fom.thermal_fin import get_space
+from ..rom.averaged_affine_ROM import AffineROMFin
+from ..rom.pod import generate_pod_basis
+
+__all__ = ["gen_affine_avg_rom_dataset", "DatasetGenerator"]
+
+
+class DatasetGenerator:
+    """Owns the three device models (prior, nodal FOM, averaged affine ROM) of one space."""
+
+    def __init__(self, V, phi, external_obs=False, length=1.6, device=0, chunk=16384):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("DatasetGenerator needs a CUDA device (there is no CPU fallback)")
+        self.torch = torch
+        self.dev = torch.device("cuda", device)
+        self.solver = Fin(V, external_obs, device=device)
+        self.solver_r = AffineROMFin(V, None, phi, external_obs, device=device)
+        self.prior = FieldSampler(V, "m52", length, handle=self.solver.handle)
+        self.n, self.n_obs = self.solver.dofs, self.solver.n_obs
+        self.chunk = int(chunk)
+
+    def generate(self, dataset_size, seed=0, z=None):
+        """Returns ``(z_s, qoi_errors, qois)`` as numpy arrays of shapes (N, n), (N, n_obs), (N, n_obs).
+        ``z``: optional (N, n) standard normals (otherwise drawn on the device from ``seed``; every chunk draws the
+        Philox subsequence numbered by its first sample index)."""
+        torch, dev, n, nobs = self.torch, self.dev, self.n, self.n_obs
+        N = int(dataset_size)
+        z_s, errs, qois = np.empty((N, n)), np.empty((N, nobs)), np.empty((N, nobs))
+        h_f, h_r = self.solver.handle, self.solver_r.handle
+        lib = h_f._lib
+        stream = torch.cuda.Stream(device=dev)
+        cap = min(self.chunk, max(N, 1))
+        k = torch.empty((cap, n), dtype=torch.float64, device=dev)
+        q = torch.empty((cap, nobs), dtype=torch.float64, device=dev)
+        q_r = torch.empty((cap, nobs), dtype=torch.float64, device=dev)
+        st_f = torch.empty(cap, dtype=torch.int32, device=dev)
+        st_r = torch.empty(cap, dtype=torch.int32, device=dev)
+        zbuf = torch.empty((cap, n), dtype=torch.float64, device=dev) if z is not None else None
+        with torch.cuda.stream(stream):
+            sp = stream.cuda_stream
+            for s0 in range(0, N, cap):
+                m = min(cap, N - s0)
+                zp = None
+                if z is not None:
+                    zbuf[:m].copy_(torch.from_numpy(np.ascontiguousarray(z[s0:s0 + m], dtype=np.float64)))
+                    zp = zbuf.data_ptr()
+                _cabi._check(lib, lib.tfin_field_sample(h_f._h, zp, int(seed), s0, m, _cabi.MEM_DEVICE,
+                                                        k.data_ptr(), None, sp), "tfin_field_sample")
+                h_f.fom_nodal_raw(k.data_ptr(), m, _cabi.MEM_DEVICE, self.solver.tol, self.solver.maxit,
+                                  qoi=q.data_ptr(), status=st_f.data_ptr(), stream=sp)
+                h_r.rom_raw(k.data_ptr(), m, _cabi.IN_NODAL, _cabi.MEM_DEVICE, qoi=q_r.data_ptr(),
+                            status=st_r.data_ptr(), stream=sp)
+                stream.synchronize()
+                if int(st_f[:m].max()) != 0 or int(st_r[:m].max()) != 0:
+                    raise RuntimeError("dataset generation: a forward solve failed (non-positive conductivity?)")
+                z_s[s0:s0 + m] = k[:m].cpu().numpy()
+                qois[s0:s0 + m] = q[:m].cpu().numpy()
+                errs[s0:s0 + m] = (q[:m] - q_r[:m]).cpu().numpy()
+        return z_s, errs, qois
+
+
+def gen_affine_avg_rom_dataset(dataset_size, resolution=40, genrand=False, *, phi=None, V=None, out_dir=None,
+                               seed=0, device=0):
+    """generate_fin_dataset.py:62-112.  Returns ``(z_s, qoi_errors)`` and writes the reference's ``.npy`` files into
+    ``out_dir`` when given (the reference hard-codes ``../data``): ``*_tr_avg_obs_3`` for more than 1000 samples,
+    ``*_eval_avg_obs_3`` for fewer than 600.  ``phi`` defaults to a POD basis built on this space (the reference loads
+    ``data/basis_nine_param.txt``, which belongs to its unshipped mshr mesh)."""
+    V = V if V is not None else get_space(resolution)
+    if phi is None:
+        phi = generate_pod_basis(V, device=device)
+    gen = DatasetGenerator(V, phi, external_obs=genrand, device=device)
+    z_s, qoi_errors, qois = gen.generate(dataset_size, seed=seed)
+    if out_dir is not None:
+        os.makedirs(out_dir, exist_ok=True)
+        tag = "tr" if dataset_size > 1000 else "eval" if dataset_size < 600 else None
+        if tag:
+            np.save(os.path.join(out_dir, f"z_aff_avg_{tag}_avg_obs_3"), z_s)
+            np.save(os.path.join(out_dir, f"errors_aff_avg_{tag}_avg_obs_3"), qoi_errors)
+            np.save(os.path.join(out_dir, f"qois_avg_{tag}_avg_obs_3"), qois)
+    return z_s, qoi_errors

@@ -188,6 +188,33 @@ int tfin_fom_nodal_sensitivity(tfin_handle_t h, const double* k, int64_t N, int3
                                double* jac_out, double* qoi_out, int32_t* iters_out, int32_t* status_out,
                                void* stream);
 
+/* covariance kernels of tfin_field_set_cov (bayesian_inference/gaussian_field.py:16-28) */
+#define TFIN_KERN_SQ_EXP 0 /* exp(-d^2 / (2 l^2)) + 1e-5 I */
+#define TFIN_KERN_M52 1    /* Matern 5/2: (1 + t + t^2/3) exp(-t), t = sqrt(5) d / l */
+#define TFIN_KERN_M32 2    /* Matern 3/2: (1 + t) exp(-t),          t = sqrt(3) d / l */
+
+/*
+ * Gaussian-random-field prior over the dofs = make_cov_chol(V, kern_type, length)
+ * (bayesian_inference/gaussian_field.py:9-31): pairwise distances of coords (n_pts, 2), covariance kernel and
+ * Cholesky factor, all on the device.  chol_out (n_pts, n_pts) | NULL receives the UPPER factor (cov = chol^T chol)
+ * like scipy.linalg.cholesky; the handle keeps the factor for tfin_field_sample.
+ */
+int tfin_field_set_cov(tfin_handle_t h, int32_t n_pts, const double* coords, int32_t kern_type, double length,
+                       double* chol_out);
+
+/* Use a caller-supplied upper factor chol (n_pts, n_pts), e.g. of a stored prior covariance. */
+int tfin_field_set_chol(tfin_handle_t h, int32_t n_pts, const double* chol);
+
+/*
+ * Batched conductivity draws k_s = exp(0.5 * chol^T z_s) (deep_learning/generate_fin_dataset.py:87-88).
+ *   z (N, n_pts) standard normals, or NULL: drawn on the device (Philox4x32-10 keyed by `seed`; counter = (index of
+ *   the element pair in the row-major (N, n_pts) array, `subsequence`); Box-Muller).  Calls with different
+ *   `subsequence` values (e.g. the index of the first sample of a chunk) draw disjoint streams of the same seed.
+ *   k_out (N, n_pts);  z_out (N, n_pts) | NULL
+ */
+int tfin_field_sample(tfin_handle_t h, const double* z, uint64_t seed, uint64_t subsequence, int64_t N, int32_t mem,
+                      double* k_out, double* z_out, void* stream);
+
 /* theta = averaging(k) for N nodal fields (subfin_avg_op batched); out (N, n_rows). */
 int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double* theta_out,
                     void* stream);

@@ -333,6 +333,41 @@ def sample_field(chol, z):
     return np.exp(0.5 * chol.T @ z)
 
 
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., SC'11; Random123): counter = 4 uint64 arrays holding 32-bit words, key = 2 ints.
+    Pinned against the Random123 known-answer vectors in tests/test_oracle.py."""
+    m32 = np.uint64(0xFFFFFFFF)
+    c = [np.asarray(x, dtype=np.uint64) for x in counter]
+    k0, k1 = np.uint64(key[0] & 0xFFFFFFFF), np.uint64(key[1] & 0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        n0 = (p1 >> np.uint64(32)) ^ c[1] ^ k0
+        n2 = (p0 >> np.uint64(32)) ^ c[3] ^ k1
+        c = [n0, p1 & m32, n2, p0 & m32]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    return c
+
+
+def philox_normals(seed, count, subsequence=0):
+    """Restatement of the product's device generator (csrc/field.cuh, F3) -- NOT part of the reference, which draws
+    ``np.random.randn`` unseeded (generate_fin_dataset.py:87): Philox4x32-10 with counter (pair index lo, hi, 0, 0) and
+    key ``seed`` (counter words 2, 3 = ``subsequence``), two 53-bit uniforms per pair, Box-Muller.  Returns ``count`` standard normals."""
+    pairs = (count + 1) // 2
+    e = np.arange(pairs, dtype=np.uint64)
+    sub_lo = np.full(pairs, subsequence & 0xFFFFFFFF, np.uint64)
+    sub_hi = np.full(pairs, (subsequence >> 32) & 0xFFFFFFFF, np.uint64)
+    c = philox4x32_10([e & np.uint64(0xFFFFFFFF), e >> np.uint64(32), sub_lo, sub_hi], (seed, seed >> 32))
+    u1 = ((((c[0] << np.uint64(32)) | c[1]) >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740992.0
+    u2 = (((c[2] << np.uint64(32)) | c[3]) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+    r = np.sqrt(-2.0 * np.log(u1))
+    out = np.empty(2 * pairs)
+    out[0::2] = r * np.cos(2.0 * np.pi * u2)
+    out[1::2] = r * np.sin(2.0 * np.pi * u2)
+    return out[:count]
+
+
 def pod_basis(oracle: FinOracle, n_snapshots=200, basis_size=81, seed=0, lo=0.1, hi=3.5):
     """POD recipe of rom/generate_reduced_basis_nine_param.py:296-318 (commented script that produced
     data/basis_nine_param.txt): snapshots of forward_nine_param at k ~ U(0.1, 3.5)^9, eigenvectors of

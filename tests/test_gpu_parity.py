@@ -369,3 +369,59 @@ def test_r_fwd_no_full_and_reduced_forward(fin_m3, oracle_m3, pod_m3):
     ref = orc.reduced_forward(A, orc.B, orc.C, A @ pod_m3, pod_m3)
     assert np.max(np.abs(got[0] - ref[0])) <= 1e-12 * np.max(np.abs(ref[0]))
     assert abs(got[4] - ref[4]) <= 1e-8 * abs(ref[4])
+
+
+def test_field_prior_on_device(space_m2, oracle_m2):
+    """make_cov_chol / FieldSampler (gaussian_field.py:9-31, generate_fin_dataset.py:87-88) on the device: covariance
+    kernel, blocked Cholesky, triangular-GEMM + exp sampler, Philox normals -- against the scipy/numpy restatement."""
+    from bayesianinferencedl_b200 import make_cov_chol, sample_fields
+    from bayesianinferencedl_b200.bayesian_inference.gaussian_field import FieldSampler
+    from oracle.thermal_fin_oracle import make_cov_chol as cov_ref, sample_field, philox_normals
+    n = oracle_m2.n
+    for kern in ("m52", "sq_exp", "m32"):
+        chol = make_cov_chol(space_m2, kern, 1.6)
+        ref = cov_ref(oracle_m2.coords, kern, 1.6)
+        assert chol.shape == (n, n) and np.array_equal(chol, np.triu(chol))   # UPPER factor, like scipy
+        # the factor itself is only conditioning-stable; the covariance it reproduces is exact to rounding
+        assert np.max(np.abs(chol.T @ chol - ref.T @ ref)) <= 1e-12
+        assert np.max(np.abs(chol - ref)) <= 1e-7
+    prior = FieldSampler(space_m2, "m52", 1.6)
+    rng = np.random.default_rng(5)
+    z = rng.standard_normal((70, n))                                         # two 64-sample tiles
+    k = prior.sample(z=z)
+    for s in (0, 63, 64, 69):
+        assert relerr(k[s], sample_field(prior.chol, z[s])) <= 1e-12, s
+    assert np.array_equal(prior.sample(z=z[3]), k[3])                         # single-draw signature
+    assert np.array_equal(sample_fields(prior.chol, z[:5]), k[:5])            # caller-supplied factor
+    # device generator: bit pattern of Philox is exact, log / sincos differ by ulps from numpy's
+    k2, z2 = prior.sample(N=33, seed=2026, return_z=True)
+    z_ref = philox_normals(2026, 33 * n).reshape(33, n)
+    assert np.max(np.abs(z2 - z_ref)) <= 1e-13
+    assert relerr(k2[17], sample_field(prior.chol, z2[17])) <= 1e-12
+    assert not np.array_equal(prior.sample(N=33, seed=2027), k2)
+
+
+def test_dataset_generator(space_m2, oracle_m2, tmp_path):
+    """gen_affine_avg_rom_dataset (generate_fin_dataset.py:62-112): device-resident prior -> FOM -> ROM pipeline and
+    the .npy layout, against the oracle's per-sample loop."""
+    from bayesianinferencedl_b200.deep_learning.generate_fin_dataset import DatasetGenerator, gen_affine_avg_rom_dataset
+    from oracle.thermal_fin_oracle import pod_basis, philox_normals, sample_field
+    orc = oracle_m2
+    phi = pod_basis(orc, n_snapshots=40, basis_size=20, seed=1)
+    gen = DatasetGenerator(space_m2, phi, chunk=16)                           # several chunks, ragged tail
+    z_s, errs, qois = gen.generate(37, seed=9)
+    assert z_s.shape == (37, orc.n) and errs.shape == (37, 9) and qois.shape == (37, 9)
+    for s0 in (0, 16, 32):                                                    # chunk = Philox subsequence s0
+        m = min(16, 37 - s0)
+        zn = philox_normals(9, m * orc.n, subsequence=s0).reshape(m, orc.n)
+        assert relerr(z_s[s0], sample_field(gen.prior.chol, zn[0])) <= 1e-11
+    for s in (0, 15, 16, 36):
+        q = orc.qoi_operator(orc.forward(z_s[s]))
+        q_r = orc.qoi_reduced(orc.forward_reduced(z_s[s], phi), phi)
+        assert relerr(qois[s], q) <= 1e-10
+        assert np.max(np.abs(errs[s] - (q - q_r))) <= 1e-10 * np.max(np.abs(q))
+    z_eval, e_eval = gen_affine_avg_rom_dataset(5, V=space_m2, phi=phi, out_dir=str(tmp_path), seed=9)
+    assert np.array_equal(z_eval, z_s[:5]) and np.array_equal(e_eval, errs[:5])
+    for name in ("z_aff_avg_eval_avg_obs_3", "errors_aff_avg_eval_avg_obs_3", "qois_avg_eval_avg_obs_3"):
+        assert (tmp_path / f"{name}.npy").exists()
+    assert np.array_equal(np.load(tmp_path / "qois_avg_eval_avg_obs_3.npy"), qois[:5])

@@ -120,3 +120,19 @@ def test_cov_chol(oracle_m1):
         assert np.allclose(np.diag(cov), 1.0 + (1e-5 if kern == "sq_exp" else 0.0), atol=1e-10)
     k = sample_field(chol, np.zeros(oracle_m1.n))
     assert np.array_equal(k, np.ones(oracle_m1.n))
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10 (the generator of the device field sampler)."""
+    from oracle.thermal_fin_oracle import philox4x32_10, philox_normals
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10([np.array([v], np.uint64) for v in ctr], key)
+        assert tuple(int(g[0]) for g in got) == want
+    z = philox_normals(12345, 200001)
+    assert z.shape == (200001,) and np.all(np.isfinite(z))
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    assert np.array_equal(philox_normals(12345, 11), z[:11])            # counter based: prefix stable
