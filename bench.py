@@ -46,8 +46,10 @@ def parse_args():
     ap.add_argument("--nodal-batch", type=int, default=100_000,
                     help="nodal Gaussian-field FOM samples per GPU per step; 0 disables the leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-fom-sample", type=int, default=2048)
-    ap.add_argument("--cpu-rom-sample", type=int, default=2048)
+    ap.add_argument("--cpu-fom-sample", type=int, default=65536, help="CPU baseline FOM sample (~10 s on 16 cores)")
+    ap.add_argument("--cpu-rom-sample", type=int, default=65536)
+    ap.add_argument("--grad-batch", type=int, default=16384, help="samples per GPU per step of the gradient legs (0 = skip)")
+    ap.add_argument("--ref-step-samples", type=int, default=8192, help="--impl reference: CPU solves per step")
     return ap.parse_args()
 
 
@@ -125,7 +127,7 @@ def run_reference(args):
         return
     phi = cpu_pod_basis()
     pool = CpuPool(phi)
-    per_step = max(pool.cores * 16, 256)
+    per_step = max(pool.cores * 16, args.ref_step_samples)
     th = fom_inputs(per_step * (args.steps + args.warmup), FOM_SEED)
     thr = rom_inputs(per_step * (args.steps + args.warmup), ROM_SEED)
     t_f = t_r = 0.0
@@ -322,16 +324,29 @@ def run_b200(args):
     # generated on the device with torch -- input generation, not the measured path), in-kernel assembly + PCG
     nodal = None
     if args.nodal_batch > 0:
-        from bayesianinferencedl_b200 import Fin, make_cov_chol
+        from bayesianinferencedl_b200 import Fin
+        from bayesianinferencedl_b200.bayesian_inference.gaussian_field import FieldSampler
         NN = args.nodal_batch
         fin = Fin(V, device=local_rank)
-        chol = torch.from_numpy(make_cov_chol(V, length=1.6)).to(dev)
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(NODAL_SEED + rank)
+        prior = FieldSampler(V, "m52", 1.6, handle=fin.handle)      # covariance + Cholesky on the device
         k_dev = torch.empty((NN, n), dtype=f64, device=dev)
-        for lo in range(0, NN, 20000):
-            z = torch.randn((min(20000, NN - lo), n), dtype=f64, device=dev, generator=gen)
-            k_dev[lo:lo + len(z)] = torch.exp(0.5 * (z @ chol))
+        lib = fin.handle._lib
+
+        def draw():  # k = exp(0.5 chol^T z), z from the device Philox generator; 16384-sample chunks
+            for lo in range(0, NN, 16384):
+                m = min(16384, NN - lo)
+                rc = lib.tfin_field_sample(fin.handle._h, None, NODAL_SEED + rank, lo, m, _cabi.MEM_DEVICE,
+                                           k_dev[lo:].data_ptr(), None, sp)
+                if rc:
+                    raise RuntimeError(lib.tfin_last_error().decode())
+        draw()
+        torch.cuda.synchronize()
+        e0s, e1s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0s.record(stream)
+        draw()
+        e1s.record(stream)
+        torch.cuda.synchronize()
+        sampler_ms = e0s.elapsed_time(e1s)
         k_host = torch.empty((NN, n), dtype=f64).pin_memory()
         k_host.copy_(k_dev)
         q_n = torch.empty((NN, n_obs), dtype=f64, device=dev)
@@ -365,12 +380,47 @@ def run_b200(args):
                     "h2d_bytes_per_step": NN * n * 8, "d2h_bytes_per_step": NN * (n_obs * 8 + 4),
                     "ms_per_step": ms_ne / K - flush_ms},
             "gpu_launches": ln,
+            "field_sampler": {"value": NN / (sampler_ms * 1e-3), "unit": "fields/s/GPU", "ms": sampler_ms,
+                              "what": "tfin_field_sample: Philox normals + fp64 triangular GEMM + exp, device resident",
+                              "tflops_fp64": NN * float(n) * n / (sampler_ms * 1e-3) / 1e12},
             "roofline": {"bound": "hbm", "unit": "GB/s", "peak": None,
                          "achieved": ((88.0 * n + 8.0 * n_cells) * it_sum_n + NN * n * 8.0) / (step_n * 1e-3) / 1e9,
                          "note": "algorithmic bytes (88 n + 8 n_cells) per iteration + the k field read once; "
                                  "on-chip kernel, see roofline.note"},
         }
-        del k_dev, k_host, chol
+        # ---- gradient legs: FOM adjoint gradient and reduced gradient, device resident
+        if args.grad_batch > 0:
+            NG = min(args.grad_batch, NN)
+            data_dev = q_n[:1].clone()
+            g_n = torch.empty((NG, n), dtype=f64, device=dev)
+            c_n = torch.empty(NG, dtype=f64, device=dev)
+
+            def fom_grad():
+                rc = lib.tfin_fom_nodal_gradient(hn._h, k_dev.data_ptr(), NG, _cabi.MEM_DEVICE, TOL, 20000,
+                                                 data_dev.data_ptr(), 1, g_n.data_ptr(), c_n.data_ptr(), None, None,
+                                                 st_n.data_ptr(), sp)
+                if rc:
+                    raise RuntimeError(lib.tfin_last_error().decode())
+            ms_g, lg = timed(fom_grad, K, Wm, hn)
+            model.set_data(np.zeros(n_obs))
+            model.grad_reduced_nine_param(np.ones((2, 9)))        # builds / uploads the Gram blocks once
+            g_r = torch.empty((NG, n), dtype=f64, device=dev)
+
+            def rom_grad():
+                rc = lib.tfin_rom_gradient(h._h, k_dev.data_ptr(), NG, _cabi.IN_NODAL, _cabi.MEM_DEVICE,
+                                           data_dev.data_ptr(), 1, _cabi.IN_NODAL, g_r.data_ptr(), c_n.data_ptr(),
+                                           None, None, st_n.data_ptr(), sp)
+                if rc:
+                    raise RuntimeError(lib.tfin_last_error().decode())
+            ms_gr, lgr = timed(rom_grad, K, Wm)
+            nodal["gradients"] = {
+                "fom": {"value": world * NG / ((ms_g / K - flush_ms) * 1e-3), "unit": "gradients/s",
+                        "what": f"Fin.gradient batched: forward + adjoint PCG + gradient form in one kernel, {NG} fields",
+                        "gpu_launches": lg, "all_converged": bool((st_n[:NG] == 0).all().item())},
+                "rom": {"value": world * NG / ((ms_gr / K - flush_ms) * 1e-3), "unit": "gradients/s",
+                        "what": f"AffineROMFin.grad_reduced batched (nodal in, nodal out), {NG} fields",
+                        "gpu_launches": lgr}}
+        del k_dev, k_host
         fin.handle.close()
 
     # ---- config[3] refined mesh (m=26, n=99 945), nine-param FOM: the genuinely HBM-streaming PCG kernel
