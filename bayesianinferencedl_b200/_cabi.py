@@ -51,8 +51,11 @@ SIGNATURES = {
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfin_field_set_cov": (C.c_int, [_handle, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "tfin_field_set_chol": (C.c_int, [_handle, C.c_int32, C.c_void_p]),
-    "tfin_field_sample": (C.c_int, [_handle, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+    "tfin_field_sample": (C.c_int, [_handle, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    "tfin_pcn_chains": (C.c_int, [_handle, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
+                                  C.c_double, C.c_uint64, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfin_subfin_avg": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "tfin_kernel_launches": (C.c_int64, [_handle]),
     "tfin_get_int": (C.c_int64, [_handle, C.c_char_p]),
@@ -316,7 +319,7 @@ class TfinHandle:
         _check(self._lib, self._lib.tfin_field_set_chol(self._h, chol.shape[0], _ptr(chol)), "tfin_field_set_chol")
         self.field_n = chol.shape[0]
 
-    def field_sample(self, N=None, z=None, seed=0, subsequence=0, want_z=False):
+    def field_sample(self, N=None, z=None, seed=0, subsequence=0, first_row=0, want_z=False):
         """k = exp(0.5 chol^T z): from given normals z (N, n) or from the device generator (N, seed)."""
         n = self.field_n
         if z is not None:
@@ -328,7 +331,8 @@ class TfinHandle:
             raise ValueError("field_sample: give N or z")
         k = np.empty((int(N), n))
         z_out = np.empty((int(N), n)) if want_z else None
-        _check(self._lib, self._lib.tfin_field_sample(self._h, _ptr(z), int(seed), int(subsequence), int(N), MEM_HOST, _ptr(k),
+        _check(self._lib, self._lib.tfin_field_sample(self._h, _ptr(z), int(seed), int(subsequence), int(first_row), int(N),
+                                                      MEM_HOST, _ptr(k),
                                                       _ptr(z_out), None), "tfin_field_sample")
         return (k, z_out) if want_z else k
 

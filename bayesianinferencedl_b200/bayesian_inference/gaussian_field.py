@@ -39,15 +39,15 @@ class FieldSampler:
     def handle(self):
         return self._h
 
-    def sample(self, N=None, z=None, seed=0, subsequence=0, return_z=False):
+    def sample(self, N=None, z=None, seed=0, subsequence=0, first_row=0, return_z=False):
         """``exp(0.5 * chol.T @ z)`` row by row.  ``z`` (n,) | (N, n) standard normals, or ``N`` draws from the
-        device generator (Philox4x32-10 keyed by ``seed``, disjoint streams per ``subsequence``, Box-Muller)."""
+        device generator (Philox4x32-10 + Box-Muller; row r is the stream of (seed, first_row + r, subsequence))."""
         if z is not None:
             z = np.asarray(z, dtype=np.float64)
             if z.ndim == 1:
                 return self._h.field_sample(z=z[None, :])[0]
             return self._h.field_sample(z=z)
-        return self._h.field_sample(N=N, seed=seed, subsequence=subsequence, want_z=return_z)
+        return self._h.field_sample(N=N, seed=seed, subsequence=subsequence, first_row=first_row, want_z=return_z)
 
 
 def make_cov_chol(V, kern_type="m52", length=1.6):

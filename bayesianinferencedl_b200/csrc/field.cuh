@@ -113,9 +113,10 @@ __global__ void __launch_bounds__(256) field_syrk_kernel(double* __restrict__ A,
 }
 
 // ------------------------------------------------------------------------------------------- F3 normals
-// Philox4x32-10 counter RNG + Box-Muller.  Element pair e (two consecutive doubles of the row-major (N, n) array) uses
-// counter (e_lo, e_hi, sub_lo, sub_hi) and key (seed_lo, seed_hi), `sub` being the caller's subsequence id (e.g. the
-// index of the first sample of a chunk); the four 32-bit outputs give two 53-bit uniforms.
+// Philox4x32-10 counter RNG + Box-Muller, one independent stream per ROW (sample / chain) of the (N, n) array:
+// the pair of entries (2p, 2p+1) of global row g draws counter (p, g_lo, g_hi, sub) under key (seed_lo, seed_hi), so a
+// row's normals depend only on (seed, g, sub) -- not on the batch, chunk or rank that computes it.  `sub` numbers
+// independent draws of the same row (e.g. the MCMC step).  The four 32-bit outputs give two 53-bit uniforms.
 __host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
@@ -129,22 +130,40 @@ __host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
     }
 }
 
-__global__ void __launch_bounds__(256) field_normal_kernel(unsigned long long seed, unsigned long long sub,
-                                                           long long count /* doubles */,
-                                                           double* __restrict__ z) {
-    const long long pairs = (count + 1) / 2;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < pairs;
+constexpr uint32_t PHILOX_PAIR_UNIFORM = 0xFFFFFFFFu;  // pair index reserved for the per-row accept/reject uniform
+
+// two uniforms of (row g, pair p, draw sub): u1 in (0, 1], u2 in [0, 1)
+__device__ __forceinline__ void philox_uniform2(unsigned long long seed, unsigned long long g, uint32_t p, uint32_t sub,
+                                                double& u1, double& u2) {
+    uint32_t c[4] = {p, (uint32_t)g, (uint32_t)(g >> 32), sub};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double two53 = 1.0 / 9007199254740992.0;
+    u1 = ((double)((((uint64_t)c[0] << 32) | c[1]) >> 11) + 1.0) * two53;
+    u2 = ((double)((((uint64_t)c[2] << 32) | c[3]) >> 11)) * two53;
+}
+
+__device__ __forceinline__ void philox_normal2(unsigned long long seed, unsigned long long g, uint32_t p, uint32_t sub,
+                                               double& z0, double& z1) {
+    double u1, u2, sn, cs;
+    philox_uniform2(seed, g, p, sub, u1, u2);
+    const double r = sqrt(-2.0 * log(u1));
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
+__global__ void __launch_bounds__(256) field_normal_kernel(unsigned long long seed, uint32_t sub, long long row0,
+                                                           long long N, int n, double* __restrict__ z) {
+    const int ppr = (n + 1) / 2;  // pairs per row
+    const long long total = N * ppr;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
-        uint32_t c[4] = {(uint32_t)e, (uint32_t)((unsigned long long)e >> 32), (uint32_t)sub, (uint32_t)(sub >> 32)};
-        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        const double two53 = 1.0 / 9007199254740992.0;
-        const double u1 = ((double)((((uint64_t)c[0] << 32) | c[1]) >> 11) + 1.0) * two53;  // (0, 1]
-        const double u2 = ((double)((((uint64_t)c[2] << 32) | c[3]) >> 11)) * two53;        // [0, 1)
-        const double r = sqrt(-2.0 * log(u1));
-        double sn, cs;
-        sincospi(2.0 * u2, &sn, &cs);
-        z[2 * e] = r * cs;
-        if (2 * e + 1 < count) z[2 * e + 1] = r * sn;
+        const long long r = e / ppr;
+        const int p = (int)(e - r * ppr);
+        double z0, z1;
+        philox_normal2(seed, (unsigned long long)(row0 + r), (uint32_t)p, sub, z0, z1);
+        z[r * n + 2 * p] = z0;
+        if (2 * p + 1 < n) z[r * n + 2 * p + 1] = z1;
     }
 }
 

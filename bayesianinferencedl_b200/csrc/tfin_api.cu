@@ -13,6 +13,7 @@
 #include "rom.cuh"
 #include "rom_nodal.cuh"
 #include "field.cuh"
+#include "chains.cuh"
 
 using namespace tfin;
 
@@ -128,6 +129,10 @@ struct tfin_ctx {
     int n_r = 0, rom_terms = 0, rom_obs = 0;
     DevBuf<double> d_S, d_obs_phi, d_romC;
     int64_t rom_chunk = 0;  // 0 = auto
+    // ---- many-chain pCN (C)
+    DevBuf<double> d_cz, d_czp, d_ck, d_ckp, d_cq, d_cqp, d_cphi, d_cqs, d_cqq, d_cks, d_cdata;
+    DevBuf<unsigned long long> d_cacc;
+    DevBuf<int> d_cstat;
     // ---- Gaussian-field sampler (F): lower Cholesky factor of the covariance, normals
     int f_n = 0;
     DevBuf<double> d_fL, d_fz, d_fk, d_fxy;
@@ -194,6 +199,11 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
     h->d_obsT_ptr.release();
     h->d_obsT_idx.release();
     for (auto* b : {&h->d_fL, &h->d_fz, &h->d_fk, &h->d_fxy}) b->release();
+    for (auto* b : {&h->d_cz, &h->d_czp, &h->d_ck, &h->d_ckp, &h->d_cq, &h->d_cqp, &h->d_cphi, &h->d_cqs, &h->d_cqq, &h->d_cks,
+                    &h->d_cdata})
+        b->release();
+    h->d_cacc.release();
+    h->d_cstat.release();
     h->d_finfo.release();
     for (auto* b : {&h->d_NG, &h->d_vr, &h->d_gtheta, &h->d_avgT_val, &h->d_bphi, &h->d_bout, &h->d_Ar, &h->d_Br, &h->d_y})
         b->release();
@@ -1212,8 +1222,18 @@ extern "C" int tfin_field_set_chol(tfin_handle_t h, int32_t n_pts, const double*
     return 0;
 }
 
-extern "C" int tfin_field_sample(tfin_handle_t h, const double* z, uint64_t seed, uint64_t subsequence, int64_t N,
-                                 int32_t mem,
+static int launch_field_sample(tfin_ctx* h, const double* d_z, int64_t N, double* d_k, cudaStream_t st) {
+    const int n = h->f_n;
+    dim3 grid((unsigned)((n + FS_BN - 1) / FS_BN), (unsigned)((N + FS_BM - 1) / FS_BM));
+    if (grid.y > 65535) return fail(TFIN_E_ARG, "field sampler: at most %d rows per call", 65535 * FS_BM);
+    field_sample_kernel<<<grid, 256, 0, st>>>(d_z, (long long)N, n, h->d_fL.p, d_k);
+    h->launches += 1;
+    TFIN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tfin_field_sample(tfin_handle_t h, const double* z, uint64_t seed, uint32_t subsequence,
+                                 int64_t first_row, int64_t N, int32_t mem,
                                  double* k_out, double* z_out, void* stream) {
     CHECK_HANDLE(h);
     if (h->f_n <= 0) return fail(TFIN_E_STATE, "tfin_field_sample: call tfin_field_set_cov or tfin_field_set_chol first");
@@ -1234,18 +1254,14 @@ extern "C" int tfin_field_sample(tfin_handle_t h, const double* z, uint64_t seed
             if (int e = h->d_fz.reserve(cnt)) return e;
             d_zw = h->d_fz.p;
         }
-        const long long pairs = ((long long)cnt + 1) / 2;
+        const long long pairs = (long long)N * ((n + 1) / 2);
         field_normal_kernel<<<(int)std::min<long long>((pairs + 255) / 256, (long long)h->sm_count * 16), 256, 0, st>>>(
-            (unsigned long long)seed, (unsigned long long)subsequence, (long long)cnt, d_zw);
+            (unsigned long long)seed, subsequence, (long long)first_row, (long long)N, n, d_zw);
         h->launches += 1;
         d_z = d_zw;
     }
     if (int e = sg.out_alloc(k_out, cnt, h->d_fk, &d_k)) return e;
-    dim3 grid((unsigned)((n + FS_BN - 1) / FS_BN), (unsigned)((N + FS_BM - 1) / FS_BM));
-    if (grid.y > 65535) return fail(TFIN_E_ARG, "tfin_field_sample: at most %d samples per call", 65535 * FS_BM);
-    field_sample_kernel<<<grid, 256, 0, st>>>(d_z, (long long)N, n, h->d_fL.p, d_k);
-    h->launches += 1;
-    TFIN_CUDA(cudaGetLastError());
+    if (int e = launch_field_sample(h, d_z, N, d_k, st)) return e;
     if (int e = sg.out_copy(k_out, cnt, (const double*)d_k)) return e;
     if (z_out && d_z != z_out) {
         if (sg.host) {
@@ -1255,6 +1271,123 @@ extern "C" int tfin_field_sample(tfin_handle_t h, const double* z, uint64_t seed
         }
     }
     if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ many-chain pCN
+extern "C" int tfin_pcn_chains(tfin_handle_t h, int32_t model, int64_t C, int64_t first_chain, int32_t n_steps,
+                               int32_t first_step, double beta, const double* data, double sigma, uint64_t seed,
+                               double tol, int32_t maxit, int32_t mem, double* z_state, int32_t init_from_prior,
+                               double* misfit_out, int64_t* accepted_out, double* qoi_out, double* qoi_sum_out,
+                               double* qoi_sq_out, double* k_sum_out, void* stream) {
+    CHECK_HANDLE(h);
+    if (h->f_n <= 0) return fail(TFIN_E_STATE, "tfin_pcn_chains: call tfin_field_set_cov / tfin_field_set_chol first");
+    if (h->f_n != h->n) return fail(TFIN_E_STATE, "tfin_pcn_chains: the prior has %d points but the operator %d dofs", h->f_n, h->n);
+    if (model != 0 && model != 1) return fail(TFIN_E_ARG, "tfin_pcn_chains: model must be 0 (nodal FOM) or 1 (averaged ROM)");
+    if (model == 0 && h->n_cells <= 0) return fail(TFIN_E_STATE, "tfin_pcn_chains: model 0 needs tfin_set_cells");
+    if (model == 1 && (h->n_r <= 0 || h->n_avg != h->rom_terms - 1))
+        return fail(TFIN_E_STATE, "tfin_pcn_chains: model 1 needs tfin_set_rom and tfin_set_averaging");
+    const int nobs = model == 0 ? h->n_obs : h->rom_obs;
+    if (nobs <= 0) return fail(TFIN_E_STATE, "tfin_pcn_chains: no observation operator");
+    if (C < 0 || n_steps < 0 || first_step < 0 || !(beta > 0.0 && beta <= 1.0) || !(sigma > 0.0) || !data ||
+        (C > 0 && !z_state) || !(tol > 0.0) || maxit < 1)
+        return fail(TFIN_E_ARG, "tfin_pcn_chains: bad argument (0 < beta <= 1, sigma > 0, z_state required)");
+    if (C == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const bool host = mem == TFIN_MEM_HOST;
+    const int n = h->n;
+    const size_t cn = (size_t)C * n, co = (size_t)C * nobs;
+    const bool want_k = k_sum_out != nullptr;
+    // device state: caller's buffers in device mode, staging otherwise
+    ChainState cs{};
+    if (host) {
+        if (int e = h->d_cz.reserve(cn)) return e;
+        cs.z = h->d_cz.p;
+        if (!init_from_prior) TFIN_CUDA(cudaMemcpyAsync(cs.z, z_state, cn * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        cs.z = z_state;
+    }
+    auto pick = [&](double* user, DevBuf<double>& buf, size_t count, double** out) -> int {
+        if (!host && user) {
+            *out = user;
+            return 0;
+        }
+        if (int e = buf.reserve(count)) return e;
+        *out = buf.p;
+        return 0;
+    };
+    if (int e = pick(misfit_out, h->d_cphi, (size_t)C, &cs.phi)) return e;
+    if (int e = pick(qoi_out, h->d_cq, co, &cs.qoi)) return e;
+    if (int e = pick(qoi_sum_out, h->d_cqs, co, &cs.qoi_sum)) return e;
+    if (int e = pick(qoi_sq_out, h->d_cqq, co, &cs.qoi_sq)) return e;
+    if (want_k) {
+        if (int e = pick(k_sum_out, h->d_cks, cn, &cs.k_sum)) return e;
+        if (int e = h->d_ck.reserve(cn)) return e;
+        cs.k = h->d_ck.p;
+    }
+    if (!host && accepted_out) cs.accepted = reinterpret_cast<unsigned long long*>(accepted_out);
+    else {
+        if (int e = h->d_cacc.reserve((size_t)C)) return e;
+        cs.accepted = h->d_cacc.p;
+    }
+    if (int e = h->d_czp.reserve(cn)) return e;
+    if (int e = h->d_ckp.reserve(cn)) return e;
+    if (int e = h->d_cqp.reserve(co)) return e;
+    if (int e = h->d_cstat.reserve((size_t)C)) return e;
+    std::vector<double> hd(data, data + nobs);   // data is a set-up array: always a host pointer
+    if (int e = h->d_cdata.upload(hd, st)) return e;
+    TFIN_CUDA(cudaMemsetAsync(cs.accepted, 0, (size_t)C * 8, st));
+    TFIN_CUDA(cudaMemsetAsync(cs.qoi_sum, 0, co * 8, st));
+    TFIN_CUDA(cudaMemsetAsync(cs.qoi_sq, 0, co * 8, st));
+    if (want_k) TFIN_CUDA(cudaMemsetAsync(cs.k_sum, 0, cn * 8, st));
+    const int ppr = (n + 1) / 2;
+    const int gp = (int)std::min<int64_t>((C * ppr + 255) / 256, (int64_t)h->sm_count * 16);
+    const int ga = (int)std::min<int64_t>((C + 7) / 8, (int64_t)h->sm_count * 8);
+    const double inv_s2 = 1.0 / (sigma * sigma);
+    auto forward = [&](const double* d_z) -> int {   // k' = T(z), qoi' = F(k'), status'
+        if (int e = launch_field_sample(h, d_z, C, h->d_ckp.p, st)) return e;
+        if (model == 0)
+            return fom_common(h, true, h->d_ckp.p, C, TFIN_IN_NODAL, TFIN_MEM_DEVICE, tol, maxit, nullptr, h->d_cqp.p,
+                              nullptr, h->d_cstat.p, nullptr, st);
+        return tfin_rom(h, h->d_ckp.p, C, TFIN_IN_NODAL, TFIN_MEM_DEVICE, nullptr, h->d_cqp.p, h->d_cstat.p, st);
+    };
+    // ---- start state: z from the caller or from the prior (Philox draw 0 of every chain), evaluated once
+    if (init_from_prior) {
+        field_normal_kernel<<<gp, 256, 0, st>>>((unsigned long long)seed, 0u, (long long)first_chain, (long long)C, n, cs.z);
+        h->launches += 1;
+    }
+    if (int e = forward(cs.z)) return e;
+    chain_accept_kernel<<<ga, 256, 0, st>>>(cs, cs.z, h->d_ckp.p, h->d_cqp.p, h->d_cstat.p, h->d_cdata.p, inv_s2,
+                                           (unsigned long long)seed, 0u, (long long)first_chain, (long long)C, n, nobs, 1);
+    h->launches += 1;
+    // ---- steps first_step+1 .. first_step+n_steps (draw index = step number, so runs can be continued)
+    for (int t = 1; t <= n_steps; ++t) {
+        const uint32_t step = (uint32_t)(first_step + t);
+        pcn_propose_kernel<<<gp, 256, 0, st>>>(cs.z, beta, (unsigned long long)seed, step, (long long)first_chain,
+                                              (long long)C, n, h->d_czp.p);
+        h->launches += 1;
+        if (int e = forward(h->d_czp.p)) return e;
+        chain_accept_kernel<<<ga, 256, 0, st>>>(cs, h->d_czp.p, h->d_ckp.p, h->d_cqp.p, h->d_cstat.p, h->d_cdata.p, inv_s2,
+                                               (unsigned long long)seed, step, (long long)first_chain, (long long)C, n,
+                                               nobs, 0);
+        h->launches += 1;
+    }
+    TFIN_CUDA(cudaGetLastError());
+    if (host) {
+        auto back = [&](void* dst, const void* src, size_t bytes) -> int {
+            if (dst) TFIN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+            return 0;
+        };
+        if (int e = back(z_state, cs.z, cn * 8)) return e;
+        if (int e = back(misfit_out, cs.phi, (size_t)C * 8)) return e;
+        if (int e = back(accepted_out, cs.accepted, (size_t)C * 8)) return e;
+        if (int e = back(qoi_out, cs.qoi, co * 8)) return e;
+        if (int e = back(qoi_sum_out, cs.qoi_sum, co * 8)) return e;
+        if (int e = back(qoi_sq_out, cs.qoi_sq, co * 8)) return e;
+        if (want_k)
+            if (int e = back(k_sum_out, cs.k_sum, cn * 8)) return e;
+        TFIN_CUDA(cudaStreamSynchronize(st));
+    }
     return 0;
 }
 

@@ -41,8 +41,8 @@ class DatasetGenerator:
 
     def generate(self, dataset_size, seed=0, z=None):
         """Returns ``(z_s, qoi_errors, qois)`` as numpy arrays of shapes (N, n), (N, n_obs), (N, n_obs).
-        ``z``: optional (N, n) standard normals (otherwise drawn on the device from ``seed``; every chunk draws the
-        Philox subsequence numbered by its first sample index)."""
+        ``z``: optional (N, n) standard normals (otherwise drawn on the device: sample s is the Philox stream
+        (seed, s), independent of the chunking)."""
         torch, dev, n, nobs = self.torch, self.dev, self.n, self.n_obs
         N = int(dataset_size)
         z_s, errs, qois = np.empty((N, n)), np.empty((N, nobs)), np.empty((N, nobs))
@@ -64,7 +64,7 @@ class DatasetGenerator:
                 if z is not None:
                     zbuf[:m].copy_(torch.from_numpy(np.ascontiguousarray(z[s0:s0 + m], dtype=np.float64)))
                     zp = zbuf.data_ptr()
-                _cabi._check(lib, lib.tfin_field_sample(h_f._h, zp, int(seed), s0, m, _cabi.MEM_DEVICE,
+                _cabi._check(lib, lib.tfin_field_sample(h_f._h, zp, int(seed), 0, s0, m, _cabi.MEM_DEVICE,
                                                         k.data_ptr(), None, sp), "tfin_field_sample")
                 h_f.fom_nodal_raw(k.data_ptr(), m, _cabi.MEM_DEVICE, self.solver.tol, self.solver.maxit,
                                   qoi=q.data_ptr(), status=st_f.data_ptr(), stream=sp)

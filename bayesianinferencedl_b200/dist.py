@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["shard_size", "shard_bounds", "gather_rows", "allreduce_moments", "sharded_map"]
+__all__ = ["shard_size", "shard_bounds", "gather_rows", "allreduce_moments", "chain_moments", "sharded_map"]
 
 
 def shard_size(n_total: int, world: int) -> int:
@@ -57,6 +57,30 @@ def allreduce_moments(local, group=None):
     mean = acc[1:1 + m] / c
     var = acc[1 + m:] / c - mean * mean
     return int(c), mean, var
+
+
+def chain_moments(count, col_sum, col_sq, group=None, device=None):
+    """Chain statistics from per-rank accumulators (count, sum, sum of squares per observable, numpy): summed over the
+    ranks when a process group is initialised -> ``(count, mean, var)`` as numpy.  Single-process: no communication."""
+    col_sum, col_sq = np.asarray(col_sum, dtype=np.float64), np.asarray(col_sq, dtype=np.float64)
+    acc = np.concatenate([[float(count)], col_sum, col_sq])
+    try:
+        import torch.distributed as dist
+        active = dist.is_available() and dist.is_initialized()
+    except Exception:
+        active = False
+    if active:
+        import torch
+        t = torch.from_numpy(acc)
+        if device is None and dist.get_backend(group) == "nccl":
+            device = torch.device("cuda", torch.cuda.current_device())
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        acc = t.cpu().numpy()
+    c, m = acc[0], len(col_sum)
+    mean = acc[1:1 + m] / c
+    return int(c), mean, acc[1 + m:] / c - mean * mean
 
 
 def sharded_map(fn, batch: np.ndarray, group=None, device=None):

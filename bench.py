@@ -335,7 +335,7 @@ def run_b200(args):
         def draw():  # k = exp(0.5 chol^T z), z from the device Philox generator; 16384-sample chunks
             for lo in range(0, NN, 16384):
                 m = min(16384, NN - lo)
-                rc = lib.tfin_field_sample(fin.handle._h, None, NODAL_SEED + rank, lo, m, _cabi.MEM_DEVICE,
+                rc = lib.tfin_field_sample(fin.handle._h, None, NODAL_SEED, 0, rank * NN + lo, m, _cabi.MEM_DEVICE,
                                            k_dev[lo:].data_ptr(), None, sp)
                 if rc:
                     raise RuntimeError(lib.tfin_last_error().decode())

@@ -207,13 +207,33 @@ int tfin_field_set_chol(tfin_handle_t h, int32_t n_pts, const double* chol);
 
 /*
  * Batched conductivity draws k_s = exp(0.5 * chol^T z_s) (deep_learning/generate_fin_dataset.py:87-88).
- *   z (N, n_pts) standard normals, or NULL: drawn on the device (Philox4x32-10 keyed by `seed`; counter = (index of
- *   the element pair in the row-major (N, n_pts) array, `subsequence`); Box-Muller).  Calls with different
- *   `subsequence` values (e.g. the index of the first sample of a chunk) draw disjoint streams of the same seed.
+ *   z (N, n_pts) standard normals, or NULL: drawn on the device, one independent Philox4x32-10 stream per row:
+ *   entries (2p, 2p+1) of row r = Box-Muller of counter (p, first_row + r, subsequence) under key `seed`, so a sample
+ *   depends only on (seed, its global index, subsequence) -- not on chunking or on the rank that draws it.
  *   k_out (N, n_pts);  z_out (N, n_pts) | NULL
  */
-int tfin_field_sample(tfin_handle_t h, const double* z, uint64_t seed, uint64_t subsequence, int64_t N, int32_t mem,
-                      double* k_out, double* z_out, void* stream);
+int tfin_field_sample(tfin_handle_t h, const double* z, uint64_t seed, uint32_t subsequence, int64_t first_row,
+                      int64_t N, int32_t mem, double* k_out, double* z_out, void* stream);
+
+/*
+ * Many-chain preconditioned Crank-Nicolson Metropolis on the Gaussian-field prior, all chains advanced together on the
+ * device: the batched replacement of one likelihood evaluation per sampler proposal
+ * (bayesian_inference/pymc_func_bayes_inverse.py:68-90, 201; inference.py:42-52).
+ *   state z_c (n normals), k_c = exp(0.5 chol^T z_c), misfit Phi = 0.5 ||qoi(k_c) - data||^2 / sigma^2,
+ *   proposal z' = sqrt(1 - beta^2) z + beta xi, accepted when log u < Phi(z) - Phi(z').
+ *   model: 0 = nodal full-order solve (tfin_fom_nodal), 1 = sub-fin-averaged LSPG ROM (tfin_rom, nodal input).
+ *   Chain c is global chain first_chain + c: all its random numbers are the Philox streams (seed, first_chain + c,
+ *   step), so results do not depend on how chains are sharded over GPUs; steps are numbered first_step + 1 ...
+ *   first_step + n_steps (pass the previous total to continue a run).
+ *   data (n_obs) HOST pointer.  z_state (C, n) in/out (ignored on input if init_from_prior != 0: draw 0 of the prior).
+ *   Outputs (each | NULL): misfit_out (C) of the final state, accepted_out (C) accepted proposals, qoi_out (C, n_obs)
+ *   final observables, qoi_sum_out / qoi_sq_out (C, n_obs) sums over the steps of the chain's current observables,
+ *   k_sum_out (C, n) sum over the steps of the current conductivity field.
+ */
+int tfin_pcn_chains(tfin_handle_t h, int32_t model, int64_t C, int64_t first_chain, int32_t n_steps, int32_t first_step,
+                    double beta, const double* data, double sigma, uint64_t seed, double tol, int32_t maxit, int32_t mem,
+                    double* z_state, int32_t init_from_prior, double* misfit_out, int64_t* accepted_out, double* qoi_out,
+                    double* qoi_sum_out, double* qoi_sq_out, double* k_sum_out, void* stream);
 
 /* theta = averaging(k) for N nodal fields (subfin_avg_op batched); out (N, n_rows). */
 int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double* theta_out,

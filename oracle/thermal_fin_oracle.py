@@ -350,22 +350,59 @@ def philox4x32_10(counter, key):
     return c
 
 
-def philox_normals(seed, count, subsequence=0):
-    """Restatement of the product's device generator (csrc/field.cuh, F3) -- NOT part of the reference, which draws
-    ``np.random.randn`` unseeded (generate_fin_dataset.py:87): Philox4x32-10 with counter (pair index lo, hi, 0, 0) and
-    key ``seed`` (counter words 2, 3 = ``subsequence``), two 53-bit uniforms per pair, Box-Muller.  Returns ``count`` standard normals."""
-    pairs = (count + 1) // 2
-    e = np.arange(pairs, dtype=np.uint64)
-    sub_lo = np.full(pairs, subsequence & 0xFFFFFFFF, np.uint64)
-    sub_hi = np.full(pairs, (subsequence >> 32) & 0xFFFFFFFF, np.uint64)
-    c = philox4x32_10([e & np.uint64(0xFFFFFFFF), e >> np.uint64(32), sub_lo, sub_hi], (seed, seed >> 32))
+def philox_uniforms(seed, rows, pairs, subsequence=0):
+    """Two 53-bit uniforms per (row, pair): counter (pair, row_lo, row_hi, subsequence), key ``seed``.
+    ``rows`` / ``pairs``: integer arrays (broadcast together).  u1 in (0, 1], u2 in [0, 1)."""
+    rows, pairs = np.broadcast_arrays(np.asarray(rows, dtype=np.uint64), np.asarray(pairs, dtype=np.uint64))
+    m32 = np.uint64(0xFFFFFFFF)
+    c = philox4x32_10([pairs & m32, rows & m32, rows >> np.uint64(32),
+                       np.full(rows.shape, subsequence & 0xFFFFFFFF, np.uint64)], (seed, seed >> 32))
     u1 = ((((c[0] << np.uint64(32)) | c[1]) >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740992.0
     u2 = (((c[2] << np.uint64(32)) | c[3]) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+    return u1, u2
+
+
+def philox_normals(seed, n_rows, n, first_row=0, subsequence=0):
+    """Restatement of the product's device generator (csrc/field.cuh, F3) -- NOT part of the reference, which draws
+    ``np.random.randn`` unseeded (generate_fin_dataset.py:87): one Philox4x32-10 stream per row, entries (2p, 2p+1) of
+    global row g = Box-Muller of counter (p, g, subsequence) under key ``seed``.  Returns (n_rows, n) normals."""
+    ppr = (n + 1) // 2
+    g = (first_row + np.arange(n_rows))[:, None]
+    u1, u2 = philox_uniforms(seed, g, np.arange(ppr)[None, :], subsequence)
     r = np.sqrt(-2.0 * np.log(u1))
-    out = np.empty(2 * pairs)
-    out[0::2] = r * np.cos(2.0 * np.pi * u2)
-    out[1::2] = r * np.sin(2.0 * np.pi * u2)
-    return out[:count]
+    out = np.empty((n_rows, 2 * ppr))
+    out[:, 0::2] = r * np.cos(2.0 * np.pi * u2)
+    out[:, 1::2] = r * np.sin(2.0 * np.pi * u2)
+    return out[:, :n]
+
+
+def pcn_chains(qoi_fn, chol, data, sigma, seed, n_chains, n_steps, beta, first_chain=0, z0=None):
+    """Restatement of the product's many-chain pCN driver (csrc/chains.cuh; not in the reference, whose samplers are
+    PyMC3 / MUQ): misfit 0.5 ||qoi_fn(k) - data||^2 / sigma^2 (pymc_func_bayes_inverse.py:76, 201) with
+    k = exp(0.5 chol^T z) (generate_fin_dataset.py:88); proposal z' = sqrt(1 - beta^2) z + beta xi; accept when
+    log u < Phi - Phi'.  xi / u of chain g at step t are the Philox draws (seed, g, t)."""
+    n = chol.shape[0]
+    z = philox_normals(seed, n_chains, n, first_chain, 0) if z0 is None else np.array(z0, dtype=np.float64)
+    misfit = lambda q: 0.5 * np.sum((q - data) ** 2) / sigma ** 2
+    q = np.stack([qoi_fn(sample_field(chol, z[c])) for c in range(n_chains)])
+    phi = np.array([misfit(q[c]) for c in range(n_chains)])
+    acc = np.zeros(n_chains, dtype=np.int64)
+    q_sum, q_sq = np.zeros_like(q), np.zeros_like(q)
+    k_sum = np.zeros((n_chains, n))
+    for t in range(1, n_steps + 1):
+        xi = philox_normals(seed, n_chains, n, first_chain, t)
+        u, _ = philox_uniforms(seed, first_chain + np.arange(n_chains), 0xFFFFFFFF, t)
+        zp = np.sqrt(1.0 - beta * beta) * z + beta * xi
+        for c in range(n_chains):
+            qp = qoi_fn(sample_field(chol, zp[c]))
+            pp = misfit(qp)
+            if np.log(u[c]) < phi[c] - pp:
+                z[c], q[c], phi[c] = zp[c], qp, pp
+                acc[c] += 1
+        q_sum += q
+        q_sq += q * q
+        k_sum += np.exp(0.5 * (z @ chol))
+    return {"z": z, "qoi": q, "misfit": phi, "accepted": acc, "qoi_sum": q_sum, "qoi_sq": q_sq, "k_sum": k_sum}
 
 
 def pod_basis(oracle: FinOracle, n_snapshots=200, basis_size=81, seed=0, lo=0.1, hi=3.5):

@@ -395,10 +395,11 @@ def test_field_prior_on_device(space_m2, oracle_m2):
     assert np.array_equal(sample_fields(prior.chol, z[:5]), k[:5])            # caller-supplied factor
     # device generator: bit pattern of Philox is exact, log / sincos differ by ulps from numpy's
     k2, z2 = prior.sample(N=33, seed=2026, return_z=True)
-    z_ref = philox_normals(2026, 33 * n).reshape(33, n)
+    z_ref = philox_normals(2026, 33, n)
     assert np.max(np.abs(z2 - z_ref)) <= 1e-13
     assert relerr(k2[17], sample_field(prior.chol, z2[17])) <= 1e-12
     assert not np.array_equal(prior.sample(N=33, seed=2027), k2)
+    assert np.array_equal(prior.sample(N=5, seed=2026, first_row=20), k2[20:25])   # row streams are position independent
 
 
 def test_dataset_generator(space_m2, oracle_m2, tmp_path):
@@ -411,10 +412,9 @@ def test_dataset_generator(space_m2, oracle_m2, tmp_path):
     gen = DatasetGenerator(space_m2, phi, chunk=16)                           # several chunks, ragged tail
     z_s, errs, qois = gen.generate(37, seed=9)
     assert z_s.shape == (37, orc.n) and errs.shape == (37, 9) and qois.shape == (37, 9)
-    for s0 in (0, 16, 32):                                                    # chunk = Philox subsequence s0
-        m = min(16, 37 - s0)
-        zn = philox_normals(9, m * orc.n, subsequence=s0).reshape(m, orc.n)
-        assert relerr(z_s[s0], sample_field(gen.prior.chol, zn[0])) <= 1e-11
+    zn = philox_normals(9, 37, orc.n)                                         # sample s = Philox stream (seed, s)
+    for s in (0, 16, 36):
+        assert relerr(z_s[s], sample_field(gen.prior.chol, zn[s])) <= 1e-11
     for s in (0, 15, 16, 36):
         q = orc.qoi_operator(orc.forward(z_s[s]))
         q_r = orc.qoi_reduced(orc.forward_reduced(z_s[s], phi), phi)
@@ -425,3 +425,58 @@ def test_dataset_generator(space_m2, oracle_m2, tmp_path):
     for name in ("z_aff_avg_eval_avg_obs_3", "errors_aff_avg_eval_avg_obs_3", "qois_avg_eval_avg_obs_3"):
         assert (tmp_path / f"{name}.npy").exists()
     assert np.array_equal(np.load(tmp_path / "qois_avg_eval_avg_obs_3.npy"), qois[:5])
+
+
+def test_likelihood_and_pcn_chains(space_m2, oracle_m2):
+    """SqError.err_grad_FOM/ROM (pymc_func_bayes_inverse.py:68-90) batched, and the many-chain pCN driver against its
+    numpy restatement driven by the same Philox streams (accept decisions must coincide exactly)."""
+    from bayesianinferencedl_b200 import make_cov_chol
+    from bayesianinferencedl_b200.bayesian_inference.likelihood import PCNChains, SqError
+    from oracle.thermal_fin_oracle import pcn_chains, pod_basis
+    orc = oracle_m2
+    chol = make_cov_chol(space_m2, "m52", 1.6)
+    phi = pod_basis(orc, n_snapshots=40, basis_size=20, seed=1)
+    sq = SqError(space_m2, chol, False, phi=phi, seed=4)
+    assert relerr(sq.obs_data, orc.qoi_operator(orc.forward(sq.k_true))) <= 1e-10
+    rng = np.random.default_rng(31)
+    k = np.exp(0.3 * rng.standard_normal((3, orc.n)))
+    err, grad = sq.err_grad_FOM(k)
+    err_r, grad_r = sq.err_grad_ROM(k)
+    for s in range(3):
+        q = orc.qoi_operator(orc.forward(k[s]))
+        assert abs(err[s] - 0.5 * np.sum((q - sq.obs_data) ** 2)) <= 1e-9 * err[s]
+        ref = orc.gradient(k[s], sq.obs_data)
+        assert np.max(np.abs(grad[s] - ref)) <= 1e-9 * np.max(np.abs(ref))
+        ref_r, J_r, _ = orc.grad_reduced(k[s], sq.obs_data, phi)
+        assert np.max(np.abs(grad_r[s] - ref_r)) <= 1e-8 * np.max(np.abs(ref_r)) and abs(err_r[s] - J_r) <= 1e-9 * J_r
+    e1, g1 = sq.err_grad_FOM(k[1])                                     # single-field signature of the reference
+    assert isinstance(e1, float) and np.array_equal(g1, grad[1])
+
+    # ---- pCN, full-order likelihood: 6 chains x 7 steps, then 3 more steps continuing the run
+    sigma, beta, seed = 0.02, 0.15, 77
+    ch = PCNChains(sq._solver, chol, sq.obs_data, sigma, seed=seed)
+    out = ch.run(7, n_chains=6, beta=beta, first_chain=10, want_k_mean=True)
+    ref = pcn_chains(lambda kk: orc.qoi_operator(orc.forward(kk)), chol, sq.obs_data, sigma, seed, 6, 7, beta,
+                     first_chain=10)
+    assert np.array_equal(out["accepted"], ref["accepted"]) and 0 < out["accepted"].sum() < 42
+    assert np.max(np.abs(out["z"] - ref["z"])) <= 1e-12
+    assert np.max(np.abs(out["misfit"] - ref["misfit"])) <= 1e-7 * np.max(ref["misfit"])
+    assert relerr(out["qoi_sum"], ref["qoi_sum"]) <= 1e-9 and relerr(out["qoi_sq"], ref["qoi_sq"]) <= 1e-9
+    assert relerr(out["k_sum"], ref["k_sum"]) <= 1e-10
+    out2 = ch.run(3, beta=beta)
+    ref10 = pcn_chains(lambda kk: orc.qoi_operator(orc.forward(kk)), chol, sq.obs_data, sigma, seed, 6, 10, beta,
+                       first_chain=10)
+    assert np.array_equal(out["accepted"] + out2["accepted"], ref10["accepted"])
+    assert np.max(np.abs(out2["z"] - ref10["z"])) <= 1e-12
+    # chains are independent of the sharding: chains 12..13 alone reproduce rows 2..3
+    sub = PCNChains(sq._solver, chol, sq.obs_data, sigma, seed=seed).run(7, n_chains=2, beta=beta, first_chain=12)
+    assert np.array_equal(sub["accepted"], out["accepted"][2:4]) and np.array_equal(sub["qoi_sum"], out["qoi_sum"][2:4])
+    summ = PCNChains.summarize(out)
+    assert summ["count"] == 42 and np.allclose(summ["qoi_mean"], out["qoi_sum"].sum(0) / 42)
+    # ---- reduced likelihood
+    chr_ = PCNChains(sq._solver_r, chol, sq.obs_data, sigma, seed=seed)
+    outr = chr_.run(5, n_chains=4, beta=beta)
+    refr = pcn_chains(lambda kk: orc.qoi_reduced(orc.forward_reduced(kk, phi), phi), chol, sq.obs_data, sigma, seed, 4,
+                      5, beta)
+    assert np.array_equal(outr["accepted"], refr["accepted"])
+    assert np.max(np.abs(outr["z"] - refr["z"])) <= 1e-12 and relerr(outr["qoi_sum"], refr["qoi_sum"]) <= 1e-8

@@ -132,7 +132,9 @@ def test_philox_known_answers():
     for ctr, key, want in kat:
         got = philox4x32_10([np.array([v], np.uint64) for v in ctr], key)
         assert tuple(int(g[0]) for g in got) == want
-    z = philox_normals(12345, 200001)
-    assert z.shape == (200001,) and np.all(np.isfinite(z))
+    z = philox_normals(12345, 400, 501)
+    assert z.shape == (400, 501) and np.all(np.isfinite(z))
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
-    assert np.array_equal(philox_normals(12345, 11), z[:11])            # counter based: prefix stable
+    # one stream per row: a row depends only on (seed, global row, subsequence)
+    assert np.array_equal(philox_normals(12345, 3, 501, first_row=7), z[7:10])
+    assert not np.array_equal(philox_normals(12345, 3, 501, first_row=7, subsequence=1), z[7:10])
