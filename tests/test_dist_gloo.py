@@ -30,11 +30,14 @@ def _worker(rank, world, port, n_total, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from bayesianinferencedl_b200.dist import allreduce_moments, shard_bounds, sharded_map
+    from bayesianinferencedl_b200.dist import allreduce_moments, chain_moments, shard_bounds, sharded_map
     batch = np.random.default_rng(5).uniform(0.1, 3.5, (n_total, 9))
     full = sharded_map(_fake_forward, batch)
     lo, hi = shard_bounds(n_total, world, rank)
     cnt, mean, var = allreduce_moments(torch.from_numpy(_fake_forward(batch[lo:hi])))
+    loc = _fake_forward(batch[lo:hi])                   # per-rank chain accumulators (count, sum, sum of squares)
+    c2, m2, v2 = chain_moments(len(loc), loc.sum(0), (loc * loc).sum(0))
+    assert c2 == cnt and np.allclose(m2, mean.numpy()) and np.allclose(v2, var.numpy(), atol=1e-12)
     dist.destroy_process_group()
     q.put((rank, full, cnt, mean.numpy(), var.numpy()))
 

@@ -138,6 +138,61 @@ def test_rom_offline_tensors(space_m1, oracle_m1):
     assert np.allclose(obs_phi, oracle_m1.B_obs @ phi)
 
 
+def test_rom_gradient_tensors(space_m1, oracle_m1):
+    """Gram-block form of the reduced gradient equals the literal formula of averaged_affine_ROM.py:335-356."""
+    from bayesianinferencedl_b200.assembly import build_operators
+    from bayesianinferencedl_b200.rom.averaged_affine_ROM import rom_gradient_tensors
+    ops = build_operators(space_m1)
+    rng = np.random.default_rng(4)
+    phi = np.linalg.qr(rng.standard_normal((ops.n, 6)))[0]
+    NG = rom_gradient_tensors(ops, phi)
+    assert NG.shape == (10, 9, 6, 6)
+    k = np.exp(0.3 * rng.standard_normal(ops.n))
+    data = rng.uniform(0.1, 0.5, 9)
+    dJ, J, g = oracle_m1.grad_reduced(k, data, phi)
+    th = np.concatenate([[1.0], oracle_m1.subfin_avg_op(k)])
+    psi = oracle_m1.matrix_affine(th[1:]) @ phi
+    A_r = psi.T @ psi
+    w_r = np.linalg.solve(A_r, psi.T @ oracle_m1.B)
+    obs_phi = oracle_m1.B_obs @ phi
+    v_r = np.linalg.solve(A_r, obs_phi.T @ (data - obs_phi @ w_r))
+    g_gram = np.array([sum(th[t] * v_r @ NG[t, q] @ w_r for t in range(10)) for q in range(9)])
+    assert np.allclose(g_gram, g, rtol=1e-10, atol=1e-14 * np.max(np.abs(g)))
+    assert np.allclose(g_gram @ ops.B_obs, dJ, rtol=1e-10, atol=1e-14 * np.max(np.abs(dJ)))
+
+
+def test_oracle_gradients_finite_difference(oracle_m1):
+    """The oracle's adjoint gradient / sensitivity restatements (forward_solve.py:293-342) against central differences."""
+    o = oracle_m1
+    rng = np.random.default_rng(8)
+    k = np.exp(0.3 * rng.standard_normal(o.n))
+    data = rng.uniform(0.1, 0.5, 9)
+    cost = lambda kk: 0.5 * np.sum((o.qoi_operator(o.forward(kk)) - data) ** 2)
+    g, Jac = o.gradient(k, data), o.sensitivity(k)
+    d = rng.standard_normal(o.n)
+    eps = 1e-6
+    fd = (cost(k + eps * d) - cost(k - eps * d)) / (2 * eps)
+    assert abs(fd - g @ d) <= 1e-6 * abs(fd)
+    fdq = (o.qoi_operator(o.forward(k + eps * d)) - o.qoi_operator(o.forward(k - eps * d))) / (2 * eps)
+    assert np.allclose(Jac @ d, fdq, rtol=1e-6, atol=1e-12)
+
+
+def test_oracle_pcn_chains_invariants(oracle_m1):
+    """The pCN restatement: beta -> tiny accepts (almost) everything, chains are independent of their neighbours."""
+    from oracle.thermal_fin_oracle import make_cov_chol, pcn_chains
+    o = oracle_m1
+    chol = make_cov_chol(o.coords, "m52", 1.6)
+    data = o.qoi_operator(o.forward(np.ones(o.n)))
+    f = lambda kk: o.qoi_operator(o.forward(kk))
+    a = pcn_chains(f, chol, data, 0.05, 3, 4, 5, 0.2, first_chain=0)
+    b = pcn_chains(f, chol, data, 0.05, 3, 2, 5, 0.2, first_chain=2)
+    assert np.array_equal(a["accepted"][2:], b["accepted"]) and np.array_equal(a["z"][2:], b["z"])
+    assert np.all(a["accepted"] <= 5) and np.all(a["misfit"] >= 0)
+    tiny = pcn_chains(f, chol, data, 10.0, 3, 3, 4, 1e-6)
+    assert np.all(tiny["accepted"] >= 3)
+    assert np.allclose(tiny["qoi_sum"] / 4, tiny["qoi"], rtol=1e-4)
+
+
 def test_shard_bounds():
     from bayesianinferencedl_b200.dist import shard_bounds, shard_size
     for n, w in [(10, 3), (8, 8), (5, 8), (0, 2), (1000001, 8)]:
