@@ -43,7 +43,25 @@ struct PcgOp {
     const double* dcoef;  // [dnnz]
     const double* dcst;   // [ld]
     const int* cells;     // [n_cells][3]
+    int coef_mode;        // cell coefficient of the nodal operator: 0 = mean(k) (exact for P1 k), 1 = quadrature of exp(k)
 };
+
+// Cell coefficient (1/|e|) int_e c(k) dx of the nodal-conductivity stiffness for vertex values (ka, kb, kc):
+//   mode 0: c = k      -> mean of the vertex values (Fin._F, fom/forward_solve.py:160-161)
+//   mode 1: c = exp(k) -> the degree-3 rule dolfin's form compiler picks for exp(P1) * grad(P1).grad(P1)
+//           (fom/forward_solve_exp.py:160-161; UFL estimates degree(exp(k)) = 1 + 2, FIAT's degree-3 triangle scheme is
+//           the 6-point Strang-Fix rule with equal weights: barycentric permutations of (a, b, c) below)
+__device__ __forceinline__ double cell_coefficient(int mode, double ka, double kb, double kc) {
+    if (mode == 0) return ((ka + kb) + kc) / 3.0;
+    const double a = 0.659027622374092, b = 0.231933368553031, c = 0.109039009072877;
+    double s = exp(fma(a, ka, fma(b, kb, c * kc)));
+    s += exp(fma(a, ka, fma(c, kb, b * kc)));
+    s += exp(fma(b, ka, fma(a, kb, c * kc)));
+    s += exp(fma(b, ka, fma(c, kb, a * kc)));
+    s += exp(fma(c, ka, fma(a, kb, b * kc)));
+    s += exp(fma(c, ka, fma(b, kb, a * kc)));
+    return s * (1.0 / 6.0);
+}
 
 struct CsrRows {
     int rows;
@@ -210,7 +228,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, 
             // cell means:  int k grad w.grad v over a cell = mean(k at its vertices) * K_e
             for (int e = tid; e < nc; e += T) {
                 const int a = op.cells[3 * e], b = op.cells[3 * e + 1], c = op.cells[3 * e + 2];
-                s_kbar[e] = ((kk[a] + kk[b]) + kk[c]) / 3.0;
+                s_kbar[e] = cell_coefficient(op.coef_mode, kk[a], kk[b], kk[c]);
             }
             __syncthreads();
 #pragma unroll

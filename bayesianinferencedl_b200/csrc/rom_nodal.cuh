@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256, 2) rom_nodal_gram_kernel(PcgOp op, const 
         __syncthreads();  // previous sample finished with every buffer
         for (int e = tid; e < nc; e += NT) {
             const int a = op.cells[3 * e], b = op.cells[3 * e + 1], c = op.cells[3 * e + 2];
-            s_kbar[e] = ((__ldg(kk + a) + __ldg(kk + b)) + __ldg(kk + c)) / 3.0;  // same association as K2
+            s_kbar[e] = cell_coefficient(op.coef_mode, __ldg(kk + a), __ldg(kk + b), __ldg(kk + c));  // as in K2
         }
         if (tid == 0) s_kbar[nc] = 0.0;  // sentinel "no cell"
         __syncthreads();

@@ -119,6 +119,7 @@ struct tfin_ctx {
     DevBuf<double> d_obs_val, d_avg_val;
     // ---- nodal operator (K2)
     int n_cells = 0, Wn = 0;
+    int coef_mode = 0;  // 0: k, 1: exp(k) (forward_solve_exp.py)
     DevBuf<uint16_t> d_ncol;
     DevBuf<int> d_ncell, d_dptr, d_dcell, d_cells;
     DevBuf<double> d_ncoef, d_ncst, d_dcoef, d_dcst, d_Ke;
@@ -667,6 +668,7 @@ static int launch_pcg(tfin_ctx* h, bool nodal, const double* d_in, int in_stride
         op.dcoef = h->d_dcoef.p;
         op.dcst = h->d_dcst.p;
         op.cells = h->d_cells.p;
+        op.coef_mode = h->coef_mode;
     } else {
         op.col = h->d_col.p;
         op.val = h->d_val.p;
@@ -921,6 +923,7 @@ static int rom_run(tfin_ctx* h, const RomSrc& src, int nr, int nobs, const doubl
             op.col = h->d_ncol.p; op.cell = h->d_ncell.p; op.coef = h->d_ncoef.p; op.cst = h->d_ncst.p;
             op.dptr = h->d_dptr.p; op.dcell = h->d_dcell.p; op.dcoef = h->d_dcoef.p; op.dcst = h->d_dcst.p;
             op.cells = h->d_cells.p;
+            op.coef_mode = h->coef_mode;
             const int g1 = (int)std::min<int64_t>(s1 - s0, (int64_t)h->sm_count * gram_occ);
             rom_nodal_gram_kernel<<<g1, gram_threads, gram_smem, st>>>(op, src.d_in, s0, s1, h->d_bphi.p, nr, h->b_TT,
                                                                        h->d_romC.p);
@@ -1108,6 +1111,7 @@ static int fom_adjoint(tfin_handle_t h, int mode, const double* k, int64_t N, in
                        const double* data, int64_t data_rows, double* grad_out, double* cost_out, double* qoi_out,
                        int32_t* iters_out, int32_t* status_out, void* stream) {
     if (h->n_cells <= 0) return fail(TFIN_E_STATE, "adjoint solve: call tfin_set_cells first");
+    if (h->coef_mode != 0) return fail(TFIN_E_STATE, "adjoint solve: not available for the exp(k) parametrisation");
     if (h->n_obs <= 0 || h->n_obs > 64) return fail(TFIN_E_STATE, "adjoint solve: needs an observation operator with <= 64 rows");
     if (N < 0 || (N > 0 && (!k || !grad_out))) return fail(TFIN_E_ARG, "adjoint solve: bad batch argument");
     if (!(tol > 0.0) || maxit < 1) return fail(TFIN_E_ARG, "adjoint solve: tol must be > 0 and maxit >= 1");
@@ -1413,6 +1417,7 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
     if (k == "pcg_reg_slots") return h->last_WR;
     if (k == "rom_chunk") return h->rom_chunk;
     if (k == "pcg_path") return h->last_path;
+    if (k == "nodal_coef_mode") return h->coef_mode;
     if (k == "stream_tile") return h->last_tile;
     if (k == "stream_ell_width") return h->s_We;
     if (k == "stream_ld") return h->s_ldr;
@@ -1448,6 +1453,11 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
     }
     if (k == "pcg_path") {
         h->pcg_path = (int)value;
+        return 0;
+    }
+    if (k == "nodal_coef_mode") {
+        if (value != 0 && value != 1) return fail(TFIN_E_ARG, "nodal_coef_mode must be 0 (k) or 1 (exp(k))");
+        h->coef_mode = (int)value;
         return 0;
     }
     if (k == "stream_tile") {

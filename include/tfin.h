@@ -246,7 +246,10 @@ int64_t tfin_kernel_launches(tfin_handle_t h);
  * "pcg_threads", "pcg_rows_per_thread", "pcg_ctas_per_sm", "pcg_smem_bytes"; returns -1 if unknown. */
 int64_t tfin_get_int(tfin_handle_t h, const char* key);
 
-/* Tuning knobs (before the next solve call): "pcg_rows_per_thread" (0 = auto), "rom_chunk" ...  */
+/* Knobs (before the next solve call): "pcg_rows_per_thread" (0 = auto), "rom_chunk", "pcg_path", "stream_tile" ...;
+ * "nodal_coef_mode": 0 = conductivity k (fom/forward_solve.py:160), 1 = conductivity exp(k) integrated with the
+ * degree-3 rule of dolfin's form compiler (fom/forward_solve_exp.py:160) in tfin_fom_nodal / tfin_rom_nodal /
+ * tfin_pcn_chains(model 0); the adjoint entry points refuse mode 1. */
 int tfin_set_int(tfin_handle_t h, const char* key, int64_t value);
 
 #ifdef __cplusplus

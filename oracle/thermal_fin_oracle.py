@@ -172,6 +172,22 @@ class FinOracle:
         kbar = np.asarray(k, dtype=np.float64)[self.cells].mean(axis=1)
         return (self._stiffness(kbar) + self.Bi * self.M_robin).tocsc()
 
+    def matrix_nodal_exp(self, k):
+        """A of ``forward_solve_exp.py:160-161``: ``exp(k) grad w . grad v``.  The form compiler integrates it with the
+        rule UFL/FIAT select: degree(exp(P1)) is estimated as 1 + 2 = 3 and FIAT's degree-3 triangle scheme is the
+        6-point Strang-Fix rule (equal weights, barycentric permutations of 0.659..., 0.231..., 0.109...), so the cell
+        coefficient is the mean of exp(k) over those six points.  (dolfin/FFC 2018.1 are not installable here: the
+        rule is restated from FIAT's quadrature_schemes, parity unpinned like the rest of this file.)"""
+        kv = np.asarray(k, dtype=np.float64)[self.cells]                       # (n_cells, 3)
+        a, b, c = 0.659027622374092, 0.231933368553031, 0.109039009072877
+        pts = np.array([[a, b, c], [a, c, b], [b, a, c], [b, c, a], [c, a, b], [c, b, a]])
+        coeff = np.exp(kv @ pts.T).mean(axis=1)
+        return (self._stiffness(coeff) + self.Bi * self.M_robin).tocsc()
+
+    def forward_exp(self, k):
+        """``Fin.forward`` of forward_solve_exp.py:252-275."""
+        return spla.splu(self.matrix_nodal_exp(k)).solve(self.B)
+
     def forward(self, k):
         """``Fin.forward(k)`` (forward_solve.py:270-291): dolfin ``solve`` = sparse direct LU."""
         return spla.splu(self.matrix_nodal(k)).solve(self.B)

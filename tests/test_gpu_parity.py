@@ -480,3 +480,26 @@ def test_likelihood_and_pcn_chains(space_m2, oracle_m2):
                       5, beta)
     assert np.array_equal(outr["accepted"], refr["accepted"])
     assert np.max(np.abs(outr["z"] - refr["z"])) <= 1e-12 and relerr(outr["qoi_sum"], refr["qoi_sum"]) <= 1e-8
+
+
+def test_exp_parametrisation(space_m2, oracle_m2):
+    """fom/forward_solve_exp.py:160-161: conductivity exp(k), cell coefficient by the 6-point degree-3 rule."""
+    from bayesianinferencedl_b200.fom.forward_solve_exp import Fin as FinExp
+    orc = oracle_m2
+    fin = FinExp(space_m2)
+    rng = np.random.default_rng(41)
+    k = 0.5 * rng.standard_normal((5, orc.n))                              # log-conductivities, any sign
+    q = fin.forward_qoi(k)
+    w = fin.forward(k)[0]
+    for s in range(5):
+        w_ref = orc.forward_exp(k[s])
+        assert np.max(np.abs(w[s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref))
+        assert relerr(q[s], orc.qoi_operator(w_ref)) <= RTOL_FOM
+    # constant log-conductivity c: exp(c) exactly, i.e. the plain model at k = e^c
+    from bayesianinferencedl_b200 import Fin
+    plain = Fin(space_m2)
+    assert relerr(fin.forward_qoi(np.full(orc.n, 0.3)), plain.forward_qoi(np.full(orc.n, np.exp(0.3)))) <= 1e-11
+    with pytest.raises(NotImplementedError):
+        fin.gradient(k[0], np.zeros(9))
+    with pytest.raises(RuntimeError):                                      # the C ABI refuses too
+        fin.handle.fom_nodal_gradient(k[:1], np.zeros(9))

@@ -138,3 +138,24 @@ def test_philox_known_answers():
     # one stream per row: a row depends only on (seed, global row, subsequence)
     assert np.array_equal(philox_normals(12345, 3, 501, first_row=7), z[7:10])
     assert not np.array_equal(philox_normals(12345, 3, 501, first_row=7, subsequence=1), z[7:10])
+
+
+def test_exp_quadrature_rule(oracle_m1):
+    """The 6-point degree-3 rule of the exp(k) restatement: exact for cubics, e^c for constants, close to the analytic
+    cell mean of exp(linear)."""
+    o = oracle_m1
+    A1 = o.matrix_nodal_exp(np.full(o.n, 0.7))
+    A2 = o.matrix_nodal(np.full(o.n, np.exp(0.7)))
+    assert abs(A1 - A2).max() <= 1e-13 * abs(A2).max()
+    a, b, c = 0.659027622374092, 0.231933368553031, 0.109039009072877
+    pts = np.array([[a, b, c], [a, c, b], [b, a, c], [b, c, a], [c, a, b], [c, b, a]])
+    assert np.allclose(pts.sum(1), 1.0, atol=1e-14)
+    # mean over the reference triangle of l1^p l2^q l3^r is 2 p! q! r! / (p+q+r+2)!
+    from math import factorial as f
+    for p_, q_, r_ in [(1, 0, 0), (2, 0, 0), (1, 1, 0), (3, 0, 0), (2, 1, 0), (1, 1, 1)]:
+        exact = 2.0 * f(p_) * f(q_) * f(r_) / f(p_ + q_ + r_ + 2)
+        assert abs((pts[:, 0] ** p_ * pts[:, 1] ** q_ * pts[:, 2] ** r_).mean() - exact) <= 1e-14
+    # smooth field: the exp model tends to the plain model at exp(k) under refinement of the data (here: small slope)
+    k = 0.05 * o.coords[:, 0]
+    w_exp, w_plain = o.forward_exp(k), o.forward(np.exp(k))
+    assert np.max(np.abs(w_exp - w_plain)) <= 1e-5 * np.max(np.abs(w_plain))
