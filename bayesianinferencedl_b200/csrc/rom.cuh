@@ -152,6 +152,76 @@ __device__ __forceinline__ void rom_fwd_subst(const double* __restrict__ A, cons
     }
 }
 
+// One panel (4 columns starting at j0) of the left-looking Cholesky of the augmented packed matrix, for a warp.  Lane l
+// holds rows j0 + l + 32 m (m < M live slabs) of the four panel columns in registers; one sweep over the finished
+// columns k < j0 updates the whole panel (M + 4 shared loads for 4 M FMAs), then the panel is factored in registers with
+// shuffles and written back once.
+template <int M>
+__device__ __forceinline__ void rom_chol_panel(double* __restrict__ A, double* __restrict__ dinv, int j0, int nr,
+                                               int lane, int& status) {
+    const int nrow = nr + 1, ncol = min(4, nr - j0);
+    double c[4][M];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const int oc = rom_col_off(j0 + cc, nr) - cc;  // + (i - j0) addresses row i of column j0+cc
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const int i = j0 + lane + 32 * m;
+            c[cc][m] = (cc < ncol && i < nrow && i >= j0 + cc) ? A[oc + lane + 32 * m] : 0.0;
+        }
+    }
+    // Sweep over the finished columns.  colp walks row (j0 + lane) of column k: consecutive columns of the packed layout
+    // are nr - k entries apart, so there is no per-k offset arithmetic.  Loads are NOT bounds-checked: a lane whose row
+    // lies past the matrix (or a panel column past ncol) reads at most 31 doubles beyond the column -- still inside
+    // this warp's region (dinv / w follow A) -- and only pollutes accumulators that are never stored or shuffled out.
+    {
+        const double* colp = A + j0 + lane;
+        int stride = nr;
+#pragma unroll 4
+        for (int k = 0; k < j0; ++k) {
+            double lk[M], lj[4];
+#pragma unroll
+            for (int m = 0; m < M; ++m) lk[m] = colp[32 * m];
+            const double* rowp = colp - lane;  // row j0 of column k (warp-uniform address: broadcast)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) lj[cc] = rowp[cc];
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) c[cc][m] = fma(-lk[m], lj[cc], c[cc][m]);
+            colp += stride;
+            --stride;
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        if (cc < ncol) {
+            // updates from the already finished columns of this panel
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) {
+                if (c2 < cc) {
+                    const double ljc = __shfl_sync(0xffffffffu, c[c2][0], cc);  // L[j0+cc][j0+c2]
+#pragma unroll
+                    for (int m = 0; m < M; ++m) c[cc][m] = fma(-c[c2][m], ljc, c[cc][m]);
+                }
+            }
+            const double d = __shfl_sync(0xffffffffu, c[cc][0], cc);
+            if (!(d > 0.0)) status = TFIN_STATUS_BREAKDOWN;
+            const double ljj = sqrt(d);
+            const double inv0 = rsqrt(d);
+            const double invl = inv0 * (2.0 - ljj * inv0);  // one Newton step on 1 / ljj
+            const int oc = rom_col_off(j0 + cc, nr) - cc;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int i = j0 + lane + 32 * m;
+                c[cc][m] = (i == j0 + cc) ? ljj : c[cc][m] * invl;
+                if (i < nrow && i >= j0 + cc) A[oc + lane + 32 * m] = c[cc][m];
+            }
+            if (lane == 0) dinv[j0 + cc] = invl;
+        }
+    }
+}
+
 template <int MAXM /* ceil((n_r+1)/32) */, bool ADJ = false>
 __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict__ C, long long s_begin,
                                                        long long s_end, int nr, int n_obs,
@@ -170,69 +240,27 @@ __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict_
     for (long long s = s_begin + (long long)blockIdx.x * wpb + warp; s < s_end;
          s += (long long)gridDim.x * wpb) {
         const double* src = C + (size_t)(s - s_begin) * Taug;
-        for (int e = lane; e < Taug; e += 32) A[e] = ldg_stream(src + e);
+        if ((Taug & 1) == 0) {  // rows of C are 16-byte aligned when Taug is even (per_warp is): 16-byte copies
+            const double2* src2 = reinterpret_cast<const double2*>(src);
+            double2* A2 = reinterpret_cast<double2*>(A);
+            for (int e = lane; e < (Taug >> 1); e += 32) {
+                double2 v;
+                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(src2 + e));
+                A2[e] = v;
+            }
+        } else {
+            for (int e = lane; e < Taug; e += 32) A[e] = ldg_stream(src + e);
+        }
         __syncwarp();
         int status = TFIN_STATUS_CONVERGED;
-        // Panel-blocked left-looking Cholesky, NB = 4 columns at a time.  Lane l holds rows j0 + l + 32 m of all four
-        // panel columns in registers; one pass over the previous columns k < j0 updates the whole panel (3 + 4 loads
-        // for 12 FMAs), then the panel is factored in registers with shuffles and written back once.
+        // Panel-blocked left-looking Cholesky, NB = 4 columns at a time; the panel body is instantiated for the number
+        // of 32-row slabs that still hold rows (warp-uniform), so empty slabs cost no issue slots at all.
         for (int j0 = 0; j0 < nr; j0 += 4) {
-            const int ncol = min(4, nr - j0);
-            double c[4][MAXM];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int oc = rom_col_off(j0 + cc, nr) - cc;  // + (i - j0) addresses row i of column j0+cc
-#pragma unroll
-                for (int m = 0; m < MAXM; ++m) {
-                    const int i = j0 + lane + 32 * m;
-                    c[cc][m] = (cc < ncol && i < nrow && i >= j0 + cc) ? A[oc + lane + 32 * m] : 0.0;
-                }
-            }
-            // number of 32-row slabs that still contain rows (warp-uniform): skips the empty slabs' loads and FMAs
             const int mact = min(MAXM, (nrow - j0 + 31) >> 5);
-#pragma unroll 4
-            for (int k = 0; k < j0; ++k) {
-                const int ok = rom_col_off(k, nr) + (j0 - k);  // row j0 of column k
-                double lk[MAXM], lj[4];
-#pragma unroll
-                for (int m = 0; m < MAXM; ++m)
-                    if (m < mact) lk[m] = (j0 + lane + 32 * m < nrow) ? A[ok + lane + 32 * m] : 0.0;
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) lj[cc] = A[ok + (cc < ncol ? cc : 0)];
-#pragma unroll
-                for (int m = 0; m < MAXM; ++m)
-                    if (m < mact) {
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) c[cc][m] = fma(-lk[m], lj[cc], c[cc][m]);
-                    }
-            }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                if (cc < ncol) {
-                    // updates from the already finished columns of this panel
-#pragma unroll
-                    for (int c2 = 0; c2 < 4; ++c2) {
-                        if (c2 < cc) {
-                            const double ljc = __shfl_sync(0xffffffffu, c[c2][0], cc);  // L[j0+cc][j0+c2]
-#pragma unroll
-                            for (int m = 0; m < MAXM; ++m) c[cc][m] = fma(-c[c2][m], ljc, c[cc][m]);
-                        }
-                    }
-                    const double d = __shfl_sync(0xffffffffu, c[cc][0], cc);
-                    if (!(d > 0.0)) status = TFIN_STATUS_BREAKDOWN;
-                    const double ljj = sqrt(d);
-                    const double inv0 = rsqrt(d);
-                    const double invl = inv0 * (2.0 - ljj * inv0);  // one Newton step on 1 / ljj
-                    const int oc = rom_col_off(j0 + cc, nr) - cc;
-#pragma unroll
-                    for (int m = 0; m < MAXM; ++m) {
-                        const int i = j0 + lane + 32 * m;
-                        c[cc][m] = (i == j0 + cc) ? ljj : c[cc][m] * invl;
-                        if (i < nrow && i >= j0 + cc) A[oc + lane + 32 * m] = c[cc][m];
-                    }
-                    if (lane == 0) dinv[j0 + cc] = invl;
-                }
-            }
+            if (MAXM >= 4 && mact == 4) rom_chol_panel<(MAXM >= 4 ? 4 : 1)>(A, dinv, j0, nr, lane, status);
+            else if (MAXM >= 3 && mact == 3) rom_chol_panel<(MAXM >= 3 ? 3 : 1)>(A, dinv, j0, nr, lane, status);
+            else if (MAXM >= 2 && mact == 2) rom_chol_panel<(MAXM >= 2 ? 2 : 1)>(A, dinv, j0, nr, lane, status);
+            else rom_chol_panel<1>(A, dinv, j0, nr, lane, status);
             __syncwarp();
         }
         // y = last row of the factor (the forward substitution rode along with the factorisation)

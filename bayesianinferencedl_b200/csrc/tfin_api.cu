@@ -887,7 +887,7 @@ static int rom_run(tfin_ctx* h, const RomSrc& src, int nr, int nobs, const doubl
     const int per_warp = ((Taug + 2 * nr + 2) + 1) & ~1;
     int wpb = std::min<int>(8, (int)((size_t)(h->max_smem_optin - 1024) / ((size_t)per_warp * 8)));
     if (wpb < 1) return fail(TFIN_E_STATE, "tfin_rom: n_r = %d does not fit shared memory", nr);
-    const size_t chol_smem = (size_t)wpb * per_warp * 8;
+    const size_t chol_smem = (size_t)wpb * per_warp * 8 + 256;  // + slack for the unchecked panel-sweep loads
     const int64_t chunk = h->rom_chunk > 0 ? h->rom_chunk : (int64_t)h->sm_count * wpb * 8;
     if (int e = h->d_romC.reserve((size_t)std::min<int64_t>(chunk, N) * Taug)) return e;
     size_t comb_smem = 0, gram_smem = 0;
