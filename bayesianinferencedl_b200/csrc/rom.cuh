@@ -19,74 +19,107 @@ namespace tfin {
 __host__ __device__ inline int rom_col_off(int j, int nr) { return j * (nr + 1) - (j * (j - 1)) / 2; }
 __host__ __device__ inline int rom_taug(int nr) { return nr * (nr + 1) / 2 + nr; }
 
-constexpr int ROM_BM = 64;    // samples per CTA tile
-constexpr int ROM_BN = 128;   // packed entries per CTA tile
+constexpr int ROM_BM = 64;    // samples per CTA
+constexpr int ROM_BN = 128;   // packed entries per tile of the sweep
 constexpr int ROM_MAXP2 = TFIN_MAX_TERMS * (TFIN_MAX_TERMS + 1) / 2;
 
+__host__ __device__ inline size_t rom_combine_smem(int n_terms) {
+    return (size_t)(n_terms * (n_terms + 1) / 2) * (ROM_BM + 2 * ROM_BN) * sizeof(double);
+}
+
 // ------------------------------------------------------------------------------------------- R1
-// C[s][t] = sum_pq coef[s][pq] * S[pq][t],  coef[s][(p,q)] = th_p th_q.  Register tile 4 samples x 8 entries.
-// Shared memory: coef [P2][BM] + S tile [P2][BN]  (P2 = 55: 28 KB + 56 KB -> 2 CTAs / SM).
-__global__ void __launch_bounds__(256) rom_combine_kernel(const double* __restrict__ theta,  // (N, n_terms-1)
-                                                          long long s_begin, long long s_end, int n_terms,
-                                                          const double* __restrict__ S,  // [P2][Taug]
-                                                          int Taug, double* __restrict__ C /* [Nchunk][Taug] */) {
+// C[s][t] = sum_pq coef[s][pq] * S[pq][t],  coef[s][(p,q)] = th_p th_q.  One CTA owns 64 samples and sweeps ALL entry
+// tiles (128 entries each): the coefficient tile is built once, the S tiles stream from L2 through a double buffer
+// filled by cp.async while the previous tile is being multiplied, and results are stored as they finish -- so the
+// FP64 pipe never waits for a tile prologue.  Register tile 4 samples x 8 entries: thread (ty, tx) owns samples
+// 4 ty .. 4 ty + 3 and the entry pairs 2 tx + 32 j (+0, +1): every shared load is a 16-byte access at unit stride
+// across the warp and a warp stores 256 contiguous bytes per row.
+// Shared memory (P2 = 55): coef [P2][64] 28 KB + 2 x S tile [P2][128] 112 KB.
+__global__ void __launch_bounds__(256, 1) rom_combine_kernel(const double* __restrict__ theta,  // (N, n_terms-1)
+                                                             long long s_begin, long long s_end, int n_terms,
+                                                             const double* __restrict__ S,  // [P2][ldS], ldS % 128 == 0
+                                                             int ldS, int Taug, double* __restrict__ C /* [Nchunk][Taug] */) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int P2 = n_terms * (n_terms + 1) / 2;
     double* s_coef = reinterpret_cast<double*>(smem);          // [P2][BM]
-    double* s_S = s_coef + (size_t)P2 * ROM_BM;                 // [P2][BN]
-    double* s_th = s_S + (size_t)P2 * ROM_BN;                   // [BM][n_terms]
+    double* s_S = s_coef + (size_t)P2 * ROM_BM;                 // [2][P2][BN]
     const int tid = threadIdx.x;
-    const long long s0 = s_begin + (long long)blockIdx.x * ROM_BM;
-    const int t0 = blockIdx.y * ROM_BN;
-
-    for (int e = tid; e < ROM_BM * n_terms; e += 256) {
-        const int sl = e / n_terms, t = e - sl * n_terms;
-        const long long s = s0 + sl;
-        s_th[e] = (t == 0) ? 1.0 : (s < s_end ? theta[s * (n_terms - 1) + t - 1] : 0.0);
-    }
-    for (int e = tid; e < P2 * ROM_BN; e += 256) {
-        const int pq = e / ROM_BN, tl = e - pq * ROM_BN;
-        s_S[e] = (t0 + tl < Taug) ? S[(size_t)pq * Taug + t0 + tl] : 0.0;
-    }
-    __syncthreads();
-    {
-        int pq = 0;
-        for (int p = 0; p < n_terms; ++p)
-            for (int q = p; q < n_terms; ++q, ++pq)
-                for (int sl = tid; sl < ROM_BM; sl += 256)
-                    s_coef[pq * ROM_BM + sl] = s_th[sl * n_terms + p] * s_th[sl * n_terms + q];
-    }
-    __syncthreads();
-
-    const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads: samples 4*ty..+3, entries tx + 16 j
-    double acc[4][8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-    for (int pq = 0; pq < P2; ++pq) {
-        const double4 a = *reinterpret_cast<const double4*>(&s_coef[pq * ROM_BM + 4 * ty]);
-        double b[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = s_S[pq * ROM_BN + tx + 16 * j];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            acc[0][j] = fma(a.x, b[j], acc[0][j]);
-            acc[1][j] = fma(a.y, b[j], acc[1][j]);
-            acc[2][j] = fma(a.z, b[j], acc[2][j]);
-            acc[3][j] = fma(a.w, b[j], acc[3][j]);
+    const int n_tiles = ldS / ROM_BN;
+    const bool even = (Taug & 1) == 0;  // rows of C are then 16-byte aligned
+    auto issue = [&](int tile) {
+        if (tile < n_tiles) {
+            double* dst = s_S + (size_t)(tile & 1) * P2 * ROM_BN;
+            const double* src = S + (size_t)tile * ROM_BN;
+            for (int e = tid; e < P2 * (ROM_BN / 2); e += 256) {
+                const int pq = e / (ROM_BN / 2), c2 = e - pq * (ROM_BN / 2);
+                cp_async16(dst + pq * ROM_BN + 2 * c2, src + (size_t)pq * ldS + 2 * c2);
+            }
         }
-    }
+        cp_async_commit();
+    };
+    for (long long s0 = s_begin + (long long)blockIdx.x * ROM_BM; s0 < s_end; s0 += (long long)gridDim.x * ROM_BM) {
+        __syncthreads();  // previous sample tile is done with both buffers and s_coef
+        issue(0);
+        for (int sl = tid; sl < ROM_BM; sl += 256) {  // th_p th_q of one sample, straight from global memory
+            const long long s = s0 + sl;
+            double th[TFIN_MAX_TERMS];
+            th[0] = s < s_end ? 1.0 : 0.0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long long s = s0 + 4 * ty + i;
-        if (s >= s_end) continue;
-        double* row = C + (size_t)(s - s_begin) * Taug;
+            for (int t = 1; t < TFIN_MAX_TERMS; ++t)
+                th[t] = (t < n_terms && s < s_end) ? theta[s * (n_terms - 1) + t - 1] : 0.0;
+            int pq = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int t = t0 + tx + 16 * j;
-            if (t < Taug) row[t] = acc[i][j];
+            for (int p = 0; p < TFIN_MAX_TERMS; ++p)
+#pragma unroll
+                for (int q = p; q < TFIN_MAX_TERMS; ++q)
+                    if (p < n_terms && q < n_terms) s_coef[(pq++) * ROM_BM + sl] = th[p] * th[q];
         }
+        const int ty = tid >> 4, tx = tid & 15;
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            cp_async_wait<0>();
+            __syncthreads();       // tile landed (and s_coef written); everyone finished the other buffer
+            issue(tile + 1);
+            const double* sS = s_S + (size_t)(tile & 1) * P2 * ROM_BN;
+            double acc[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+#pragma unroll 5
+            for (int pq = 0; pq < P2; ++pq) {
+                const double4 a4 = *reinterpret_cast<const double4*>(&s_coef[pq * ROM_BM + 4 * ty]);
+                const double a[4] = {a4.x, a4.y, a4.z, a4.w};
+                double b[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 v = *reinterpret_cast<const double2*>(&sS[pq * ROM_BN + 2 * tx + 32 * j]);
+                    b[2 * j] = v.x;
+                    b[2 * j + 1] = v.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+            const int t0 = tile * ROM_BN;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long s = s0 + 4 * ty + i;
+                if (s >= s_end) continue;
+                double* row = C + (size_t)(s - s_begin) * Taug;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = t0 + 2 * tx + 32 * j;
+                    if (even && t + 1 < Taug) {
+                        *reinterpret_cast<double2*>(row + t) = make_double2(acc[i][2 * j], acc[i][2 * j + 1]);
+                    } else {
+                        if (t < Taug) row[t] = acc[i][2 * j];
+                        if (t + 1 < Taug) row[t + 1] = acc[i][2 * j + 1];
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
     }
 }
 

@@ -524,12 +524,13 @@ extern "C" int tfin_set_rom(tfin_handle_t h, int32_t n_r, int32_t n_terms, int32
         return fail(TFIN_E_ARG, "tfin_set_rom: bad argument (n_r must be in [1,127])");
     if (n_terms < 1 || n_terms > TFIN_MAX_TERMS) return fail(TFIN_E_ARG, "tfin_set_rom: bad n_terms");
     const int P2 = n_terms * (n_terms + 1) / 2, T = n_r * (n_r + 1) / 2, Taug = rom_taug(n_r);
+    const int ldS = (Taug + ROM_BN - 1) / ROM_BN * ROM_BN;  // whole tiles of the combine sweep, zero padded
     // repack: row-major packed lower (i>=j -> i(i+1)/2+j)  ->  augmented column-major, G in the extra row
-    std::vector<double> Saug((size_t)P2 * Taug, 0.0);
+    std::vector<double> Saug((size_t)P2 * ldS, 0.0);
     int pq = 0;
     for (int p = 0; p < n_terms; ++p)
         for (int q = p; q < n_terms; ++q, ++pq) {
-            double* dst = Saug.data() + (size_t)pq * Taug;
+            double* dst = Saug.data() + (size_t)pq * ldS;
             const double* src = S + (size_t)pq * T;
             for (int j = 0; j < n_r; ++j) {
                 const int oj = rom_col_off(j, n_r);
@@ -893,7 +894,7 @@ static int rom_run(tfin_ctx* h, const RomSrc& src, int nr, int nobs, const doubl
     size_t comb_smem = 0, gram_smem = 0;
     int gram_threads = 0, gram_occ = 1;
     if (!src.nodal) {
-        comb_smem = ((size_t)P2 * (ROM_BM + ROM_BN) + (size_t)ROM_BM * nt) * 8;
+        comb_smem = rom_combine_smem(nt);
         TFIN_CUDA(cudaFuncSetAttribute(rom_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comb_smem));
     } else {
         const int TT = h->b_TT;
@@ -915,8 +916,9 @@ static int rom_run(tfin_ctx* h, const RomSrc& src, int nr, int nobs, const doubl
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
         const int64_t s1 = std::min<int64_t>(N, s0 + chunk);
         if (!src.nodal) {
-            dim3 g1((unsigned)((s1 - s0 + ROM_BM - 1) / ROM_BM), (unsigned)((Taug + ROM_BN - 1) / ROM_BN));
-            rom_combine_kernel<<<g1, 256, comb_smem, st>>>(src.d_in, s0, s1, nt, h->d_S.p, Taug, h->d_romC.p);
+            const int g1 = (int)std::min<int64_t>((s1 - s0 + ROM_BM - 1) / ROM_BM, (int64_t)h->sm_count);
+            const int ldS = (Taug + ROM_BN - 1) / ROM_BN * ROM_BN;
+            rom_combine_kernel<<<g1, 256, comb_smem, st>>>(src.d_in, s0, s1, nt, h->d_S.p, ldS, Taug, h->d_romC.p);
         } else {
             PcgOp op{};
             op.n = h->n; op.ld = h->ld; op.W = h->Wn; op.n_cells = h->n_cells; op.rhs = h->d_rhs.p;
