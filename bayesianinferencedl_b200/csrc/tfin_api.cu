@@ -10,6 +10,7 @@
 #include "pcg_variants.h"
 #include "project.cuh"
 #include "pcg_stream.cuh"
+#include "pcg_f32.cuh"
 #include "rom.cuh"
 #include "rom_nodal.cuh"
 #include "field.cuh"
@@ -111,6 +112,7 @@ struct tfin_ctx {
     int stream_prof = 0;
     int stream_pad_smem = 0;  // experiment knob: extra (unused) dynamic shared memory in KB
     int pcg_path = 0;     // 0 auto, 1 on-chip, 2 streaming
+    int precision = 64;   // 64, or 32: optional single-precision on-chip affine PCG (K1f)
     int stream_tile = 0;  // 0 auto, else 8 / 16 / 32
     int last_path = 0, last_tile = 0;
     // ---- observation / averaging
@@ -683,6 +685,68 @@ static int launch_pcg(tfin_ctx* h, bool nodal, const double* d_in, int in_stride
     return 0;
 }
 
+// Optional fp32 variant of the on-chip affine PCG (K1f, pcg_f32.cuh).
+static int launch_pcg_f32(tfin_ctx* h, const double* d_in, int in_stride, int64_t N, double tol, int maxit, double* d_w,
+                          double* d_qoi, int* d_iters, int* d_status, double* d_relres, cudaStream_t st) {
+    int cnt = 0;
+    const PcgF32Variant* tab = pcg_f32_variants(&cnt);
+    const PcgF32Variant* best = nullptr;
+    int bestT = 0, best_occ = 0;
+    size_t best_smem = 0;
+    double best_score = -1.0;
+    for (int i = 0; i < cnt; ++i) {
+        const PcgF32Variant* v = &tab[i];
+        if (v->WT < h->W) continue;
+        const int T = ((h->n + v->R - 1) / v->R + 31) & ~31;
+        if (T > v->maxT) continue;
+        const size_t sm = PcgF32Smem::make(v->WT, v->R * T).total;
+        if (sm > (size_t)h->max_smem_optin) continue;
+        if (cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, T, sm) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            continue;
+        }
+        const double score = (double)h->n / (v->R * T) * std::min(occ, 3) / v->WT;  // useful rows, residency, padding
+        if (score > best_score) {
+            best_score = score;
+            best = v;
+            bestT = T;
+            best_occ = occ;
+            best_smem = sm;
+        }
+    }
+    if (!best)
+        return fail(TFIN_E_STATE, "fp32 PCG: no compiled variant fits (n=%d, ell width=%d); use pcg_precision = 64", h->n, h->W);
+    const int grid = (int)std::min<int64_t>(N, (int64_t)h->sm_count * best_occ);
+    h->last_R = best->R;
+    h->last_T = bestT;
+    h->last_occ = best_occ;
+    h->last_smem = best_smem;
+    h->last_WT = best->WT;
+    h->last_WR = 0;
+    h->last_path = 3;
+    TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
+    CsrRows obs{h->n_obs, h->d_obs_ptr.p, h->d_obs_idx.p, h->d_obs_val.p};
+    PcgIO io{d_in, (long long)N, in_stride, tol * tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, h->d_counter.p};
+    PcgOp op{};
+    op.n = h->n;
+    op.ld = h->ld;
+    op.W = h->W;
+    op.n_terms = h->n_terms;
+    op.rhs = h->d_rhs.p;
+    op.col = h->d_col.p;
+    op.val = h->d_val.p;
+    op.diag = h->d_diag.p;
+    void* args[] = {&op, &obs, &io};
+    TFIN_CUDA(cudaLaunchKernel(best->func, dim3(grid), dim3(bestT), args, best_smem, st));
+    h->launches += 1;
+    return 0;
+}
+
 static int launch_pcg_stream(tfin_ctx* h, const double* d_in, int in_stride, int64_t N, double tol, int maxit,
                              double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres,
                              cudaStream_t st) {
@@ -840,8 +904,11 @@ static int fom_common(tfin_handle_t h, bool nodal_op, const double* in, int64_t 
     const bool use_stream = !nodal_op && (h->pcg_path == 2 || (h->pcg_path == 0 && !h->small_ok));
     if (!use_stream && !h->small_ok)
         return fail(TFIN_E_STATE, "on-chip PCG needs n <= 8191 (n = %d); use the streaming path", h->n);
+    const bool use_f32 = !use_stream && !nodal_op && h->precision == 32;
     int rc = use_stream
                  ? launch_pcg_stream(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st)
+             : use_f32
+                 ? launch_pcg_f32(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st)
                  : launch_pcg(h, nodal_op, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st);
     if (rc) return rc;
     if (int e = sg.out_copy(w_out, (size_t)N * h->n, d_w)) return e;
@@ -1420,6 +1487,7 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
     if (k == "rom_chunk") return h->rom_chunk;
     if (k == "pcg_path") return h->last_path;
     if (k == "nodal_coef_mode") return h->coef_mode;
+    if (k == "pcg_precision") return h->precision;
     if (k == "stream_tile") return h->last_tile;
     if (k == "stream_ell_width") return h->s_We;
     if (k == "stream_ld") return h->s_ldr;
@@ -1455,6 +1523,11 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
     }
     if (k == "pcg_path") {
         h->pcg_path = (int)value;
+        return 0;
+    }
+    if (k == "pcg_precision") {
+        if (value != 64 && value != 32) return fail(TFIN_E_ARG, "pcg_precision must be 64 or 32");
+        h->precision = (int)value;
         return 0;
     }
     if (k == "nodal_coef_mode") {
