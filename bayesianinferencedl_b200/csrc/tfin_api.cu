@@ -2,6 +2,7 @@
 // device workspaces, launch geometry, host<->device staging.  No CPU compute path exists here.
 #include <algorithm>
 #include <cmath>
+#include <climits>
 #include <cstring>
 #include <map>
 
@@ -82,6 +83,46 @@ static std::vector<int> rcm_order(int n, const int32_t* rp, const int32_t* ci) {
     }
     std::reverse(order.begin(), order.end());
     return order;
+}
+
+// Slot assignment of the on-chip ELL.  A warp owns 32 CONSECUTIVE rows and gathers slot w of all of them with one
+// shared-memory load, which is conflict-free when the 32 columns are consecutive too, i.e. when slot w means the same
+// relative offset (col - row) for the whole warp.  CSR order breaks that at every row with a missing neighbour
+// (boundaries, junctions): ncu showed 24-41 wavefronts instead of 20 on the gather loads.  So a row inherits, offset
+// by offset, the slots of the previous row; entries with a new offset take the free slots.  keep[i] comes in as CSR
+// positions of the kept off-diagonals and leaves as a slot-aligned list (-1 = padding).
+static void align_ell_slots(int n, int W, const int32_t* col_idx, std::vector<std::vector<int>>& keep) {
+    const int NONE = INT32_MIN;
+    std::vector<int> prev_off(W, NONE), cur_off(W), slot(W);
+    for (int i = 0; i < n; ++i) {
+        std::fill(slot.begin(), slot.end(), -1);
+        std::fill(cur_off.begin(), cur_off.end(), NONE);
+        std::vector<int> rest;
+        for (int j : keep[i]) {
+            const int off = col_idx[j] - i;
+            int w = 0;
+            while (w < W && !(prev_off[w] == off && slot[w] < 0)) ++w;
+            if (w < W) {
+                slot[w] = j;
+                cur_off[w] = off;
+            } else {
+                rest.push_back(j);
+            }
+        }
+        for (int j : rest) {  // new offsets: prefer a slot the previous row left empty, else any free one
+            int w = 0;
+            while (w < W && !(slot[w] < 0 && prev_off[w] == NONE)) ++w;
+            if (w == W) {
+                w = 0;
+                while (slot[w] >= 0) ++w;
+            }
+            slot[w] = j;
+            cur_off[w] = col_idx[j] - i;
+        }
+        keep[i].assign(slot.begin(), slot.end());
+        for (int w = 0; w < W; ++w)
+            if (cur_off[w] != NONE) prev_off[w] = cur_off[w];  // a gap keeps the offset of the last row that had one
+    }
 }
 
 struct tfin_ctx {
@@ -262,6 +303,7 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
         W = std::max(W, (int)keep[i].size());
     }
     if (W == 0) W = 1;
+    align_ell_slots(n, W, col_idx, keep);
     std::vector<uint16_t> col((size_t)W * ld);
     std::vector<double> val((size_t)n_terms * W * ld, 0.0), diag((size_t)n_terms * ld, 0.0), b(ld, 0.0);
     for (int w = 0; w < W; ++w)
@@ -269,12 +311,15 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
     for (int i = 0; i < n; ++i) {
         b[i] = rhs[i];
         for (int t = 0; t < n_terms; ++t) diag[(size_t)t * ld + i] = vals[(size_t)t * nnz + diag_pos[i]];
-        for (int w = 0; w < (int)keep[i].size(); ++w) {
+        for (int w = 0; w < W; ++w) {
             const int j = keep[i][w];
+            if (j < 0) {  // padding: own row, value 0
+                col[(size_t)w * ld + i] = (uint16_t)i;
+                continue;
+            }
             col[(size_t)w * ld + i] = (uint16_t)col_idx[j];
             for (int t = 0; t < n_terms; ++t) val[((size_t)t * W + w) * ld + i] = vals[(size_t)t * nnz + j];
         }
-        for (int w = (int)keep[i].size(); w < W; ++w) col[(size_t)w * ld + i] = (uint16_t)i;
     }
     h->n = n;
     h->ld = ld;
@@ -474,6 +519,7 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
         W = std::max(W, (int)keep[i].size());
     }
     if (W == 0) W = 1;
+    align_ell_slots(n, W, ci.data(), keep);
     const size_t plane = (size_t)W * ld;
     std::vector<uint16_t> col(plane);
     std::vector<int> cell(2 * plane, n_cells), dptr(ld + 1, 0), dcell, cl(cells, cells + 3 * (size_t)n_cells);
@@ -481,9 +527,13 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
     for (int w = 0; w < W; ++w)
         for (int i = 0; i < ld; ++i) col[(size_t)w * ld + i] = (uint16_t)std::min(i, n - 1);
     for (int i = 0; i < n; ++i) {
-        for (int w = 0; w < (int)keep[i].size(); ++w) {
+        for (int w = 0; w < W; ++w) {
             const int j = keep[i][w];
             const size_t o = (size_t)w * ld + i;
+            if (j < 0) {  // padding: own row, no cells, constant 0
+                col[o] = (uint16_t)i;
+                continue;
+            }
             col[o] = (uint16_t)ci[j];
             cst[o] = h->h_const[j];
             for (size_t c = 0; c < contrib[j].size(); ++c) {
@@ -491,7 +541,6 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
                 coef[c * plane + o] = contrib[j][c].second;
             }
         }
-        for (int w = (int)keep[i].size(); w < W; ++w) col[(size_t)w * ld + i] = (uint16_t)i;
         dptr[i] = (int)dcell.size();
         dcst[i] = h->h_const[diag_pos[i]];
         for (auto& pc : contrib[diag_pos[i]]) {
