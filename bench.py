@@ -366,8 +366,15 @@ def run_b200(args):
             hn.fom_nodal_raw(k_host.data_ptr(), NN, _cabi.MEM_HOST, TOL, 20000, qoi=q_n_host.data_ptr(),
                              status=st_n_host.data_ptr(), stream=sp)
 
+        def nodal_pipeline():   # fields drawn ON the device (tfin_field_sample), only the observables cross PCIe
+            draw()
+            hn.fom_nodal_raw(k_dev.data_ptr(), NN, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_n.data_ptr(),
+                             status=st_n.data_ptr(), stream=sp)
+            q_n_host.copy_(q_n, non_blocking=True)
+
         ms_n, ln = timed(nodal_dev, K, Wm, hn)
         ms_ne, _ = timed(nodal_e2e, K, Wm, hn)
+        ms_np, lnp = timed(nodal_pipeline, K, Wm, hn)
         it_sum_n = int(it_n.to(torch.int64).sum().item())
         n_cells = fin.ops.n_cells
         step_n = ms_n / K - flush_ms
@@ -380,6 +387,12 @@ def run_b200(args):
                     "h2d_bytes_per_step": NN * n * 8, "d2h_bytes_per_step": NN * (n_obs * 8 + 4),
                     "ms_per_step": ms_ne / K - flush_ms},
             "gpu_launches": ln,
+            "e2e_device_prior": {"value": world * NN / ((ms_np / K - flush_ms) * 1e-3), "unit": "solves/s",
+                                 "h2d_bytes_per_step": 0, "d2h_bytes_per_step": NN * n_obs * 8,
+                                 "ms_per_step": ms_np / K - flush_ms, "gpu_launches": lnp,
+                                 "what": "prior draw (Philox + triangular GEMM + exp) -> nodal FOM -> observables to "
+                                         "pinned host memory; the generate_fin_dataset.py:83-100 loop without its "
+                                         "per-sample H2D"},
             "field_sampler": {"value": NN / (sampler_ms * 1e-3), "unit": "fields/s/GPU", "ms": sampler_ms,
                               "what": "tfin_field_sample: Philox normals + fp64 triangular GEMM + exp, device resident",
                               "tflops_fp64": NN * float(n) * n / (sampler_ms * 1e-3) / 1e12},

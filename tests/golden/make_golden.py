@@ -57,6 +57,23 @@ def oracle_m1():
         "phi": phi, "qoi_rom": np.stack([o.qoi_reduced(o.forward_nine_param_reduced(t, phi), phi) for t in theta]),
         "nine_to_fn": o.nine_param_to_function(theta[0]),
     }
+    # rows added for the 'next' components (gradients, nodal LSPG, exp(k), prior, Philox, pCN)
+    from oracle.thermal_fin_oracle import pcn_chains, philox_normals
+    data = rng.uniform(0.05, 0.6, 9)
+    gr = [o.grad_reduced(k, data, phi) for k in knod]
+    rf = [o.r_fwd_no_full(k, phi) for k in knod]
+    logk = 0.5 * rng.standard_normal((3, o.n))
+    pcn = pcn_chains(lambda kk: o.qoi_operator(o.forward(kk)), chol, out["qoi_nodal"][0], 0.05, 11, 4, 6, 0.2, first_chain=3)
+    out.update({
+        "data": data, "grad_fom": np.stack([o.gradient(k, data) for k in knod]),
+        "sens_fom0": o.sensitivity(knod[0]),
+        "grad_rom": np.stack([g[0] for g in gr]), "cost_rom": np.array([g[1] for g in gr]),
+        "gtheta_rom": np.stack([g[2] for g in gr]),
+        "lspg_Ar0": rf[0][0], "lspg_Br": np.stack([r[1] for r in rf]), "lspg_y": np.array([r[4] for r in rf]),
+        "logk": logk, "qoi_exp": np.stack([o.qoi_operator(o.forward_exp(k)) for k in logk]),
+        "chol_m52": chol, "philox_z": philox_normals(2026, 5, o.n, first_row=3, subsequence=2),
+        "pcn_accepted": pcn["accepted"], "pcn_z": pcn["z"], "pcn_qoi_sum": pcn["qoi_sum"], "pcn_misfit": pcn["misfit"],
+    })
     np.savez_compressed(os.path.join(OUT, "oracle_m1.npz"), **out)
 
 

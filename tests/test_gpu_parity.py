@@ -529,3 +529,44 @@ def test_optional_fp32_path(space_m3, oracle_m3, pod_m3, rom_m3):
     loose = AffineROMFin(space_m3, None, pod_m3, tol=1e-9)
     ql, sl = loose.forward_nine_param_qoi(theta, return_stats=True)
     assert relerr(ql, q64) <= 1e-5 and np.all(sl["status"] == 0)
+
+
+def test_against_committed_golden(space_m1):
+    """CUDA path vs the COMMITTED fixture tests/golden/oracle_m1.npz (no oracle code runs here): forward maps, ROM,
+    gradients, nodal LSPG, exp(k), device prior, Philox streams and the pCN driver on the m = 1 mesh."""
+    import os
+    from bayesianinferencedl_b200 import AffineROMFin, Fin
+    from bayesianinferencedl_b200.assembly import five_to_nine
+    from bayesianinferencedl_b200.bayesian_inference.gaussian_field import FieldSampler
+    from bayesianinferencedl_b200.bayesian_inference.likelihood import PCNChains
+    from bayesianinferencedl_b200.fom.forward_solve_exp import Fin as FinExp
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_m1.npz"))
+    phi, k, data = g["phi"], g["k_nodal"], g["data"]
+    rom = AffineROMFin(space_m1, None, phi)
+    fin = Fin(space_m1)
+    assert relerr(rom.forward_nine_param_qoi(g["theta"]), g["qoi_affine"]) <= RTOL_FOM
+    assert np.max(np.abs(rom.forward_nine_param(g["theta"][0]) - g["w_affine0"])) <= 1e-10 * np.max(np.abs(g["w_affine0"]))
+    assert relerr(rom.forward_nine_param_qoi(five_to_nine(g["k5"])), g["qoi_five"]) <= RTOL_FOM
+    assert relerr(fin.forward_qoi(k), g["qoi_nodal"]) <= RTOL_FOM
+    assert relerr(fin.subfin_avg_op(k), g["theta_of_k"]) <= 1e-12
+    assert relerr(rom.forward_reduced_qoi(g["theta"]), g["qoi_rom"]) <= 1e-8
+    assert np.array_equal(np.asarray(fin.nine_param_to_function(g["theta"][0])), g["nine_to_fn"])
+    gf = fin.gradient(k, data)
+    assert np.max(np.abs(gf - g["grad_fom"])) <= 1e-9 * np.max(np.abs(g["grad_fom"]))
+    assert np.max(np.abs(fin.sensitivity(k[0]) - g["sens_fom0"])) <= 1e-9 * np.max(np.abs(g["sens_fom0"]))
+    rom.set_data(data)
+    dJ, J = rom.grad_reduced(k)
+    assert np.max(np.abs(dJ - g["grad_rom"])) <= 1e-8 * np.max(np.abs(g["grad_rom"])) and relerr(J, g["cost_rom"]) <= 1e-9
+    g9, _ = rom.grad_reduced_nine_param(fin.subfin_avg_op(k))
+    assert np.max(np.abs(g9 - g["gtheta_rom"])) <= 1e-8 * np.max(np.abs(g["gtheta_rom"]))
+    A_r, B_r, C_r, x_r, y_r = fin.r_fwd_no_full(k, phi)
+    assert np.max(np.abs(A_r[0] - g["lspg_Ar0"])) <= 1e-12 * np.max(np.abs(g["lspg_Ar0"]))
+    assert np.max(np.abs(B_r - g["lspg_Br"])) <= 1e-12 * np.max(np.abs(g["lspg_Br"])) and relerr(y_r, g["lspg_y"]) <= 1e-9
+    assert relerr(FinExp(space_m1).forward_qoi(g["logk"]), g["qoi_exp"]) <= RTOL_FOM
+    prior = FieldSampler(space_m1, "m52", 1.6)
+    assert np.max(np.abs(prior.chol - g["chol_m52"])) <= 1e-7
+    _, z = prior.sample(N=5, seed=2026, subsequence=2, first_row=3, return_z=True)
+    assert np.max(np.abs(z - g["philox_z"])) <= 1e-13
+    out = PCNChains(fin, g["chol_m52"], g["qoi_nodal"][0], 0.05, seed=11).run(6, n_chains=4, beta=0.2, first_chain=3)
+    assert np.array_equal(out["accepted"], g["pcn_accepted"]) and np.max(np.abs(out["z"] - g["pcn_z"])) <= 1e-11
+    assert relerr(out["qoi_sum"], g["pcn_qoi_sum"]) <= 1e-9

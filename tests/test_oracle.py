@@ -159,3 +159,23 @@ def test_exp_quadrature_rule(oracle_m1):
     k = 0.05 * o.coords[:, 0]
     w_exp, w_plain = o.forward_exp(k), o.forward(np.exp(k))
     assert np.max(np.abs(w_exp - w_plain)) <= 1e-5 * np.max(np.abs(w_plain))
+
+
+def test_oracle_golden_regression_next_rows(gold, oracle_m1):
+    """Regression pins of the oracle restatements added after the forward map (gradients, nodal LSPG, exp(k), pCN)."""
+    from oracle.thermal_fin_oracle import make_cov_chol, pcn_chains, philox_normals
+    o = oracle_m1
+    k, phi, data = gold["k_nodal"], gold["phi"], gold["data"]
+    assert np.allclose(o.gradient(k[1], data), gold["grad_fom"][1], rtol=1e-9, atol=1e-16)
+    assert np.allclose(o.sensitivity(k[0]), gold["sens_fom0"], rtol=1e-9, atol=1e-16)
+    dJ, J, g = o.grad_reduced(k[2], data, phi)
+    assert np.allclose(g, gold["gtheta_rom"][2], rtol=1e-8, atol=1e-16) and abs(J - gold["cost_rom"][2]) <= 1e-10 * J
+    A_r, B_r, C_r, x_r, y_r = o.r_fwd_no_full(k[0], phi)
+    assert np.allclose(A_r, gold["lspg_Ar0"], rtol=1e-11, atol=1e-14) and abs(y_r - gold["lspg_y"][0]) <= 1e-9 * abs(y_r)
+    assert relerr(o.qoi_operator(o.forward_exp(gold["logk"][1])), gold["qoi_exp"][1]) < 1e-12
+    assert np.array_equal(philox_normals(2026, 5, o.n, first_row=3, subsequence=2), gold["philox_z"])
+    chol = make_cov_chol(o.coords, "m52", 1.6)
+    assert np.max(np.abs(chol - gold["chol_m52"])) <= 1e-9
+    pcn = pcn_chains(lambda kk: o.qoi_operator(o.forward(kk)), gold["chol_m52"], gold["qoi_nodal"][0], 0.05, 11, 4, 6, 0.2,
+                     first_chain=3)
+    assert np.array_equal(pcn["accepted"], gold["pcn_accepted"]) and np.allclose(pcn["z"], gold["pcn_z"], atol=1e-12)
