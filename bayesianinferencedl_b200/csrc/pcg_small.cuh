@@ -63,6 +63,20 @@ __device__ __forceinline__ double cell_coefficient(int mode, double ka, double k
     return s * (1.0 / 6.0);
 }
 
+// Weight (1/|e|) int_e lambda_a exp(k) dx of vertex a (values ka; the other two vertices kb, kc) in the gradient form
+// assemble(k_hat * exp(k) * inner(grad z, grad v) * dx) of fom/forward_solve_exp.py:299, 328: the integrand has estimated
+// degree 1 + 3, for which FIAT's triangle scheme is the 6-point degree-4 Strang-Fix rule (two orbits of three points).
+// For the plain parametrisation the weight is 1/3.
+__device__ __forceinline__ double vertex_weight_exp(double ka, double kb, double kc) {
+    const double a1 = 0.816847572980459, b1 = 0.091576213509771, w1 = 0.109951743655322;
+    const double a2 = 0.108103018168070, b2 = 0.445948490915965, w2 = 0.223381589678011;
+    double s = w1 * a1 * exp(fma(a1, ka, b1 * (kb + kc)));
+    s = fma(w1 * b1, exp(fma(a1, kb, b1 * (ka + kc))) + exp(fma(a1, kc, b1 * (ka + kb))), s);
+    s = fma(w2 * a2, exp(fma(a2, ka, b2 * (kb + kc))), s);
+    s = fma(w2 * b2, exp(fma(a2, kb, b2 * (ka + kc))) + exp(fma(a2, kc, b2 * (ka + kb))), s);
+    return s;
+}
+
 struct CsrRows {
     int rows;
     const int* ptr;
@@ -462,14 +476,15 @@ __global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, 
                     s_r[i] = v[k] * s_dsi[i];  // adjoint state
                 }
                 __syncthreads();
-                for (int e = tid; e < nc; e += T) {  // (1/3) w_e^T K_e v_e per cell
+                const bool expm = op.coef_mode == 1;
+                for (int e = tid; e < nc; e += T) {  // (1/3) w_e^T K_e v_e per cell (exp(k): vertex weights below)
                     const int ca = op.cells[3 * e], cb = op.cells[3 * e + 1], cc = op.cells[3 * e + 2];
                     const double* K = adj.Ke + 9 * (size_t)e;
                     const double va = s_r[ca], vb = s_r[cb], vc = s_r[cc];
                     const double t0 = fma(K[0], va, fma(K[1], vb, K[2] * vc));
                     const double t1 = fma(K[3], va, fma(K[4], vb, K[5] * vc));
                     const double t2 = fma(K[6], va, fma(K[7], vb, K[8] * vc));
-                    s_kbar[e] = fma(s_w[ca], t0, fma(s_w[cb], t1, s_w[cc] * t2)) * (1.0 / 3.0);
+                    s_kbar[e] = fma(s_w[ca], t0, fma(s_w[cb], t1, s_w[cc] * t2)) * (expm ? 1.0 : 1.0 / 3.0);
                 }
                 __syncthreads();
                 double* g = adj.grad_out + (sample * n_adj + a) * (long long)n;
@@ -478,7 +493,17 @@ __global__ void __launch_bounds__(MAXT, MINB) pcg_kernel(PcgOp op, CsrRows obs, 
                     const int i = tid + k * T;
                     if (i < n) {
                         double acc = 0.0;
-                        for (int j = op.dptr[i]; j < op.dptr[i + 1]; ++j) acc += s_kbar[op.dcell[j]];
+                        if (!expm) {
+                            for (int j = op.dptr[i]; j < op.dptr[i + 1]; ++j) acc += s_kbar[op.dcell[j]];
+                        } else {  // k_hat-weighted quadrature of exp(k): the field is re-read from global memory
+                            const double* krow = io.in + sample * (long long)io.in_stride;
+                            for (int j = op.dptr[i]; j < op.dptr[i + 1]; ++j) {
+                                const int e = op.dcell[j];
+                                const int c0 = op.cells[3 * e], c1 = op.cells[3 * e + 1], c2 = op.cells[3 * e + 2];
+                                const int ob = c0 == i ? c1 : c0, oc = c2 == i ? c1 : c2;  // the two other vertices
+                                acc = fma(s_kbar[e], vertex_weight_exp(krow[i], krow[ob], krow[oc]), acc);
+                            }
+                        }
                         g[i] = acc;
                     }
                 }

@@ -1229,7 +1229,6 @@ static int fom_adjoint(tfin_handle_t h, int mode, const double* k, int64_t N, in
                        const double* data, int64_t data_rows, double* grad_out, double* cost_out, double* qoi_out,
                        int32_t* iters_out, int32_t* status_out, void* stream) {
     if (h->n_cells <= 0) return fail(TFIN_E_STATE, "adjoint solve: call tfin_set_cells first");
-    if (h->coef_mode != 0) return fail(TFIN_E_STATE, "adjoint solve: not available for the exp(k) parametrisation");
     if (h->n_obs <= 0 || h->n_obs > 64) return fail(TFIN_E_STATE, "adjoint solve: needs an observation operator with <= 64 rows");
     if (N < 0 || (N > 0 && (!k || !grad_out))) return fail(TFIN_E_ARG, "adjoint solve: bad batch argument");
     if (!(tol > 0.0) || maxit < 1) return fail(TFIN_E_ARG, "adjoint solve: tol must be > 0 and maxit >= 1");

@@ -249,7 +249,8 @@ int64_t tfin_get_int(tfin_handle_t h, const char* key);
 /* Knobs (before the next solve call): "pcg_rows_per_thread" (0 = auto), "rom_chunk", "pcg_path", "stream_tile" ...;
  * "nodal_coef_mode": 0 = conductivity k (fom/forward_solve.py:160), 1 = conductivity exp(k) integrated with the
  * degree-3 rule of dolfin's form compiler (fom/forward_solve_exp.py:160) in tfin_fom_nodal / tfin_rom_nodal /
- * tfin_pcn_chains(model 0); the adjoint entry points refuse mode 1;
+ * tfin_pcn_chains(model 0), and the gradient form k_hat exp(k) grad z . grad v with its degree-4 rule (:299, :328) in
+ * tfin_fom_nodal_gradient / _sensitivity;
  * "pcg_precision": 64 (default) or 32 = opt-in single-precision on-chip PCG for tfin_fom_affine, n <= 2048 (operator
  * formed in fp64 and rounded, fp32 CG vectors, fp64 dot products / solution / observables).  Measured error floor of
  * the observables 3.6e-5 relative, 1.4x faster per iteration; for 1e-5 use the fp64 kernel with tol = 1e-9. */

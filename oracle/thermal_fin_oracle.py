@@ -188,6 +188,38 @@ class FinOracle:
         """``Fin.forward`` of forward_solve_exp.py:252-275."""
         return spla.splu(self.matrix_nodal_exp(k)).solve(self.B)
 
+    def grad_form_exp(self, k, z, v):
+        """assemble(k_hat * exp(k) * inner(grad z, grad v) * dx) (forward_solve_exp.py:299, 328).  Estimated degree
+        1 + 3 = 4 -> FIAT's degree-4 triangle scheme: 6-point Strang-Fix rule, orbits (0.8168..., 0.0915..., 0.0915...)
+        with weight 0.10995... and (0.1081..., 0.4459..., 0.4459...) with weight 0.22338... (normalised to area 1)."""
+        a1, b1, w1 = 0.816847572980459, 0.091576213509771, 0.109951743655322
+        a2, b2, w2 = 0.108103018168070, 0.445948490915965, 0.223381589678011
+        pts = np.array([[a1, b1, b1], [b1, a1, b1], [b1, b1, a1], [a2, b2, b2], [b2, a2, b2], [b2, b2, a2]])
+        wts = np.array([w1, w1, w1, w2, w2, w2])
+        kv = np.asarray(k, dtype=np.float64)[self.cells]                      # (n_cells, 3)
+        ek = np.exp(kv @ pts.T)                                                # exp(k) at the 6 points
+        vert_w = (ek * wts) @ pts                                              # (n_cells, 3): int lambda_a exp(k) / |e|
+        ge = np.einsum("ea,eab,eb->e", z[self.cells], self.Ke, v[self.cells])  # |e| grad z . grad v
+        out = np.zeros(self.n)
+        for a in range(3):
+            np.add.at(out, self.cells[:, a], ge * vert_w[:, a])
+        return out
+
+    def gradient_exp(self, k, data):
+        """``Fin.gradient`` of forward_solve_exp.py:277-310."""
+        A = self.matrix_nodal_exp(k)
+        lu = spla.splu(A)
+        z = lu.solve(self.B)
+        adj_rhs = -np.dot((self.B_obs @ z - data).T, self.B_obs)
+        return self.grad_form_exp(k, z, lu.solve(adj_rhs))
+
+    def sensitivity_exp(self, k):
+        """``Fin.sensitivity`` of forward_solve_exp.py:312-342."""
+        lu = spla.splu(self.matrix_nodal_exp(k))
+        z = lu.solve(self.B)
+        V = lu.solve(np.ascontiguousarray(-self.B_obs.T))
+        return np.stack([self.grad_form_exp(k, z, V[:, o]) for o in range(self.B_obs.shape[0])])
+
     def forward(self, k):
         """``Fin.forward(k)`` (forward_solve.py:270-291): dolfin ``solve`` = sparse direct LU."""
         return spla.splu(self.matrix_nodal(k)).solve(self.B)

@@ -223,3 +223,19 @@ def test_unstructured_nonconforming_mesh_assembly():
     assert np.allclose(ops.rhs, o.B) and np.allclose(ops.B_obs, o.B_obs, atol=1e-15)
     # marker-0 cells carry no conductivity in the affine model but do in the nodal model
     assert np.abs(ops.k_unmarked).max() > 0
+
+
+def test_enrich_matches_reference_recipe():
+    """model_constr_adaptive_sampling.py:52-68: Gram-Schmidt against columns 0..k-2 (the reference's loop bound)."""
+    from bayesianinferencedl_b200.rom.model_constr_adaptive_sampling import enrich
+    rng = np.random.default_rng(6)
+    basis = np.linalg.qr(rng.standard_normal((30, 4)))[0]
+    w = rng.standard_normal((30, 1))
+    U = enrich(basis, w)
+    assert U.shape == (30, 5) and np.array_equal(U[:, :4], basis)
+    assert abs(np.linalg.norm(U[:, 4]) - 1.0) < 1e-14
+    assert np.allclose(U[:, :3].T @ U[:, 4], 0.0, atol=1e-14)          # orthogonal to all but the last column
+    ref = w[:, 0].copy()                                                  # literal restatement
+    for j in range(0, 4 - 1):
+        ref = ref - (ref @ basis[:, j]) / (basis[:, j] @ basis[:, j]) * basis[:, j]
+    assert np.allclose(U[:, 4], ref / np.sqrt(ref @ ref), atol=1e-15)

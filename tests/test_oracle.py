@@ -179,3 +179,29 @@ def test_oracle_golden_regression_next_rows(gold, oracle_m1):
     pcn = pcn_chains(lambda kk: o.qoi_operator(o.forward(kk)), gold["chol_m52"], gold["qoi_nodal"][0], 0.05, 11, 4, 6, 0.2,
                      first_chain=3)
     assert np.array_equal(pcn["accepted"], gold["pcn_accepted"]) and np.allclose(pcn["z"], gold["pcn_z"], atol=1e-12)
+
+
+def test_exp_gradient_rule(oracle_m1):
+    """Degree-4 Strang-Fix rule of the exp(k) gradient form: exact for quartics; the adjoint gradient is consistent with
+    finite differences up to the quadrature mismatch; for constant k it reduces to e^c times the plain gradient."""
+    from math import factorial as f
+    o = oracle_m1
+    a1, b1, w1 = 0.816847572980459, 0.091576213509771, 0.109951743655322
+    a2, b2, w2 = 0.108103018168070, 0.445948490915965, 0.223381589678011
+    pts = np.array([[a1, b1, b1], [b1, a1, b1], [b1, b1, a1], [a2, b2, b2], [b2, a2, b2], [b2, b2, a2]])
+    wts = np.array([w1, w1, w1, w2, w2, w2])
+    assert abs(wts.sum() - 1.0) < 1e-14
+    for p_, q_, r_ in [(1, 0, 0), (2, 1, 0), (4, 0, 0), (2, 2, 0), (2, 1, 1), (3, 1, 0)]:
+        exact = 2.0 * f(p_) * f(q_) * f(r_) / f(p_ + q_ + r_ + 2)
+        assert abs(np.sum(wts * pts[:, 0] ** p_ * pts[:, 1] ** q_ * pts[:, 2] ** r_) - exact) <= 1e-14
+    rng = np.random.default_rng(12)
+    data = rng.uniform(0.1, 0.5, 9)
+    c = 0.4
+    g_exp = o.gradient_exp(np.full(o.n, c), data)
+    g_plain = o.gradient(np.full(o.n, np.exp(c)), data)
+    assert np.allclose(g_exp, np.exp(c) * g_plain, rtol=1e-10, atol=1e-16)
+    k = 0.3 * rng.standard_normal(o.n)
+    d = rng.standard_normal(o.n)
+    cost = lambda kk: 0.5 * np.sum((o.qoi_operator(o.forward_exp(kk)) - data) ** 2)
+    fd = (cost(k + 1e-6 * d) - cost(k - 1e-6 * d)) / 2e-6
+    assert abs(fd - o.gradient_exp(k, data) @ d) <= 5e-2 * abs(fd)
