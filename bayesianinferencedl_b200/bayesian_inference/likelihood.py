@@ -113,11 +113,11 @@ class PCNChains:
         return out
 
     @staticmethod
-    def summarize(out, group=None):
+    def summarize(out, group=None, device=None):
         """Posterior summaries over chains and steps: mean / std of the observables and the acceptance rate, reduced
         over all ranks of ``group`` when torch.distributed is initialised (dist.chain_moments)."""
         from ..dist import chain_moments
         count = out["qoi_sum"].shape[0] * out["n_steps"]
-        cnt, mean, var = chain_moments(count, out["qoi_sum"].sum(0), out["qoi_sq"].sum(0), group=group)
+        cnt, mean, var = chain_moments(count, out["qoi_sum"].sum(0), out["qoi_sq"].sum(0), group=group, device=device)
         acc = out["accepted"].sum() / max(count, 1)
         return {"count": cnt, "qoi_mean": mean, "qoi_std": np.sqrt(np.maximum(var, 0.0)), "accept_rate": float(acc)}

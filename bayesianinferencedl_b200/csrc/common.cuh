@@ -41,6 +41,23 @@ inline int fail(int code, const char* fmt, ...) {
                                 cudaGetErrorString(_e), __FILE__, __LINE__);                   \
     } while (0)
 
+// Every entry point runs on the handle's device and RESTORES the caller's current device on return: libtfin lives in
+// processes that also run torch / NCCL, which read the thread's current device (a rank that left device 0 current
+// after touching a handle there would put its next collective's tensors on the wrong GPU).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // ---------------------------------------------------------------- device buffer (RAII-free, explicit)
 template <typename T>
 struct DevBuf {

@@ -211,7 +211,7 @@ extern "C" int tfin_create(int device, tfin_handle_t* out) {
         return fail(TFIN_E_CUDA, "tfin_create: no CUDA device (%s); libtfin has no CPU fallback",
                     cudaGetErrorString(e));
     if (device < 0 || device >= count) return fail(TFIN_E_ARG, "tfin_create: device %d out of range", device);
-    TFIN_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     cudaDeviceProp prop;
     TFIN_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -229,7 +229,7 @@ extern "C" int tfin_create(int device, tfin_handle_t* out) {
 
 extern "C" int tfin_destroy(tfin_handle_t h) {
     if (!h) return 0;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     for (auto* b : {&h->d_val, &h->d_diag, &h->d_rhs, &h->d_obs_val, &h->d_avg_val, &h->d_ncoef, &h->d_ncst,
                     &h->d_dcoef, &h->d_dcst, &h->d_S, &h->d_obs_phi, &h->d_romC, &h->d_in, &h->d_theta, &h->d_w,
@@ -266,9 +266,9 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
     return 0;
 }
 
-#define CHECK_HANDLE(h)                                        \
+#define CHECK_HANDLE(h)                                             \
     if (!(h)) return fail(TFIN_E_ARG, "%s: NULL handle", __func__); \
-    TFIN_CUDA(cudaSetDevice((h)->device));
+    DeviceGuard _device_guard((h)->device);
 
 // ------------------------------------------------------------------------------------------------ setup
 extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const int32_t* row_ptr,
@@ -1545,7 +1545,7 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
         const int slot = k.back() - '0';
         if (slot < 0 || slot > 3) return -1;
         unsigned long long v[4];
-        cudaSetDevice(h->device);
+        DeviceGuard guard(h->device);
         if (cudaStreamSynchronize(h->stream) != cudaSuccess ||
             cudaMemcpy(v, h->d_sprof.p, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
             return -1;
