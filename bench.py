@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--fom-batch", type=int, default=100_000, help="FOM samples per GPU per step")
     ap.add_argument("--rom-batch", type=int, default=1_000_000, help="ROM samples per GPU per step")
-    ap.add_argument("--refined-batch", type=int, default=1184,
+    ap.add_argument("--refined-batch", type=int, default=2368,
                     help="refined-mesh (m=26, n=99 945) FOM samples per GPU per step; 0 disables the leg")
     ap.add_argument("--refined-steps", type=int, default=2)
     ap.add_argument("--nodal-batch", type=int, default=100_000,
