@@ -190,6 +190,11 @@ struct tfin_ctx {
     DevBuf<int> d_avgT_ptr, d_avgT_idx;
     // ---- batch staging / scratch
     DevBuf<double> d_in, d_theta, d_w, d_qoi, d_relres, d_wr;
+    // ---- pipelined host path of the nodal solve: second stream, two input / solution staging buffers, events
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    DevBuf<double> d_pin[2], d_pw[2];
+    int64_t host_chunk = 8192;  // samples per pipelined chunk (0 disables the pipeline)
     DevBuf<int> d_iters, d_status;
     DevBuf<unsigned long long> d_counter;
     // ---- tuning
@@ -261,6 +266,14 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
     h->d_col.release();
     h->d_ncol.release();
     h->d_counter.release();
+    for (int b = 0; b < 2; ++b) {
+        h->d_pin[b].release();
+        h->d_pw[b].release();
+        if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
+        if (h->ev_comp[b]) cudaEventDestroy(h->ev_comp[b]);
+        if (h->ev_out[b]) cudaEventDestroy(h->ev_out[b]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -917,6 +930,83 @@ extern "C" int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int3
     return 0;
 }
 
+// Nodal solve from HOST buffers, pipelined: the fields are 8 n bytes per sample (12.8 KB at n = 1597), so a plain
+// "copy everything, solve, copy back" leaves the SMs idle for the whole transfer -- and from pageable numpy memory the
+// transfer is not much faster than the solve.  Chunks of `host_chunk` samples are double buffered instead: H2D of chunk
+// c + 1 (and D2H of the solutions of chunk c - 1, if requested) run on a second stream while chunk c is being solved.
+static int fom_nodal_host_pipelined(tfin_ctx* h, const double* k, int64_t N, double tol, int maxit, double* w_out,
+                                    double* qoi_out, int32_t* iters_out, int32_t* status_out, double* relres_out,
+                                    cudaStream_t st) {
+    const int n = h->n, nobs = h->n_obs;
+    const int64_t chunk = h->host_chunk;
+    if (!h->copy_stream) {
+        TFIN_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            TFIN_CUDA(cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming));
+            TFIN_CUDA(cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming));
+            TFIN_CUDA(cudaEventCreateWithFlags(&h->ev_out[b], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t cs = h->copy_stream;
+    for (int b = 0; b < 2; ++b) {
+        if (int e = h->d_pin[b].reserve((size_t)chunk * n)) return e;
+        if (w_out)
+            if (int e = h->d_pw[b].reserve((size_t)chunk * n)) return e;
+    }
+    double *d_qoi = nullptr, *d_relres = nullptr;
+    int *d_iters = nullptr, *d_status = nullptr;
+    if (qoi_out) {
+        if (int e = h->d_qoi.reserve((size_t)N * nobs)) return e;
+        d_qoi = h->d_qoi.p;
+    }
+    if (iters_out) {
+        if (int e = h->d_iters.reserve((size_t)N)) return e;
+        d_iters = h->d_iters.p;
+    }
+    if (status_out) {
+        if (int e = h->d_status.reserve((size_t)N)) return e;
+        d_status = h->d_status.p;
+    }
+    if (relres_out) {
+        if (int e = h->d_relres.reserve((size_t)N)) return e;
+        d_relres = h->d_relres.p;
+    }
+    const int64_t n_chunks = (N + chunk - 1) / chunk;
+    auto drain_w = [&](int64_t c) -> int {  // solutions of chunk c: device staging -> host, on the copy stream
+        const int b = (int)(c & 1);
+        const int64_t s0 = c * chunk, m = std::min<int64_t>(chunk, N - s0);
+        TFIN_CUDA(cudaStreamWaitEvent(cs, h->ev_comp[b], 0));
+        TFIN_CUDA(cudaMemcpyAsync(w_out + (size_t)s0 * n, h->d_pw[b].p, (size_t)m * n * 8, cudaMemcpyDeviceToHost, cs));
+        TFIN_CUDA(cudaEventRecord(h->ev_out[b], cs));
+        return 0;
+    };
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c & 1);
+        const int64_t s0 = c * chunk, m = std::min<int64_t>(chunk, N - s0);
+        if (c >= 2) TFIN_CUDA(cudaStreamWaitEvent(cs, h->ev_comp[b], 0));  // chunk c-2 has consumed this input buffer
+        TFIN_CUDA(cudaMemcpyAsync(h->d_pin[b].p, k + (size_t)s0 * n, (size_t)m * n * 8, cudaMemcpyHostToDevice, cs));
+        TFIN_CUDA(cudaEventRecord(h->ev_in[b], cs));
+        if (w_out && c >= 1)
+            if (int e = drain_w(c - 1)) return e;                          // queued behind the H2D of chunk c
+        TFIN_CUDA(cudaStreamWaitEvent(st, h->ev_in[b], 0));
+        if (w_out && c >= 2) TFIN_CUDA(cudaStreamWaitEvent(st, h->ev_out[b], 0));  // solution staging b is free again
+        if (int e = launch_pcg(h, true, h->d_pin[b].p, n, m, tol, maxit, w_out ? h->d_pw[b].p : nullptr,
+                               d_qoi ? d_qoi + (size_t)s0 * nobs : nullptr, d_iters ? d_iters + s0 : nullptr,
+                               d_status ? d_status + s0 : nullptr, d_relres ? d_relres + s0 : nullptr, st))
+            return e;
+        TFIN_CUDA(cudaEventRecord(h->ev_comp[b], st));
+    }
+    if (w_out)
+        if (int e = drain_w(n_chunks - 1)) return e;
+    if (qoi_out) TFIN_CUDA(cudaMemcpyAsync(qoi_out, d_qoi, (size_t)N * nobs * 8, cudaMemcpyDeviceToHost, st));
+    if (iters_out) TFIN_CUDA(cudaMemcpyAsync(iters_out, d_iters, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    if (status_out) TFIN_CUDA(cudaMemcpyAsync(status_out, d_status, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    if (relres_out) TFIN_CUDA(cudaMemcpyAsync(relres_out, d_relres, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    TFIN_CUDA(cudaStreamSynchronize(st));
+    TFIN_CUDA(cudaStreamSynchronize(cs));
+    return 0;
+}
+
 static int fom_common(tfin_handle_t h, bool nodal_op, const double* in, int64_t N, int32_t in_kind, int32_t mem,
                       double tol, int32_t maxit, double* w_out, double* qoi_out, int32_t* iters_out,
                       int32_t* status_out, double* relres_out, void* stream) {
@@ -927,6 +1017,8 @@ static int fom_common(tfin_handle_t h, bool nodal_op, const double* in, int64_t 
     if (nodal_op && h->n_cells <= 0) return fail(TFIN_E_STATE, "tfin_fom_nodal: call tfin_set_cells first");
     if (N == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (nodal_op && mem == TFIN_MEM_HOST && h->small_ok && h->host_chunk > 0 && N > h->host_chunk)
+        return fom_nodal_host_pipelined(h, in, N, tol, maxit, w_out, qoi_out, iters_out, status_out, relres_out, st);
     Staged sg{h, st, mem == TFIN_MEM_HOST};
     const int nparam = h->n_terms - 1;
     const bool nodal_in = nodal_op || in_kind == TFIN_IN_NODAL;
@@ -1571,6 +1663,11 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
     }
     if (k == "pcg_path") {
         h->pcg_path = (int)value;
+        return 0;
+    }
+    if (k == "host_chunk") {
+        if (value < 0) return fail(TFIN_E_ARG, "host_chunk must be >= 0");
+        h->host_chunk = value;
         return 0;
     }
     if (k == "pcg_precision") {

@@ -601,3 +601,23 @@ def test_greedy_basis_construction(space_m1, oracle_m1):
     q_r = fin.r_fwd_no_full_qoi(k, out[:, :6])
     x_ref = oracle_m1.r_fwd_no_full(k, out[:, :6])[3]
     assert relerr(q_r, oracle_m1.B_obs @ (out[:, :6] @ x_ref)) <= 1e-8
+
+
+def test_pipelined_host_path_is_bit_identical(fin_m3):
+    """tfin_fom_nodal from host buffers in double-buffered chunks (H2D / D2H overlapped with the solves) returns exactly
+    what the single-shot path returns: ragged last chunk, with and without the solution write-back."""
+    rng = np.random.default_rng(51)
+    k = np.exp(0.3 * rng.standard_normal((11, fin_m3.dofs)))
+    h = fin_m3.handle
+    try:
+        h.set_int("host_chunk", 0)
+        ref = h.fom_nodal(k, want_w=True)
+        for chunk in (3, 4, 10):
+            h.set_int("host_chunk", chunk)
+            out = h.fom_nodal(k, want_w=True)
+            for key in ("w", "qoi", "iters", "status", "relres"):
+                assert np.array_equal(out[key], ref[key]), (chunk, key)
+            out = h.fom_nodal(k, want_w=False, want_stats=False)
+            assert np.array_equal(out["qoi"], ref["qoi"])
+    finally:
+        h.set_int("host_chunk", 8192)
