@@ -934,9 +934,11 @@ extern "C" int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int3
 // "copy everything, solve, copy back" leaves the SMs idle for the whole transfer -- and from pageable numpy memory the
 // transfer is not much faster than the solve.  Chunks of `host_chunk` samples are double buffered instead: H2D of chunk
 // c + 1 (and D2H of the solutions of chunk c - 1, if requested) run on a second stream while chunk c is being solved.
+// With `adj` (gradient mode of the adjoint kernels) the per-sample vector that streams back is the gradient instead of
+// the solution: w_out then receives grad, adj->data is a DEVICE pointer to the (1 | N, n_obs) observations.
 static int fom_nodal_host_pipelined(tfin_ctx* h, const double* k, int64_t N, double tol, int maxit, double* w_out,
                                     double* qoi_out, int32_t* iters_out, int32_t* status_out, double* relres_out,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, const PcgAdj* adj = nullptr, double* cost_out = nullptr) {
     const int n = h->n, nobs = h->n_obs;
     const int64_t chunk = h->host_chunk;
     if (!h->copy_stream) {
@@ -971,6 +973,11 @@ static int fom_nodal_host_pipelined(tfin_ctx* h, const double* k, int64_t N, dou
         if (int e = h->d_relres.reserve((size_t)N)) return e;
         d_relres = h->d_relres.p;
     }
+    double* d_cost = nullptr;
+    if (cost_out) {
+        if (int e = h->d_cost.reserve((size_t)N)) return e;
+        d_cost = h->d_cost.p;
+    }
     const int64_t n_chunks = (N + chunk - 1) / chunk;
     auto drain_w = [&](int64_t c) -> int {  // solutions of chunk c: device staging -> host, on the copy stream
         const int b = (int)(c & 1);
@@ -986,15 +993,25 @@ static int fom_nodal_host_pipelined(tfin_ctx* h, const double* k, int64_t N, dou
         if (c >= 2) TFIN_CUDA(cudaStreamWaitEvent(cs, h->ev_comp[b], 0));  // chunk c-2 has consumed this input buffer
         TFIN_CUDA(cudaMemcpyAsync(h->d_pin[b].p, k + (size_t)s0 * n, (size_t)m * n * 8, cudaMemcpyHostToDevice, cs));
         TFIN_CUDA(cudaEventRecord(h->ev_in[b], cs));
-        if (w_out && c >= 1)
-            if (int e = drain_w(c - 1)) return e;                          // queued behind the H2D of chunk c
         TFIN_CUDA(cudaStreamWaitEvent(st, h->ev_in[b], 0));
         if (w_out && c >= 2) TFIN_CUDA(cudaStreamWaitEvent(st, h->ev_out[b], 0));  // solution staging b is free again
-        if (int e = launch_pcg(h, true, h->d_pin[b].p, n, m, tol, maxit, w_out ? h->d_pw[b].p : nullptr,
+        PcgAdj a{};
+        if (adj) {
+            a = *adj;
+            a.data = adj->data + (adj->data_stride ? (size_t)s0 * nobs : 0);
+            a.grad_out = h->d_pw[b].p;
+            a.cost_out = d_cost ? d_cost + s0 : nullptr;
+        }
+        if (int e = launch_pcg(h, true, h->d_pin[b].p, n, m, tol, maxit, (w_out && !adj) ? h->d_pw[b].p : nullptr,
                                d_qoi ? d_qoi + (size_t)s0 * nobs : nullptr, d_iters ? d_iters + s0 : nullptr,
-                               d_status ? d_status + s0 : nullptr, d_relres ? d_relres + s0 : nullptr, st))
+                               d_status ? d_status + s0 : nullptr, d_relres ? d_relres + s0 : nullptr, st,
+                               adj ? &a : nullptr))
             return e;
         TFIN_CUDA(cudaEventRecord(h->ev_comp[b], st));
+        // vectors of chunk c-1 go back while chunk c is being solved.  Issued AFTER the launch: a copy to pageable host
+        // memory blocks the calling thread until it has completed
+        if (w_out && c >= 1)
+            if (int e = drain_w(c - 1)) return e;
     }
     if (w_out)
         if (int e = drain_w(n_chunks - 1)) return e;
@@ -1002,6 +1019,7 @@ static int fom_nodal_host_pipelined(tfin_ctx* h, const double* k, int64_t N, dou
     if (iters_out) TFIN_CUDA(cudaMemcpyAsync(iters_out, d_iters, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
     if (status_out) TFIN_CUDA(cudaMemcpyAsync(status_out, d_status, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
     if (relres_out) TFIN_CUDA(cudaMemcpyAsync(relres_out, d_relres, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    if (cost_out) TFIN_CUDA(cudaMemcpyAsync(cost_out, d_cost, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
     TFIN_CUDA(cudaStreamSynchronize(st));
     TFIN_CUDA(cudaStreamSynchronize(cs));
     return 0;
@@ -1328,6 +1346,18 @@ static int fom_adjoint(tfin_handle_t h, int mode, const double* k, int64_t N, in
         return fail(TFIN_E_ARG, "tfin_fom_nodal_gradient: data must have 1 or N rows");
     if (N == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (mode == 1 && mem == TFIN_MEM_HOST && h->host_chunk > 0 && N > h->host_chunk) {  // pipelined host path
+        std::vector<double> hd(data, data + (size_t)data_rows * h->n_obs);
+        if (int e = h->d_data.upload(hd, st)) return e;
+        PcgAdj adj{};
+        adj.mode = 1;
+        adj.data = h->d_data.p;
+        adj.data_stride = data_rows == 1 ? 0 : h->n_obs;
+        adj.obsT = CsrRows{h->n, h->d_obsT_ptr.p, h->d_obsT_idx.p, h->d_obsT_val.p};
+        adj.Ke = h->d_Ke.p;
+        return fom_nodal_host_pipelined(h, k, N, tol, maxit, grad_out, qoi_out, iters_out, status_out, nullptr, st, &adj,
+                                        cost_out);
+    }
     Staged sg{h, st, mem == TFIN_MEM_HOST};
     const int n = h->n, nobs = h->n_obs;
     const int64_t grad_rows = mode == 2 ? N * nobs : N;

@@ -619,5 +619,14 @@ def test_pipelined_host_path_is_bit_identical(fin_m3):
                 assert np.array_equal(out[key], ref[key]), (chunk, key)
             out = h.fom_nodal(k, want_w=False, want_stats=False)
             assert np.array_equal(out["qoi"], ref["qoi"])
+        # the adjoint gradient streams back through the same pipeline (shared and per-sample observations)
+        data = rng.uniform(0.05, 0.6, (11, 9))
+        h.set_int("host_chunk", 0)
+        g_ref, g_ref1 = h.fom_nodal_gradient(k, data), h.fom_nodal_gradient(k, data[0])
+        for chunk in (3, 5):
+            h.set_int("host_chunk", chunk)
+            for got, want in ((h.fom_nodal_gradient(k, data), g_ref), (h.fom_nodal_gradient(k, data[0]), g_ref1)):
+                for key in ("grad", "cost", "qoi", "iters", "status"):
+                    assert np.array_equal(got[key], want[key]), (chunk, key)
     finally:
         h.set_int("host_chunk", 8192)

@@ -11,3 +11,10 @@ for chunk in (0, 8192, 16384, 4096):
     fin.forward_qoi(k[:20000])
     t0 = time.perf_counter(); q = fin.forward_qoi(k); dt = time.perf_counter() - t0
     print(f"host_chunk={chunk}: {N/dt:.3e} solves/s from pageable numpy ({dt*1e3:.0f} ms)")
+data = q[0]
+NG = min(N, 50000)
+for chunk in (0, 8192):
+    fin.handle.set_int("host_chunk", chunk)
+    fin.gradient(k[:10000], data)
+    t0 = time.perf_counter(); g = fin.gradient(k[:NG], data); dt = time.perf_counter() - t0
+    print(f"host_chunk={chunk}: {NG/dt:.3e} gradients/s from pageable numpy ({dt*1e3:.0f} ms)")
