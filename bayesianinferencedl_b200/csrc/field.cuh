@@ -169,9 +169,9 @@ __global__ void __launch_bounds__(256) field_normal_kernel(unsigned long long se
 
 // ------------------------------------------------------------------------------------------- F4 sampler
 // K[s][j] = exp(0.5 * sum_{i <= j} Z[s][i] L[j][i]):  fp64 "NT" GEMM restricted to the lower triangle, exp fused in
-// the epilogue.  64 x 64 tile, BK = 16, 256 threads x (4 x 4); operands are stored k-major in shared memory and the
-// next k-slab is prefetched into registers while the current one is consumed.
-constexpr int FS_BM = 64, FS_BN = 64, FS_BK = 16;
+// the epilogue.  128 x 64 tile, BK = 8, 256 threads x (8 x 4): three 16-byte shared loads feed 32 FMAs; operands are
+// stored k-major in shared memory and the next k-slab is prefetched into registers while the current one is consumed.
+constexpr int FS_BM = 128, FS_BN = 64, FS_BK = 8;
 
 __global__ void __launch_bounds__(256) field_sample_kernel(const double* __restrict__ Z, long long N, int n,
                                                            const double* __restrict__ L, double* __restrict__ K) {
@@ -181,29 +181,27 @@ __global__ void __launch_bounds__(256) field_sample_kernel(const double* __restr
     const int j0 = blockIdx.x * FS_BN;
     const int kmax = min(n, j0 + FS_BN);  // L[j][i] = 0 for i > j
     const int nslab = (kmax + FS_BK - 1) / FS_BK;
-    // loader mapping: row lr = tid / 4 (0..63), k quad lk = (tid % 4) * 4
-    const int lr = tid >> 2, lk = (tid & 3) * 4;
-    double ra[4], rb[4];
+    // loader mapping: A rows ar = tid / 2 (0..127), k quad (tid % 2) * 4;  B rows br = tid / 4 (0..63), k pair (tid % 4) * 2
+    const int ar = tid >> 1, ak = (tid & 1) * 4, br = tid >> 2, bk = (tid & 3) * 2;
+    double ra[4], rb[2];
     auto fetch = [&](int slab) {
-        const int k0 = slab * FS_BK + lk;
-        const long long s = s0 + lr;
-        const int j = j0 + lr;
+        const int k0 = slab * FS_BK;
+        const long long s = s0 + ar;
+        const int j = j0 + br;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            ra[q] = (s < N && k0 + q < kmax) ? Z[s * n + k0 + q] : 0.0;
-            rb[q] = (j < n && k0 + q <= j) ? L[(size_t)j * n + k0 + q] : 0.0;
-        }
+        for (int q = 0; q < 4; ++q) ra[q] = (s < N && k0 + ak + q < kmax) ? Z[s * n + k0 + ak + q] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) rb[q] = (j < n && k0 + bk + q <= j) ? L[(size_t)j * n + k0 + bk + q] : 0.0;
     };
     auto stash = [&](int buf) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            As[buf][lk + q][lr] = ra[q];
-            Bs[buf][lk + q][lr] = rb[q];
-        }
-    };
-    double acc[4][4];
+        for (int q = 0; q < 4; ++q) As[buf][ak + q][ar] = ra[q];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+        for (int q = 0; q < 2; ++q) Bs[buf][bk + q][br] = rb[q];
+    };
+    double acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
     fetch(0);
@@ -214,11 +212,12 @@ __global__ void __launch_bounds__(256) field_sample_kernel(const double* __restr
         if (slab + 1 < nslab) fetch(slab + 1);
 #pragma unroll
         for (int k = 0; k < FS_BK; ++k) {
-            const double4 a4 = *reinterpret_cast<const double4*>(&As[buf][k][4 * ty]);
+            const double4 a0 = *reinterpret_cast<const double4*>(&As[buf][k][8 * ty]);
+            const double4 a1 = *reinterpret_cast<const double4*>(&As[buf][k][8 * ty + 4]);
             const double4 b4 = *reinterpret_cast<const double4*>(&Bs[buf][k][4 * tx]);
-            const double av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            const double av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
         }
@@ -226,8 +225,8 @@ __global__ void __launch_bounds__(256) field_sample_kernel(const double* __restr
         __syncthreads();
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const long long s = s0 + 4 * ty + a;
+    for (int a = 0; a < 8; ++a) {
+        const long long s = s0 + 8 * ty + a;
         if (s >= N) continue;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
