@@ -630,3 +630,40 @@ def test_pipelined_host_path_is_bit_identical(fin_m3):
                     assert np.array_equal(got[key], want[key]), (chunk, key)
     finally:
         h.set_int("host_chunk", 8192)
+
+
+def test_sampler_ops_perform_protocol(space_m2, oracle_m2):
+    """Theano-style ``perform(node, inputs, outputs)`` shims: ParamToObsFOM (inference.py:21-57, exp(k) model) and
+    SqErrorOpFOM / SqErrorOpROM (pymc_func_bayes_inverse.py:106-151), single proposal and a batch of chains."""
+    from bayesianinferencedl_b200 import make_cov_chol
+    from bayesianinferencedl_b200.bayesian_inference.ops import ParamToObsFOM, SqErrorOpFOM, SqErrorOpROM
+    from oracle.thermal_fin_oracle import pod_basis
+    orc = oracle_m2
+    rng = np.random.default_rng(61)
+    logk = 0.4 * rng.standard_normal((3, orc.n))
+    op = ParamToObsFOM(space_m2, False)
+    outputs = [[None], [None]]
+    op.perform(None, [logk[0]], outputs)
+    assert outputs[0][0].shape == (9,) and outputs[1][0].shape == (9, orc.n)
+    assert relerr(outputs[0][0], orc.qoi_operator(orc.forward_exp(logk[0]))) <= 1e-10
+    ref = orc.sensitivity_exp(logk[0])
+    assert np.max(np.abs(outputs[1][0] - ref)) <= 1e-9 * np.max(np.abs(ref))
+    qb, jb = op(logk)                                                      # three chains in one launch
+    assert qb.shape == (3, 9) and jb.shape == (3, 9, orc.n) and np.array_equal(jb[0], outputs[1][0])
+    gbar = rng.standard_normal((3, 9))
+    assert np.allclose(op.vjp(logk, gbar)[1], jb[1].T @ gbar[1]) and np.allclose(op.vjp(logk[2], gbar[2]), jb[2].T @ gbar[2])
+    chol = make_cov_chol(space_m2, "m52", 1.6)
+    phi = pod_basis(orc, n_snapshots=40, basis_size=20, seed=1)
+    fom, rom = SqErrorOpFOM(space_m2, chol, False, seed=4), SqErrorOpROM(space_m2, chol, False, phi=phi, seed=4)
+    k = np.exp(0.3 * rng.standard_normal((2, orc.n)))
+    data = fom._error_op.obs_data
+    v, g = fom(k[0])
+    assert v.shape == () and g.shape == (orc.n,)
+    q = orc.qoi_operator(orc.forward(k[0]))
+    assert abs(float(v) - 0.5 * np.sum((q - data) ** 2)) <= 1e-9 * float(v)
+    ref = orc.gradient(k[0], data)
+    assert np.max(np.abs(g - ref)) <= 1e-9 * np.max(np.abs(ref))
+    vr, gr = rom(k)
+    for s in range(2):
+        dJ, J, _ = orc.grad_reduced(k[s], data, phi)
+        assert abs(vr[s] - J) <= 1e-9 * J and np.max(np.abs(gr[s] - dJ)) <= 1e-8 * np.max(np.abs(dJ))
