@@ -353,8 +353,10 @@ __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict_
 // as a batched GEMM  c[s][o] = sum_{i,j} (v_i w_j) NG[(i,j)][o],  o = (t, q), followed by the th_t fold.
 // CTA = 64 samples x one block of 96 outputs at a time; warp = 8 samples, lane = outputs lane + 32 m.  Two-stage
 // accumulation keeps the FP64 pipe on pure FMAs:  d += w_j * NG[i][j][.] over j, then c += v_i * d once per i.
-// NG streams from L2 through a 4-stage cp.async ring of 16-row chunks; w and v sit transposed in shared memory.
-constexpr int RG_BM = 64, RG_OB = 96, RG_KC = 16, RG_STAGES = 4;
+// NG streams from L2 through a 3-stage cp.async ring of 32-row chunks; w and v sit transposed in shared memory.  The
+// operands of step k+1 are loaded into a second register set before the FMAs of step k (the fold branch between steps
+// keeps the compiler from doing that itself: ncu showed every step's 7 shared loads exposed in front of its 24 FMAs).
+constexpr int RG_BM = 64, RG_OB = 96, RG_KC = 32, RG_STAGES = 3;
 
 __host__ __device__ inline size_t rom_grad_smem(int nr, int n_par) {
     return ((size_t)2 * nr * RG_BM + (size_t)RG_STAGES * RG_KC * RG_OB + (size_t)RG_BM * n_par) * sizeof(double);
@@ -409,18 +411,20 @@ __global__ void __launch_bounds__(256, 1) rom_grad_kernel(const double* __restri
                 issue(chunk + RG_STAGES - 1);
                 const double* st = s_ring + (size_t)(chunk % RG_STAGES) * RG_KC * RG_OB;
                 const int rows = min(RG_KC, K - chunk * RG_KC);
-#pragma unroll 4
-                for (int r = 0; r < rows; ++r) {
-                    const double4 w0 = *reinterpret_cast<const double4*>(&s_w[j * RG_BM + 8 * warp]);
-                    const double4 w1 = *reinterpret_cast<const double4*>(&s_w[j * RG_BM + 8 * warp + 4]);
-                    const double wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                    double nv[3];
+                double wv[8], nv[3];
+                auto load = [&](int r, int jj, double (&w_)[8], double (&n_)[3]) {
+                    const double4 w0 = *reinterpret_cast<const double4*>(&s_w[jj * RG_BM + 8 * warp]);
+                    const double4 w1 = *reinterpret_cast<const double4*>(&s_w[jj * RG_BM + 8 * warp + 4]);
+                    w_[0] = w0.x; w_[1] = w0.y; w_[2] = w0.z; w_[3] = w0.w;
+                    w_[4] = w1.x; w_[5] = w1.y; w_[6] = w1.z; w_[7] = w1.w;
 #pragma unroll
-                    for (int m = 0; m < 3; ++m) nv[m] = st[r * RG_OB + lane + 32 * m];
+                    for (int m = 0; m < 3; ++m) n_[m] = st[r * RG_OB + lane + 32 * m];
+                };
+                auto step = [&](const double (&w_)[8], const double (&n_)[3]) {
 #pragma unroll
                     for (int a = 0; a < 8; ++a)
 #pragma unroll
-                        for (int m = 0; m < 3; ++m) d[a][m] = fma(wv[a], nv[m], d[a][m]);
+                        for (int m = 0; m < 3; ++m) d[a][m] = fma(w_[a], n_[m], d[a][m]);
                     if (++j == nr) {  // row i of the outer product is complete: c += v_i * d
                         const double4 v0 = *reinterpret_cast<const double4*>(&s_v[i * RG_BM + 8 * warp]);
                         const double4 v1 = *reinterpret_cast<const double4*>(&s_v[i * RG_BM + 8 * warp + 4]);
@@ -435,7 +439,18 @@ __global__ void __launch_bounds__(256, 1) rom_grad_kernel(const double* __restri
                         j = 0;
                         ++i;
                     }
+                };
+                auto next_j = [&]() { return (j + 1 == nr) ? 0 : j + 1; };
+                double wn[8], nn[3];
+                load(0, j, wv, nv);
+                int r = 0;
+                for (; r + 1 < rows; r += 2) {  // ping-pong between the two operand sets: no register copies
+                    load(r + 1, next_j(), wn, nn);
+                    step(wv, nv);
+                    if (r + 2 < rows) load(r + 2, next_j(), wv, nv);
+                    step(wn, nn);
                 }
+                if (r < rows) step(wv, nv);
             }
             cp_async_wait<0>();
             __syncthreads();  // everyone is done with the ring: reuse it for c[BM][OB]
