@@ -21,42 +21,57 @@ __host__ __device__ inline int rom_taug(int nr) { return nr * (nr + 1) / 2 + nr;
 
 constexpr int ROM_BM = 64;    // samples per CTA
 constexpr int ROM_BN = 128;   // packed entries per tile of the sweep
+constexpr int ROM_LDA = ROM_BM + 4, ROM_LDB = ROM_BN + 4;  // row strides = 4 (mod 16): conflict-free fragment loads
 constexpr int ROM_MAXP2 = TFIN_MAX_TERMS * (TFIN_MAX_TERMS + 1) / 2;
 
+__host__ __device__ inline int rom_combine_k4(int n_terms) { return (n_terms * (n_terms + 1) / 2 + 3) & ~3; }
 __host__ __device__ inline size_t rom_combine_smem(int n_terms) {
-    return (size_t)(n_terms * (n_terms + 1) / 2) * (ROM_BM + 2 * ROM_BN) * sizeof(double);
+    return (size_t)rom_combine_k4(n_terms) * (ROM_LDA + 2 * ROM_LDB) * sizeof(double);
+}
+
+// D (8x8) += A (8x4, row) * B (4x8, col) on the FP64 tensor path (DMMA).  Lane l = 4 g + t holds A[g][t], B[t][g] and
+// C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
 
 // ------------------------------------------------------------------------------------------- R1
-// C[s][t] = sum_pq coef[s][pq] * S[pq][t],  coef[s][(p,q)] = th_p th_q.  One CTA owns 64 samples and sweeps ALL entry
-// tiles (128 entries each): the coefficient tile is built once, the S tiles stream from L2 through a double buffer
-// filled by cp.async while the previous tile is being multiplied, and results are stored as they finish -- so the
-// FP64 pipe never waits for a tile prologue.  Register tile 4 samples x 8 entries: thread (ty, tx) owns samples
-// 4 ty .. 4 ty + 3 and the entry pairs 2 tx + 32 j (+0, +1): every shared load is a 16-byte access at unit stride
-// across the warp and a warp stores 256 contiguous bytes per row.
-// Shared memory (P2 = 55): coef [P2][64] 28 KB + 2 x S tile [P2][128] 112 KB.
+// C[s][t] = sum_pq coef[s][pq] * S[pq][t],  coef[s][(p,q)] = th_p th_q -- the one real dense contraction of the path, on
+// the FP64 tensor cores (mma.sync m8n8k4, the only FP64 tensor instruction of sm_100a).  One CTA owns 64 samples and
+// sweeps ALL entry tiles (128 entries each): the coefficient tile is built once, the S tiles stream from L2 through a
+// double buffer filled by cp.async while the previous tile is being multiplied, results are stored as they finish.
+// Warp (wm, wn) of the 2 x 4 warp grid owns 32 samples x 32 entries = 4 x 4 DMMA blocks: per k-step of 4 it loads 4 + 4
+// fragments for 16 MMAs (128 FMAs per lane), against 5 shared loads per 32 FMAs in the plain FMA version.
+// Shared memory (P2 = 55 -> K = 56): coef [K][68] 30 KB + 2 x S tile [K][132] 118 KB.
 __global__ void __launch_bounds__(256, 1) rom_combine_kernel(const double* __restrict__ theta,  // (N, n_terms-1)
                                                              long long s_begin, long long s_end, int n_terms,
                                                              const double* __restrict__ S,  // [P2][ldS], ldS % 128 == 0
                                                              int ldS, int Taug, double* __restrict__ C /* [Nchunk][Taug] */) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int P2 = n_terms * (n_terms + 1) / 2;
-    double* s_coef = reinterpret_cast<double*>(smem);          // [P2][BM]
-    double* s_S = s_coef + (size_t)P2 * ROM_BM;                 // [2][P2][BN]
-    const int tid = threadIdx.x;
+    const int P2 = n_terms * (n_terms + 1) / 2, K4 = rom_combine_k4(n_terms);
+    double* s_coef = reinterpret_cast<double*>(smem);          // [K4][LDA]
+    double* s_S = s_coef + (size_t)K4 * ROM_LDA;                // [2][K4][LDB]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;                    // 2 x 4 warps
     const int n_tiles = ldS / ROM_BN;
     const bool even = (Taug & 1) == 0;  // rows of C are then 16-byte aligned
     auto issue = [&](int tile) {
         if (tile < n_tiles) {
-            double* dst = s_S + (size_t)(tile & 1) * P2 * ROM_BN;
+            double* dst = s_S + (size_t)(tile & 1) * K4 * ROM_LDB;
             const double* src = S + (size_t)tile * ROM_BN;
             for (int e = tid; e < P2 * (ROM_BN / 2); e += 256) {
                 const int pq = e / (ROM_BN / 2), c2 = e - pq * (ROM_BN / 2);
-                cp_async16(dst + pq * ROM_BN + 2 * c2, src + (size_t)pq * ldS + 2 * c2);
+                cp_async16(dst + pq * ROM_LDB + 2 * c2, src + (size_t)pq * ldS + 2 * c2);
             }
         }
         cp_async_commit();
     };
+    for (int e = tid; e < (K4 - P2) * ROM_LDB * 2; e += 256) {  // zero the K padding rows of both S buffers, once
+        const int bsel = e / ((K4 - P2) * ROM_LDB), r = e - bsel * (K4 - P2) * ROM_LDB;
+        s_S[(size_t)bsel * K4 * ROM_LDB + (size_t)P2 * ROM_LDB + r] = 0.0;
+    }
     for (long long s0 = s_begin + (long long)blockIdx.x * ROM_BM; s0 < s_end; s0 += (long long)gridDim.x * ROM_BM) {
         __syncthreads();  // previous sample tile is done with both buffers and s_coef
         issue(0);
@@ -65,56 +80,53 @@ __global__ void __launch_bounds__(256, 1) rom_combine_kernel(const double* __res
             double th[TFIN_MAX_TERMS];
             th[0] = s < s_end ? 1.0 : 0.0;
 #pragma unroll
-            for (int t = 1; t < TFIN_MAX_TERMS; ++t)
-                th[t] = (t < n_terms && s < s_end) ? theta[s * (n_terms - 1) + t - 1] : 0.0;
+            for (int tt = 1; tt < TFIN_MAX_TERMS; ++tt)
+                th[tt] = (tt < n_terms && s < s_end) ? theta[s * (n_terms - 1) + tt - 1] : 0.0;
             int pq = 0;
 #pragma unroll
             for (int p = 0; p < TFIN_MAX_TERMS; ++p)
 #pragma unroll
                 for (int q = p; q < TFIN_MAX_TERMS; ++q)
-                    if (p < n_terms && q < n_terms) s_coef[(pq++) * ROM_BM + sl] = th[p] * th[q];
+                    if (p < n_terms && q < n_terms) s_coef[(pq++) * ROM_LDA + sl] = th[p] * th[q];
+            for (int k = P2; k < K4; ++k) s_coef[k * ROM_LDA + sl] = 0.0;
         }
-        const int ty = tid >> 4, tx = tid & 15;
         for (int tile = 0; tile < n_tiles; ++tile) {
             cp_async_wait<0>();
             __syncthreads();       // tile landed (and s_coef written); everyone finished the other buffer
             issue(tile + 1);
-            const double* sS = s_S + (size_t)(tile & 1) * P2 * ROM_BN;
-            double acc[4][8];
+            const double* sB = s_S + (size_t)(tile & 1) * K4 * ROM_LDB + 32 * wn + g;
+            const double* sA = s_coef + 32 * wm + g;
+            double acc[4][4][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-#pragma unroll 5
-            for (int pq = 0; pq < P2; ++pq) {
-                const double4 a4 = *reinterpret_cast<const double4*>(&s_coef[pq * ROM_BM + 4 * ty]);
-                const double a[4] = {a4.x, a4.y, a4.z, a4.w};
-                double b[8];
+                for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+#pragma unroll 2
+            for (int k0 = 0; k0 < K4; k0 += 4) {
+                double a[4], b[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double2 v = *reinterpret_cast<const double2*>(&sS[pq * ROM_BN + 2 * tx + 32 * j]);
-                    b[2 * j] = v.x;
-                    b[2 * j + 1] = v.y;
-                }
+                for (int mb = 0; mb < 4; ++mb) a[mb] = sA[(k0 + t) * ROM_LDA + 8 * mb];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int nb = 0; nb < 4; ++nb) b[nb] = sB[(k0 + t) * ROM_LDB + 8 * nb];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
             }
-            const int t0 = tile * ROM_BN;
+            const int t0 = tile * ROM_BN + 32 * wn + 2 * t;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long s = s0 + 4 * ty + i;
+            for (int mb = 0; mb < 4; ++mb) {
+                const long long s = s0 + 32 * wm + 8 * mb + g;
                 if (s >= s_end) continue;
                 double* row = C + (size_t)(s - s_begin) * Taug;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int t = t0 + 2 * tx + 32 * j;
-                    if (even && t + 1 < Taug) {
-                        *reinterpret_cast<double2*>(row + t) = make_double2(acc[i][2 * j], acc[i][2 * j + 1]);
+                for (int nb = 0; nb < 4; ++nb) {
+                    const int tt = t0 + 8 * nb;
+                    if (even && tt + 1 < Taug) {
+                        *reinterpret_cast<double2*>(row + tt) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
                     } else {
-                        if (t < Taug) row[t] = acc[i][2 * j];
-                        if (t + 1 < Taug) row[t + 1] = acc[i][2 * j + 1];
+                        if (tt < Taug) row[tt] = acc[mb][nb][0];
+                        if (tt + 1 < Taug) row[tt + 1] = acc[mb][nb][1];
                     }
                 }
             }

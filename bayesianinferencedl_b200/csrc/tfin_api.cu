@@ -1121,6 +1121,8 @@ static int rom_run(tfin_ctx* h, const RomSrc& src, int nr, int nobs, const doubl
     int gram_threads = 0, gram_occ = 1;
     if (!src.nodal) {
         comb_smem = rom_combine_smem(nt);
+        if (comb_smem > (size_t)h->max_smem_optin)
+            return fail(TFIN_E_STATE, "tfin_rom: %d affine terms need %zu bytes of shared memory for the operator combination (max 12 terms)", nt, comb_smem);
         TFIN_CUDA(cudaFuncSetAttribute(rom_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comb_smem));
     } else {
         const int TT = h->b_TT;
