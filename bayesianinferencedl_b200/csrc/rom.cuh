@@ -362,40 +362,46 @@ __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict_
 // ------------------------------------------------------------------------------------------- R3
 // Reduced gradient contraction (averaged_affine_ROM.py:347-351 rewritten with offline Gram blocks):
 //     g_q = (psi v_r)^T (K_q phi) w_r = sum_t th_t  v_r^T N_tq w_r,     N_tq = Psi_t^T Psi_q   (n_r x n_r)
-// as a batched GEMM  c[s][o] = sum_{i,j} (v_i w_j) NG[(i,j)][o],  o = (t, q), followed by the th_t fold.
-// CTA = 64 samples x one block of 96 outputs at a time; warp = 8 samples, lane = outputs lane + 32 m.  Two-stage
-// accumulation keeps the FP64 pipe on pure FMAs:  d += w_j * NG[i][j][.] over j, then c += v_i * d once per i.
-// NG streams from L2 through a 3-stage cp.async ring of 32-row chunks; w and v sit transposed in shared memory.  The
-// operands of step k+1 are loaded into a second register set before the FMAs of step k (the fold branch between steps
-// keeps the compiler from doing that itself: ncu showed every step's 7 shared loads exposed in front of its 24 FMAs).
-constexpr int RG_BM = 64, RG_OB = 96, RG_KC = 32, RG_STAGES = 3;
+// as a batched GEMM  c[s][o] = sum_{i,j} (v_i w_j) NG[(i,j)][o],  o = (t, q), followed by the th_t fold -- on the FP64
+// tensor cores (DMMA m8n8k4).  The A operand is never stored: lane (g, t) of an 8 x 4 fragment forms
+// v[s_g][i] * w[s_g][j0 + t] with one multiply from the transposed, padded copies of w and v in shared memory.  The j
+// range is padded to a multiple of 4 (zero rows of NG) so that a k-step of 4 never straddles two i.
+// CTA = 64 samples x 96 outputs at a time; warp (wm, wn) of the 2 x 4 grid owns 32 samples x 24 outputs = 4 x 3 DMMA
+// blocks.  NG streams from L2 through a 3-stage cp.async ring of 32-row chunks (row stride 100: conflict-free
+// fragment loads).
+constexpr int RG_BM = 64, RG_OB = 96, RG_KC = 32, RG_STAGES = 3, RG_LDB = RG_OB + 4, RG_LDA = RG_BM + 4;
 
+__host__ __device__ inline int rom_grad_jpad(int nr) { return (nr + 3) & ~3; }
 __host__ __device__ inline size_t rom_grad_smem(int nr, int n_par) {
-    return ((size_t)2 * nr * RG_BM + (size_t)RG_STAGES * RG_KC * RG_OB + (size_t)RG_BM * n_par) * sizeof(double);
+    const size_t ring = (size_t)RG_STAGES * RG_KC * RG_LDB, cbuf = (size_t)RG_BM * RG_OB;
+    return ((size_t)(rom_grad_jpad(nr) + nr) * RG_LDA + (ring > cbuf ? ring : cbuf) + (size_t)RG_BM * n_par) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(256, 1) rom_grad_kernel(const double* __restrict__ theta,  // (N, n_terms-1)
                                                           const double* __restrict__ wr,     // (N, nr)
                                                           const double* __restrict__ vr,     // (N, nr)
                                                           long long N, int nr, int n_terms,
-                                                          const double* __restrict__ NG,  // [n_ob][nr*nr][RG_OB]
+                                                          const double* __restrict__ NG,  // [n_ob][nr*jpad][RG_OB]
                                                           int n_ob, double* __restrict__ g_out /* (N, n_terms-1) */) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int n_par = n_terms - 1, O = n_terms * n_par, K = nr * nr;
-    double* s_w = reinterpret_cast<double*>(smem);     // [nr][BM]
-    double* s_v = s_w + (size_t)nr * RG_BM;             // [nr][BM]
-    double* s_ring = s_v + (size_t)nr * RG_BM;          // [STAGES][KC][OB]; reused as c[BM][OB] in the epilogue
-    double* s_g = s_ring + (size_t)RG_STAGES * RG_KC * RG_OB;  // [BM][n_par]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_par = n_terms - 1, O = n_terms * n_par, jp = rom_grad_jpad(nr), K = nr * jp;
+    double* s_w = reinterpret_cast<double*>(smem);     // [jp][LDA]  (rows >= nr are zero)
+    double* s_v = s_w + (size_t)jp * RG_LDA;            // [nr][LDA]
+    double* s_ring = s_v + (size_t)nr * RG_LDA;         // [STAGES][KC][LDB]; reused as c[BM][OB] in the epilogue
+    const size_t ring_sz = (size_t)RG_STAGES * RG_KC * RG_LDB, cbuf_sz = (size_t)RG_BM * RG_OB;
+    double* s_g = s_ring + (ring_sz > cbuf_sz ? ring_sz : cbuf_sz);  // [BM][n_par]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
     const int n_chunks = (K + RG_KC - 1) / RG_KC;
 
     for (long long s0 = (long long)blockIdx.x * RG_BM; s0 < N; s0 += (long long)gridDim.x * RG_BM) {
         __syncthreads();  // previous tile's epilogue is done with s_ring / s_g
-        for (int e = tid; e < RG_BM * nr; e += 256) {
-            const int sl = e / nr, j = e - sl * nr;
+        for (int e = tid; e < RG_BM * jp; e += 256) {
+            const int sl = e / jp, j = e - sl * jp;
             const long long s = s0 + sl;
-            s_w[j * RG_BM + sl] = s < N ? wr[s * nr + j] : 0.0;
-            s_v[j * RG_BM + sl] = s < N ? vr[s * nr + j] : 0.0;
+            const bool ok = s < N && j < nr;
+            s_w[j * RG_LDA + sl] = ok ? wr[s * nr + j] : 0.0;
+            if (j < nr) s_v[j * RG_LDA + sl] = ok ? vr[s * nr + j] : 0.0;
         }
         for (int e = tid; e < RG_BM * n_par; e += 256) s_g[e] = 0.0;
         for (int ob = 0; ob < n_ob; ++ob) {
@@ -403,87 +409,80 @@ __global__ void __launch_bounds__(256, 1) rom_grad_kernel(const double* __restri
             auto issue = [&](int chunk) {
                 if (chunk < n_chunks) {
                     const int rows = min(RG_KC, K - chunk * RG_KC);
-                    const double* g = src + (size_t)chunk * RG_KC * RG_OB;
-                    double* d = s_ring + (size_t)(chunk % RG_STAGES) * RG_KC * RG_OB;
-                    for (int e = tid; e < rows * (RG_OB / 2); e += 256) cp_async16(d + 2 * e, g + 2 * e);
+                    const double* gsrc = src + (size_t)chunk * RG_KC * RG_OB;
+                    double* d = s_ring + (size_t)(chunk % RG_STAGES) * RG_KC * RG_LDB;
+                    for (int e = tid; e < rows * (RG_OB / 2); e += 256) {
+                        const int r = e / (RG_OB / 2), c2 = e - r * (RG_OB / 2);
+                        cp_async16(d + r * RG_LDB + 2 * c2, gsrc + (size_t)r * RG_OB + 2 * c2);
+                    }
                 }
                 cp_async_commit();
             };
             __syncthreads();  // s_w / s_v visible; ring free
             for (int c = 0; c < RG_STAGES - 1; ++c) issue(c);
-            double acc[8][3], d[8][3];
+            double acc[4][3][2];
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                for (int m = 0; m < 3; ++m) acc[a][m] = 0.0, d[a][m] = 0.0;
-            int i = 0, j = 0;
+                for (int nb = 0; nb < 3; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+            const double* sA = s_w + 32 * wm + g;
+            const double* sV = s_v + 32 * wm + g;
+            int i = 0, j0 = 0;
+            double vi[4];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) vi[mb] = sV[8 * mb];   // v[.][i = 0]; s_v is visible after the barrier above
             for (int chunk = 0; chunk < n_chunks; ++chunk) {
                 cp_async_wait<RG_STAGES - 2>();
                 __syncthreads();             // chunk landed for everyone; the stage refilled below was consumed
                 issue(chunk + RG_STAGES - 1);
-                const double* st = s_ring + (size_t)(chunk % RG_STAGES) * RG_KC * RG_OB;
-                const int rows = min(RG_KC, K - chunk * RG_KC);
-                double wv[8], nv[3];
-                auto load = [&](int r, int jj, double (&w_)[8], double (&n_)[3]) {
-                    const double4 w0 = *reinterpret_cast<const double4*>(&s_w[jj * RG_BM + 8 * warp]);
-                    const double4 w1 = *reinterpret_cast<const double4*>(&s_w[jj * RG_BM + 8 * warp + 4]);
-                    w_[0] = w0.x; w_[1] = w0.y; w_[2] = w0.z; w_[3] = w0.w;
-                    w_[4] = w1.x; w_[5] = w1.y; w_[6] = w1.z; w_[7] = w1.w;
+                const double* sB = s_ring + (size_t)(chunk % RG_STAGES) * RG_KC * RG_LDB + 24 * wn + g;
+                const int rows = min(RG_KC, K - chunk * RG_KC);   // a multiple of 4
+#pragma unroll 2
+                for (int r = 0; r < rows; r += 4) {
+                    double a[4], b[3];
 #pragma unroll
-                    for (int m = 0; m < 3; ++m) n_[m] = st[r * RG_OB + lane + 32 * m];
-                };
-                auto step = [&](const double (&w_)[8], const double (&n_)[3]) {
+                    for (int mb = 0; mb < 4; ++mb) a[mb] = vi[mb] * sA[(j0 + t) * RG_LDA + 8 * mb];
 #pragma unroll
-                    for (int a = 0; a < 8; ++a)
+                    for (int nb = 0; nb < 3; ++nb) b[nb] = sB[(r + t) * RG_LDB + 8 * nb];
 #pragma unroll
-                        for (int m = 0; m < 3; ++m) d[a][m] = fma(w_[a], n_[m], d[a][m]);
-                    if (++j == nr) {  // row i of the outer product is complete: c += v_i * d
-                        const double4 v0 = *reinterpret_cast<const double4*>(&s_v[i * RG_BM + 8 * warp]);
-                        const double4 v1 = *reinterpret_cast<const double4*>(&s_v[i * RG_BM + 8 * warp + 4]);
-                        const double vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                        for (int a = 0; a < 8; ++a)
-#pragma unroll
-                            for (int m = 0; m < 3; ++m) {
-                                acc[a][m] = fma(vv[a], d[a][m], acc[a][m]);
-                                d[a][m] = 0.0;
-                            }
-                        j = 0;
+                        for (int nb = 0; nb < 3; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+                    j0 += 4;
+                    if (j0 == jp) {  // next row i of the outer product
+                        j0 = 0;
                         ++i;
+                        if (i < nr) {
+#pragma unroll
+                            for (int mb = 0; mb < 4; ++mb) vi[mb] = sV[i * RG_LDA + 8 * mb];
+                        }
                     }
-                };
-                auto next_j = [&]() { return (j + 1 == nr) ? 0 : j + 1; };
-                double wn[8], nn[3];
-                load(0, j, wv, nv);
-                int r = 0;
-                for (; r + 1 < rows; r += 2) {  // ping-pong between the two operand sets: no register copies
-                    load(r + 1, next_j(), wn, nn);
-                    step(wv, nv);
-                    if (r + 2 < rows) load(r + 2, next_j(), wv, nv);
-                    step(wn, nn);
                 }
-                if (r < rows) step(wv, nv);
             }
             cp_async_wait<0>();
             __syncthreads();  // everyone is done with the ring: reuse it for c[BM][OB]
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                for (int m = 0; m < 3; ++m) s_ring[(8 * warp + a) * RG_OB + lane + 32 * m] = acc[a][m];
+                for (int nb = 0; nb < 3; ++nb) {
+                    double* dst = s_ring + (32 * wm + 8 * mb + g) * RG_OB + 24 * wn + 8 * nb + 2 * t;
+                    dst[0] = acc[mb][nb][0];
+                    dst[1] = acc[mb][nb][1];
+                }
             __syncthreads();
             for (int e = tid; e < RG_BM * n_par; e += 256) {
                 const int sl = e / n_par, q = e - sl * n_par;
                 const long long s = s0 + sl;
                 if (s >= N) continue;
-                double g = 0.0;
+                double gq = 0.0;
                 // outputs of this block: o = ob*OB + ol = t * n_par + q
-                for (int t = 0; t < n_terms; ++t) {
-                    const int ol = t * n_par + q - ob * RG_OB;
-                    if (ol < 0 || ol >= RG_OB || t * n_par + q >= O) continue;
-                    const double th = t == 0 ? 1.0 : theta[s * n_par + t - 1];
-                    g = fma(th, s_ring[sl * RG_OB + ol], g);
+                for (int tt = 0; tt < n_terms; ++tt) {
+                    const int ol = tt * n_par + q - ob * RG_OB;
+                    if (ol < 0 || ol >= RG_OB || tt * n_par + q >= O) continue;
+                    const double th = tt == 0 ? 1.0 : theta[s * n_par + tt - 1];
+                    gq = fma(th, s_ring[sl * RG_OB + ol], gq);
                 }
-                s_g[e] += g;
+                s_g[e] += gq;
             }
         }
         __syncthreads();

@@ -619,13 +619,15 @@ extern "C" int tfin_set_rom_gradient(tfin_handle_t h, int32_t n_r, int32_t n_ter
     if (!gram || n_r != h->n_r || n_terms != h->rom_terms)
         return fail(TFIN_E_ARG, "tfin_set_rom_gradient: n_r / n_terms must match tfin_set_rom (%d, %d)", h->n_r,
                     h->rom_terms);
-    // gram[t][q-1][i][j] = (Psi_t^T Psi_q)[i][j]  ->  NG[ob][i*n_r + j][96] with output o = t (n_terms-1) + (q-1)
-    const int n_par = n_terms - 1, O = n_terms * n_par, K = n_r * n_r, n_ob = (O + RG_OB - 1) / RG_OB;
+    // gram[t][q-1][i][j] = (Psi_t^T Psi_q)[i][j]  ->  NG[ob][i*jp + j][96] with output o = t (n_terms-1) + (q-1); the j range
+    // is padded to jp = multiple of 4 with zero rows (a DMMA k-step of 4 never straddles two i)
+    const int n_par = n_terms - 1, O = n_terms * n_par, jp = rom_grad_jpad(n_r), K = n_r * jp, n_ob = (O + RG_OB - 1) / RG_OB;
     std::vector<double> ng((size_t)n_ob * K * RG_OB, 0.0);
     for (int o = 0; o < O; ++o) {
-        const double* src = gram + (size_t)o * K;
+        const double* src = gram + (size_t)o * n_r * n_r;
         double* dst = ng.data() + (size_t)(o / RG_OB) * K * RG_OB + (o % RG_OB);
-        for (int k = 0; k < K; ++k) dst[(size_t)k * RG_OB] = src[k];
+        for (int i = 0; i < n_r; ++i)
+            for (int j = 0; j < n_r; ++j) dst[(size_t)(i * jp + j) * RG_OB] = src[i * n_r + j];
     }
     if (int e = h->d_NG.upload(ng, h->stream)) return e;
     TFIN_CUDA(cudaStreamSynchronize(h->stream));
