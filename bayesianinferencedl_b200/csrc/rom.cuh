@@ -197,17 +197,58 @@ __device__ __forceinline__ void rom_fwd_subst(const double* __restrict__ A, cons
     }
 }
 
-// One panel (4 columns starting at j0) of the left-looking Cholesky of the augmented packed matrix, for a warp.  Lane l
-// holds rows j0 + l + 32 m (m < M live slabs) of the four panel columns in registers; one sweep over the finished
-// columns k < j0 updates the whole panel (M + 4 shared loads for 4 M FMAs), then the panel is factored in registers with
-// shuffles and written back once.
-template <int M>
+// Left-looking update of an 8-column panel on the FP64 tensor cores, in place in the packed factor:
+//     A[r][j0 + c] -= sum_{k < j0} L[r][k] L[j0 + c][k],      r = j0 .. n_r (augmented row included), c = 0 .. 7
+// i.e. (rows x j0) . (j0 x 8) as DMMA m8n8k4 blocks: lane (g, t) supplies L[j0 + 8 mb + g][k0 + t] as the A fragment of
+// row block mb and L[j0 + g][k0 + t] as the B fragment (the same word as its A fragment of block 0), so one k-step of
+// 4 costs 4 G shared loads and 4 G MMAs for 32 G rows x 8 columns x 4 k = 1024 G FMAs (the FMA sweep needed 38 G + 40
+// instructions for the same work).  Column k of the packed layout starts at k n_r - k (k - 1) / 2 - k relative to its
+// row index, advanced incrementally.  Loads are NOT bounds-checked (rows past the matrix read at most 31 doubles
+// beyond a column, inside this warp's region); the read-modify-write at the end is masked to the stored triangle.
+template <int G /* live 32-row groups */>
+__device__ __forceinline__ void rom_chol_sweep_mma(double* __restrict__ A, int j0, int nr, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double acc[4 * G][2];
+#pragma unroll
+    for (int mb = 0; mb < 4 * G; ++mb) acc[mb][0] = acc[mb][1] = 0.0;
+    int k = t, base = t * nr - (t * (t - 1)) / 2;  // rom_col_off(k) - k: + row addresses L[row][k]
+#pragma unroll 2
+    for (int k0 = 0; k0 < j0; k0 += 4) {
+        const double* colp = A + base + j0 + g;
+        double a[4 * G];
+#pragma unroll
+        for (int mb = 0; mb < 4 * G; ++mb) a[mb] = colp[8 * mb];
+#pragma unroll
+        for (int mb = 0; mb < 4 * G; ++mb) dmma_884(acc[mb][0], acc[mb][1], a[mb], a[0]);
+        base += 4 * nr - 4 * k - 6;
+        k += 4;
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int col = j0 + 2 * t + e;
+        if (col < nr) {
+            const int oc = rom_col_off(col, nr) - col;
+#pragma unroll
+            for (int mb = 0; mb < 4 * G; ++mb) {
+                const int row = j0 + 8 * mb + g;
+                if (row <= nr && row >= col) A[oc + row] -= acc[mb][e];
+            }
+        }
+    }
+}
+
+// One panel (NB columns starting at j0) of the left-looking Cholesky of the augmented packed matrix, for a warp.  Lane l
+// holds rows j0 + l + 32 m (m < M live slabs) of the panel columns in registers.  With SWEEP the contribution of the
+// finished columns k < j0 is applied here with FMAs (M + NB shared loads for NB M FMAs per k); without it the caller
+// has already applied it (rom_chol_sweep_mma).  Then the panel is factored in registers with shuffles and written
+// back once.
+template <int M, int NB, bool SWEEP>
 __device__ __forceinline__ void rom_chol_panel(double* __restrict__ A, double* __restrict__ dinv, int j0, int nr,
                                                int lane, int& status) {
-    const int nrow = nr + 1, ncol = min(4, nr - j0);
-    double c[4][M];
+    const int nrow = nr + 1, ncol = min(NB, nr - j0);
+    double c[NB][M];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int cc = 0; cc < NB; ++cc) {
         const int oc = rom_col_off(j0 + cc, nr) - cc;  // + (i - j0) addresses row i of column j0+cc
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -215,35 +256,33 @@ __device__ __forceinline__ void rom_chol_panel(double* __restrict__ A, double* _
             c[cc][m] = (cc < ncol && i < nrow && i >= j0 + cc) ? A[oc + lane + 32 * m] : 0.0;
         }
     }
-    // Sweep over the finished columns.  colp walks row (j0 + lane) of column k: consecutive columns of the packed layout
-    // are nr - k entries apart, so there is no per-k offset arithmetic.  Loads are NOT bounds-checked: a lane whose row
-    // lies past the matrix (or a panel column past ncol) reads at most 31 doubles beyond the column -- still inside
-    // this warp's region (dinv / w follow A) -- and only pollutes accumulators that are never stored or shuffled out.
-    {
+    if (SWEEP) {
+        // colp walks row (j0 + lane) of column k: consecutive columns of the packed layout are nr - k entries apart.
+        // Unchecked loads, see rom_chol_sweep_mma.
         const double* colp = A + j0 + lane;
         int stride = nr;
 #pragma unroll 4
         for (int k = 0; k < j0; ++k) {
-            double lk[M], lj[4];
+            double lk[M], lj[NB];
 #pragma unroll
             for (int m = 0; m < M; ++m) lk[m] = colp[32 * m];
             const double* rowp = colp - lane;  // row j0 of column k (warp-uniform address: broadcast)
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) lj[cc] = rowp[cc];
+            for (int cc = 0; cc < NB; ++cc) lj[cc] = rowp[cc];
 #pragma unroll
             for (int m = 0; m < M; ++m)
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) c[cc][m] = fma(-lk[m], lj[cc], c[cc][m]);
+                for (int cc = 0; cc < NB; ++cc) c[cc][m] = fma(-lk[m], lj[cc], c[cc][m]);
             colp += stride;
             --stride;
         }
     }
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int cc = 0; cc < NB; ++cc) {
         if (cc < ncol) {
             // updates from the already finished columns of this panel
 #pragma unroll
-            for (int c2 = 0; c2 < 4; ++c2) {
+            for (int c2 = 0; c2 < NB; ++c2) {
                 if (c2 < cc) {
                     const double ljc = __shfl_sync(0xffffffffu, c[c2][0], cc);  // L[j0+cc][j0+c2]
 #pragma unroll
@@ -298,14 +337,28 @@ __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict_
         }
         __syncwarp();
         int status = TFIN_STATUS_CONVERGED;
-        // Panel-blocked left-looking Cholesky, NB = 4 columns at a time; the panel body is instantiated for the number
-        // of 32-row slabs that still hold rows (warp-uniform), so empty slabs cost no issue slots at all.
-        for (int j0 = 0; j0 < nr; j0 += 4) {
+        // Panel-blocked left-looking Cholesky, 8 columns at a time: the update from the finished columns runs on the
+        // tensor cores (DMMA), the panel itself is factored in registers.  Both are instantiated for the number of
+        // 32-row slabs that still hold rows (warp-uniform), so empty slabs cost no issue slots at all.
+        for (int j0 = 0; j0 < nr; j0 += 8) {
             const int mact = min(MAXM, (nrow - j0 + 31) >> 5);
-            if (MAXM >= 4 && mact == 4) rom_chol_panel<(MAXM >= 4 ? 4 : 1)>(A, dinv, j0, nr, lane, status);
-            else if (MAXM >= 3 && mact == 3) rom_chol_panel<(MAXM >= 3 ? 3 : 1)>(A, dinv, j0, nr, lane, status);
-            else if (MAXM >= 2 && mact == 2) rom_chol_panel<(MAXM >= 2 ? 2 : 1)>(A, dinv, j0, nr, lane, status);
-            else rom_chol_panel<1>(A, dinv, j0, nr, lane, status);
+            if (MAXM >= 4 && mact == 4) {
+                if (j0) rom_chol_sweep_mma<(MAXM >= 4 ? 4 : 1)>(A, j0, nr, lane);
+                __syncwarp();
+                rom_chol_panel<(MAXM >= 4 ? 4 : 1), 8, false>(A, dinv, j0, nr, lane, status);
+            } else if (MAXM >= 3 && mact == 3) {
+                if (j0) rom_chol_sweep_mma<(MAXM >= 3 ? 3 : 1)>(A, j0, nr, lane);
+                __syncwarp();
+                rom_chol_panel<(MAXM >= 3 ? 3 : 1), 8, false>(A, dinv, j0, nr, lane, status);
+            } else if (MAXM >= 2 && mact == 2) {
+                if (j0) rom_chol_sweep_mma<(MAXM >= 2 ? 2 : 1)>(A, j0, nr, lane);
+                __syncwarp();
+                rom_chol_panel<(MAXM >= 2 ? 2 : 1), 8, false>(A, dinv, j0, nr, lane, status);
+            } else {
+                if (j0) rom_chol_sweep_mma<1>(A, j0, nr, lane);
+                __syncwarp();
+                rom_chol_panel<1, 8, false>(A, dinv, j0, nr, lane, status);
+            }
             __syncwarp();
         }
         // y = last row of the factor (the forward substitution rode along with the factorisation)
