@@ -573,6 +573,10 @@ def run_b200(args):
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "traffic_note": traffic_note, "kernel": "pcg_kernel<affine>", "kernel_ms": k_ms,
             "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+            "onchip": ({"bound": "smem", "pct_of_peak": ncu_t["pcg_kernel"].get("smem_pipe_pct_of_peak"),
+                        "metric": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+                        "source": "profiles/r1_ncu_summary.json (ncu --set full of a 2960-sample launch)"}
+                       if "pcg_kernel" in ncu_t else None),
             "note": "algorithmic bytes = 88*n*iterations per solve (SURVEY 8d); at n=1597 the CG vectors and the "
                     "per-sample operator live in shared memory/registers, so achieved/peak is NOT bounded by 1 "
                     "and real DRAM traffic (traffic) is orders of magnitude below it",
