@@ -152,22 +152,25 @@ struct RomAdj {
 template <int MAXM>
 __device__ __forceinline__ void rom_back_subst(const double* __restrict__ A, const double* __restrict__ dinv, int nr,
                                                int lane, double (&yv)[MAXM]) {
-    // the slab index of the pivot is a compile-time constant inside the unrolled mb loop, so yv stays in registers
+    // the slab index of the pivot is a compile-time constant inside the unrolled mb loop, so yv stays in registers and
+    // the triangle tests reduce to one lane compare in the pivot's own slab (rows of lower slabs are always above it)
+    int ci[MAXM];  // rom_col_off(i) - i of this lane's rows: + j addresses L[j][i]
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        const int i = min(lane + 32 * m, nr - 1);
+        ci[m] = rom_col_off(i, nr) - i;
+    }
 #pragma unroll
     for (int mb = MAXM - 1; mb >= 0; --mb) {
         for (int j = min(nr, 32 * mb + 32) - 1; j >= 32 * mb; --j) {
+            const int jl = j & 31;
             double lji[MAXM];
 #pragma unroll
-            for (int m = 0; m <= mb; ++m) {
-                const int i = lane + 32 * m;
-                lji[m] = i < j ? A[rom_col_off(i, nr) + (j - i)] : 0.0;
-            }
-            const double wj = __shfl_sync(0xffffffffu, yv[mb], j & 31) * dinv[j];
+            for (int m = 0; m <= mb; ++m) lji[m] = (m < mb || lane < jl) ? A[ci[m] + j] : 0.0;
+            const double wj = __shfl_sync(0xffffffffu, yv[mb], jl) * dinv[j];
 #pragma unroll
-            for (int m = 0; m <= mb; ++m) {
-                const int i = lane + 32 * m;
-                yv[m] = (i == j) ? wj : fma(-lji[m], wj, yv[m]);
-            }
+            for (int m = 0; m < mb; ++m) yv[m] = fma(-lji[m], wj, yv[m]);
+            yv[mb] = (lane == jl) ? wj : fma(-lji[mb], wj, yv[mb]);
         }
     }
 }
@@ -180,19 +183,16 @@ __device__ __forceinline__ void rom_fwd_subst(const double* __restrict__ A, cons
 #pragma unroll
     for (int mb = 0; mb < MAXM; ++mb) {
         for (int j = 32 * mb; j < min(nr, 32 * mb + 32); ++j) {
-            const int oj = rom_col_off(j, nr) - j;  // + i addresses L[i][j]
+            const int jl = j & 31;
+            const double* colp = A + (rom_col_off(j, nr) - j) + lane;  // + 32 m addresses L[lane + 32 m][j]
             double lij[MAXM];
 #pragma unroll
-            for (int m = mb; m < MAXM; ++m) {
-                const int i = lane + 32 * m;
-                lij[m] = (i > j && i < nr) ? A[oj + i] : 0.0;
-            }
-            const double zj = __shfl_sync(0xffffffffu, yv[mb], j & 31) * dinv[j];
+            for (int m = mb; m < MAXM; ++m)
+                lij[m] = ((m > mb || lane > jl) && lane + 32 * m < nr) ? colp[32 * m] : 0.0;
+            const double zj = __shfl_sync(0xffffffffu, yv[mb], jl) * dinv[j];
+            yv[mb] = (lane == jl) ? zj : fma(-lij[mb], zj, yv[mb]);
 #pragma unroll
-            for (int m = mb; m < MAXM; ++m) {
-                const int i = lane + 32 * m;
-                yv[m] = (i == j) ? zj : fma(-lij[m], zj, yv[m]);
-            }
+            for (int m = mb + 1; m < MAXM; ++m) yv[m] = fma(-lij[m], zj, yv[m]);
         }
     }
 }
@@ -247,15 +247,17 @@ __device__ __forceinline__ void rom_chol_panel(double* __restrict__ A, double* _
                                                int lane, int& status) {
     const int nrow = nr + 1, ncol = min(NB, nr - j0);
     double c[NB][M];
+    bool row_ok[M];  // row j0 + lane + 32 m exists; "on or below the diagonal of column cc" is lane >= cc in slab 0 only
 #pragma unroll
-    for (int cc = 0; cc < NB; ++cc) {
-        const int oc = rom_col_off(j0 + cc, nr) - cc;  // + (i - j0) addresses row i of column j0+cc
+    for (int m = 0; m < M; ++m) row_ok[m] = j0 + lane + 32 * m < nrow;
+    int oc[NB];      // + lane + 32 m addresses row j0 + lane + 32 m of column j0 + cc
 #pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const int i = j0 + lane + 32 * m;
-            c[cc][m] = (cc < ncol && i < nrow && i >= j0 + cc) ? A[oc + lane + 32 * m] : 0.0;
-        }
-    }
+    for (int cc = 0; cc < NB; ++cc) oc[cc] = rom_col_off(min(j0 + cc, nr - 1), nr) - cc;
+#pragma unroll
+    for (int cc = 0; cc < NB; ++cc)
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            c[cc][m] = (cc < ncol && row_ok[m] && (m > 0 || lane >= cc)) ? A[oc[cc] + lane + 32 * m] : 0.0;
     if (SWEEP) {
         // colp walks row (j0 + lane) of column k: consecutive columns of the packed layout are nr - k entries apart.
         // Unchecked loads, see rom_chol_sweep_mma.
@@ -294,12 +296,10 @@ __device__ __forceinline__ void rom_chol_panel(double* __restrict__ A, double* _
             const double ljj = sqrt(d);
             const double inv0 = rsqrt(d);
             const double invl = inv0 * (2.0 - ljj * inv0);  // one Newton step on 1 / ljj
-            const int oc = rom_col_off(j0 + cc, nr) - cc;
 #pragma unroll
             for (int m = 0; m < M; ++m) {
-                const int i = j0 + lane + 32 * m;
-                c[cc][m] = (i == j0 + cc) ? ljj : c[cc][m] * invl;
-                if (i < nrow && i >= j0 + cc) A[oc + lane + 32 * m] = c[cc][m];
+                c[cc][m] = (m == 0 && lane == cc) ? ljj : c[cc][m] * invl;
+                if (row_ok[m] && (m > 0 || lane >= cc)) A[oc[cc] + lane + 32 * m] = c[cc][m];
             }
             if (lane == 0) dinv[j0 + cc] = invl;
         }
