@@ -293,9 +293,12 @@ __device__ __forceinline__ void rom_chol_panel(double* __restrict__ A, double* _
             }
             const double d = __shfl_sync(0xffffffffu, c[cc][0], cc);
             if (!(d > 0.0)) status = TFIN_STATUS_BREAKDOWN;
-            const double ljj = sqrt(d);
+            // sqrt(d) and 1/sqrt(d) from ONE reciprocal square root (the serial chain of the factorisation runs through
+            // here 81 times): ljj = d r corrected by its exact residual, then one Newton step on 1 / ljj
             const double inv0 = rsqrt(d);
-            const double invl = inv0 * (2.0 - ljj * inv0);  // one Newton step on 1 / ljj
+            double ljj = d * inv0;
+            ljj = fma(fma(-ljj, ljj, d), 0.5 * inv0, ljj);
+            const double invl = inv0 * (2.0 - ljj * inv0);
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 c[cc][m] = (m == 0 && lane == cc) ? ljj : c[cc][m] * invl;
