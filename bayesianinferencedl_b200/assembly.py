@@ -116,6 +116,16 @@ class FinOperators:
         """CSR values of the full stiffness K (all cells, marker 0 included)."""
         return self.vals[1:].sum(axis=0) + self.k_unmarked
 
+    def mass_matrix(self):
+        """Consistent P1 mass matrix ``assemble(inner(w, v) * dx)`` (forward_solve.py:172) as scipy CSR: per cell
+        |e| / 12 * [[2, 1, 1], [1, 2, 1], [1, 1, 2]]."""
+        import scipy.sparse as sp
+        loc = (np.ones((3, 3)) + np.eye(3)) / 12.0
+        r = np.repeat(self.cells, 3, axis=1).ravel()
+        c = np.tile(self.cells, (1, 3)).ravel()
+        v = (self.cell_area[:, None, None] * loc[None, :, :]).ravel()
+        return sp.coo_matrix((v, (r, c)), shape=(self.n, self.n)).tocsr()
+
     def obs_csr(self, B=None):
         """(ptr, idx, val) CSR of an observation matrix (default: B_obs)."""
         B = self.B_obs if B is None else np.asarray(B, dtype=np.float64)

@@ -89,6 +89,21 @@ class Fin:
     def handle(self):
         return self._h
 
+    @property
+    def M(self):
+        """forward_solve.py:172: dense mass matrix ``assemble(inner(w, v) * dx).array()`` (built on first use; the prior
+        construction of bayesian_inference/inference.py:79-92 reads it)."""
+        if "M" not in self.ops._cache:
+            self.ops._cache["M"] = self.ops.mass_matrix().toarray()
+        return self.ops._cache["M"]
+
+    @property
+    def K(self):
+        """forward_solve.py:173: dense stiffness matrix ``assemble(inner(grad w, grad v) * dx).array()``."""
+        if "K" not in self.ops._cache:
+            self.ops._cache["K"] = self.ops.csr(self.ops.stiffness_values()).toarray()
+        return self.ops._cache["K"]
+
     # ------------------------------------------------------------------ forward map
     def forward(self, k):
         """forward_solve.py:270-291.  ``k``: nodal conductivity (n,) or (N, n).

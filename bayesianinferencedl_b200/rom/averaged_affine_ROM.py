@@ -112,6 +112,15 @@ class AffineROMFin:
     def handle(self):
         return self._h
 
+    @property
+    def dA_dsigmak_phi(self):
+        """:215-220: ``dA_dsigmak[q] @ phi`` = K_q phi, shape (9, n, n_r) (built on first use; the batched gradient
+        kernels use the Gram blocks of :func:`rom_gradient_tensors` instead)."""
+        if "dA_dsigmak_phi" not in self.ops._cache:
+            self.ops._cache["dA_dsigmak_phi"] = np.stack(
+                [self.ops.csr(self.ops.vals[q]) @ self.phi for q in range(1, self.num_params + 1)])
+        return self.ops._cache["dA_dsigmak_phi"]
+
     # ------------------------------------------------------------------ full-order affine model
     def forward(self, k):
         """:237-258.  ``k`` nodal field (n,) | (N, n): averaged over the sub-fins, then the affine solve."""

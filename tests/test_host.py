@@ -239,3 +239,18 @@ def test_enrich_matches_reference_recipe():
     for j in range(0, 4 - 1):
         ref = ref - (ref @ basis[:, j]) / (basis[:, j] @ basis[:, j]) * basis[:, j]
     assert np.allclose(U[:, 4], ref / np.sqrt(ref @ ref), atol=1e-15)
+
+
+def test_mass_and_stiffness_matrices(space_m1, oracle_m1):
+    """Fin.M / Fin.K (forward_solve.py:172-173) from the host operators: partition of unity and polynomial exactness."""
+    from bayesianinferencedl_b200.assembly import build_operators
+    ops = build_operators(space_m1)
+    M = ops.mass_matrix().toarray()
+    K = ops.csr(ops.stiffness_values()).toarray()
+    one = np.ones(ops.n)
+    assert abs(one @ M @ one - oracle_m1.domain_measure) <= 1e-12 * oracle_m1.domain_measure     # int 1 dx = |domain|
+    assert np.allclose(M, M.T) and np.allclose(K, K.T) and np.allclose(K @ one, 0.0, atol=1e-12)
+    x, y = ops.coords[:, 0], ops.coords[:, 1]
+    assert abs(x @ K @ x - oracle_m1.domain_measure) <= 1e-10 * oracle_m1.domain_measure        # int |grad x|^2 = |domain|
+    assert np.allclose(K, sum(Kq.toarray() for Kq in oracle_m1.K_q), atol=1e-13)                # conforming mesh: all cells marked
+    assert np.allclose(M @ one, oracle_m1.C * oracle_m1.domain_measure, rtol=1e-12)             # row sums = int phi_i
