@@ -107,6 +107,7 @@ class AffineROMFin:
         if precision == "fp32":
             self._h.set_int("pcg_precision", 32)
         self._grad_ready = False
+        self._dA_phi = None
 
     @property
     def handle(self):
@@ -116,10 +117,9 @@ class AffineROMFin:
     def dA_dsigmak_phi(self):
         """:215-220: ``dA_dsigmak[q] @ phi`` = K_q phi, shape (9, n, n_r) (built on first use; the batched gradient
         kernels use the Gram blocks of :func:`rom_gradient_tensors` instead)."""
-        if "dA_dsigmak_phi" not in self.ops._cache:
-            self.ops._cache["dA_dsigmak_phi"] = np.stack(
-                [self.ops.csr(self.ops.vals[q]) @ self.phi for q in range(1, self.num_params + 1)])
-        return self.ops._cache["dA_dsigmak_phi"]
+        if self._dA_phi is None:   # depends on phi: kept on this object (the operators are shared per space)
+            self._dA_phi = np.stack([self.ops.csr(self.ops.vals[q]) @ self.phi for q in range(1, self.num_params + 1)])
+        return self._dA_phi
 
     # ------------------------------------------------------------------ full-order affine model
     def forward(self, k):
