@@ -667,3 +667,60 @@ def test_sampler_ops_perform_protocol(space_m2, oracle_m2):
     for s in range(2):
         dJ, J, _ = orc.grad_reduced(k[s], data, phi)
         assert abs(vr[s] - J) <= 1e-9 * J and np.max(np.abs(gr[s] - dJ)) <= 1e-8 * np.max(np.abs(dJ))
+
+
+@pytest.mark.parametrize("n_terms", [2, 3, 10, 12])
+def test_rom_kernels_across_basis_sizes(n_terms):
+    """Pure ROM kernels (DMMA combine, DMMA-swept Cholesky, substitutions, DMMA gradient contraction) on synthetic
+    well-conditioned tensors for every slab / panel / padding boundary of the basis size, against dense numpy."""
+    from bayesianinferencedl_b200 import _cabi
+    rng = np.random.default_rng(100 + n_terms)
+    n_obs, N = 5, 37
+    for n_r in (1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127):
+        m = n_r + 6
+        Psi = rng.standard_normal((n_terms, m, n_r)) / np.sqrt(m)
+        Psi[0] += np.eye(m, n_r) * 3.0                                  # psi = sum theta_t Psi_t has full column rank
+        b = rng.standard_normal(m)
+        il = np.tril_indices(n_r)
+        S = []
+        for p in range(n_terms):
+            for q in range(p, n_terms):
+                M = Psi[p].T @ Psi[q]
+                S.append((M + M.T if q != p else M)[il])
+        G = np.stack([P.T @ b for P in Psi])
+        obs_phi = rng.standard_normal((n_obs, n_r))
+        h = _cabi.TfinHandle(0)
+        h.set_rom(np.stack(S), G, obs_phi)
+        gram = np.stack([np.stack([Psi[t].T @ Psi[q] for q in range(1, n_terms)]) for t in range(n_terms)])
+        h.set_rom_gradient(gram)
+        theta = rng.uniform(0.2, 1.5, (N, n_terms - 1))
+        data = rng.standard_normal((N, n_obs))
+        out = h.rom(theta)
+        outg = h.rom_gradient(theta, data, want_wr=True)
+        assert np.all(out["status"] == 0) and np.all(outg["status"] == 0), n_r
+        for s in (0, 17, N - 1):
+            th = np.concatenate([[1.0], theta[s]])
+            psi = np.tensordot(th, Psi, axes=1)
+            A_r, B_r = psi.T @ psi, psi.T @ b
+            w = np.linalg.solve(A_r, B_r)
+            scale = np.max(np.abs(w))
+            assert np.max(np.abs(out["w_r"][s] - w)) <= 1e-9 * scale, (n_r, s)
+            assert np.max(np.abs(outg["w_r"][s] - w)) <= 1e-9 * scale, (n_r, s)
+            q = obs_phi @ w
+            assert np.max(np.abs(out["qoi"][s] - q)) <= 1e-9 * max(np.max(np.abs(q)), 1e-300), (n_r, s)
+            v = np.linalg.solve(A_r, obs_phi.T @ (data[s] - q))
+            g = np.array([v @ (psi.T @ Psi[qq]) @ w for qq in range(1, n_terms)])
+            assert np.max(np.abs(outg["grad"][s] - g)) <= 1e-8 * max(np.max(np.abs(g)), 1e-300), (n_r, s)
+            assert abs(outg["cost"][s] - 0.5 * np.sum((data[s] - q) ** 2)) <= 1e-9 * (outg["cost"][s] + 1e-300)
+        h.close()
+
+
+def test_rom_too_many_terms_fails_loudly():
+    """More than 12 affine terms do not fit the combine kernel's shared memory: the call must say so, not mis-compute."""
+    from bayesianinferencedl_b200 import _cabi
+    n_terms, n_r = 14, 4
+    h = _cabi.TfinHandle(0)
+    h.set_rom(np.zeros((n_terms * (n_terms + 1) // 2, n_r * (n_r + 1) // 2)), np.zeros((n_terms, n_r)), np.zeros((2, n_r)))
+    with pytest.raises(_cabi.TfinError, match="max 12 terms"):
+        h.rom(np.ones((3, n_terms - 1)))
+    h.close()
