@@ -1062,15 +1062,25 @@ static int fom_common(tfin_handle_t h, bool nodal_op, const double* in, int64_t 
     if (int e = sg.out_alloc(iters_out, (size_t)N, h->d_iters, &d_iters)) return e;
     if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
     if (int e = sg.out_alloc(relres_out, (size_t)N, h->d_relres, &d_relres)) return e;
-    const bool use_stream = !nodal_op && (h->pcg_path == 2 || (h->pcg_path == 0 && !h->small_ok));
+    bool use_stream = !nodal_op && (h->pcg_path == 2 || (h->pcg_path == 0 && !h->small_ok));
     if (!use_stream && !h->small_ok)
         return fail(TFIN_E_STATE, "on-chip PCG needs n <= 8191 (n = %d); use the streaming path", h->n);
     const bool use_f32 = !use_stream && !nodal_op && h->precision == 32;
-    int rc = use_stream
-                 ? launch_pcg_stream(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st)
-             : use_f32
-                 ? launch_pcg_f32(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st)
-                 : launch_pcg(h, nodal_op, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st);
+    int rc = 0;
+    if (!use_stream) {
+        rc = use_f32 ? launch_pcg_f32(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st)
+                     : launch_pcg(h, nodal_op, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st);
+        // no compiled on-chip variant fits this mesh (CG state + per-sample operator exceed one SM, n >~ 4100):
+        // the affine operator falls back to the streaming kernel; the nodal operator has no streaming kernel
+        if (rc == TFIN_E_STATE && !nodal_op && !use_f32 && h->pcg_path == 0 && h->stream_ok) use_stream = true;
+        else if (rc == TFIN_E_STATE && nodal_op)
+            return fail(TFIN_E_STATE, "tfin_fom_nodal: the nodal-conductivity kernel keeps the CG state and the per-sample "
+                        "operator on one SM and no compiled variant fits n = %d (ell width %d); meshes up to about 4100 "
+                        "dofs are supported", h->n, h->Wn);
+        else if (rc) return rc;
+    }
+    if (use_stream)
+        rc = launch_pcg_stream(h, d_par, stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st);
     if (rc) return rc;
     if (int e = sg.out_copy(w_out, (size_t)N * h->n, d_w)) return e;
     if (int e = sg.out_copy(qoi_out, (size_t)N * h->n_obs, d_qoi)) return e;

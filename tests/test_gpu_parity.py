@@ -724,3 +724,32 @@ def test_rom_too_many_terms_fails_loudly():
     with pytest.raises(_cabi.TfinError, match="max 12 terms"):
         h.rom(np.ones((3, n_terms - 1)))
     h.close()
+
+
+def test_mid_size_meshes_pick_a_working_path():
+    """Meshes between the on-chip limit of the compiled variants (~4100 dofs) and the uint16 limit (8191): the affine
+    solve falls back to the streaming kernel automatically; the nodal solve (on-chip only) fails loudly."""
+    from bayesianinferencedl_b200 import _cabi, get_space
+    from bayesianinferencedl_b200.assembly import build_operators
+    from oracle.thermal_fin_oracle import FinOracle
+    rng = np.random.default_rng(9)
+    for m, path in ((4, 1), (6, 2)):                       # n = 2705 (R = 16 on chip), n = 5785 (streaming)
+        ops = build_operators(get_space(40, m=m))
+        h = _cabi.TfinHandle(0)
+        h.set_operator(ops.row_ptr, ops.col_idx, ops.vals, ops.rhs)
+        h.set_observation(*ops.obs_csr())
+        theta = rng.uniform(0.1, 3.5, (5, 9))
+        out = h.fom_affine(theta)
+        assert h.get_int("pcg_path") == path and np.all(out["status"] == 0)
+        orc = FinOracle(ops.coords, ops.cells)
+        for s in (0, 4):
+            assert relerr(out["qoi"][s], orc.qoi_operator(orc.forward_nine_param(theta[s]))) <= RTOL_FOM
+        h.set_cells(ops.cells, ops.Ke)
+        k = np.exp(0.2 * rng.standard_normal((2, ops.n)))
+        if m == 4:
+            q = h.fom_nodal(k)["qoi"]
+            assert relerr(q[1], orc.qoi_operator(orc.forward(k[1]))) <= RTOL_FOM
+        else:
+            with pytest.raises(_cabi.TfinError, match="about 4100"):
+                h.fom_nodal(k)
+        h.close()
