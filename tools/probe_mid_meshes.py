@@ -1,4 +1,6 @@
-import sys; sys.path.insert(0, '/root/repo')
+"""GPU probe: which PCG path / variant serves meshes between 2 k and 8 k dofs (affine and nodal operators)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from bayesianinferencedl_b200 import get_space, AffineROMFin, Fin, _cabi
 from bayesianinferencedl_b200.assembly import build_operators
