@@ -205,7 +205,7 @@ struct tfin_ctx {
 };
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int tfin_version(void) { return 100; }
+extern "C" int tfin_version(void) { return 120; }
 extern "C" const char* tfin_last_error(void) { return last_error().c_str(); }
 
 extern "C" int tfin_create(int device, tfin_handle_t* out) {
@@ -940,9 +940,14 @@ extern "C" int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int3
 // the solution: w_out then receives grad, adj->data is a DEVICE pointer to the (1 | N, n_obs) observations.
 static int fom_nodal_host_pipelined(tfin_ctx* h, const double* k, int64_t N, double tol, int maxit, double* w_out,
                                     double* qoi_out, int32_t* iters_out, int32_t* status_out, double* relres_out,
-                                    cudaStream_t st, const PcgAdj* adj = nullptr, double* cost_out = nullptr) {
-    const int n = h->n, nobs = h->n_obs;
+                                    cudaStream_t st, const PcgAdj* adj = nullptr, double* cost_out = nullptr,
+                                    bool affine_avg = false) {
+    // affine_avg: AffineROMFin.forward(k) -- the fields are averaged over the sub-fins (K0) and the AFFINE on-chip
+    // kernel solves; otherwise the nodal kernel consumes the fields directly
+    const int n = h->n, nobs = h->n_obs, nparam = h->n_terms - 1;
     const int64_t chunk = h->host_chunk;
+    if (affine_avg)
+        if (int e = h->d_theta.reserve((size_t)2 * chunk * nparam)) return e;
     if (!h->copy_stream) {
         TFIN_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (int b = 0; b < 2; ++b) {
@@ -1004,7 +1009,16 @@ static int fom_nodal_host_pipelined(tfin_ctx* h, const double* k, int64_t N, dou
             a.grad_out = h->d_pw[b].p;
             a.cost_out = d_cost ? d_cost + s0 : nullptr;
         }
-        if (int e = launch_pcg(h, true, h->d_pin[b].p, n, m, tol, maxit, (w_out && !adj) ? h->d_pw[b].p : nullptr,
+        const double* d_par = h->d_pin[b].p;
+        int stride = n;
+        if (affine_avg) {
+            double* th = h->d_theta.p + (size_t)b * chunk * nparam;
+            CsrRows avg{h->n_avg, h->d_avg_ptr.p, h->d_avg_idx.p, h->d_avg_val.p};
+            if (int e = launch_project(h, avg, h->d_pin[b].p, m, th, st)) return e;
+            d_par = th;
+            stride = nparam;
+        }
+        if (int e = launch_pcg(h, !affine_avg, d_par, stride, m, tol, maxit, (w_out && !adj) ? h->d_pw[b].p : nullptr,
                                d_qoi ? d_qoi + (size_t)s0 * nobs : nullptr, d_iters ? d_iters + s0 : nullptr,
                                d_status ? d_status + s0 : nullptr, d_relres ? d_relres + s0 : nullptr, st,
                                adj ? &a : nullptr))
@@ -1039,6 +1053,15 @@ static int fom_common(tfin_handle_t h, bool nodal_op, const double* in, int64_t 
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     if (nodal_op && mem == TFIN_MEM_HOST && h->small_ok && h->host_chunk > 0 && N > h->host_chunk)
         return fom_nodal_host_pipelined(h, in, N, tol, maxit, w_out, qoi_out, iters_out, status_out, relres_out, st);
+    if (!nodal_op && in_kind == TFIN_IN_NODAL && mem == TFIN_MEM_HOST && h->small_ok && h->precision == 64 &&
+        h->pcg_path != 2 && h->W <= 4 && h->n <= 4096 && h->host_chunk > 0 && N > h->host_chunk) {
+        // AffineROMFin.forward(k) from host fields: same pipeline, sub-fin averaging + affine kernel per chunk.  (Only
+        // where an on-chip variant is certain to exist; other meshes take the single-shot path with its fallbacks.)
+        if (h->n_avg != h->n_terms - 1)
+            return fail(TFIN_E_STATE, "nodal input needs tfin_set_averaging with %d rows", h->n_terms - 1);
+        return fom_nodal_host_pipelined(h, in, N, tol, maxit, w_out, qoi_out, iters_out, status_out, relres_out, st,
+                                        nullptr, nullptr, true);
+    }
     Staged sg{h, st, mem == TFIN_MEM_HOST};
     const int nparam = h->n_terms - 1;
     const bool nodal_in = nodal_op || in_kind == TFIN_IN_NODAL;

@@ -632,6 +632,23 @@ def test_pipelined_host_path_is_bit_identical(fin_m3):
         h.set_int("host_chunk", 8192)
 
 
+def test_pipelined_affine_nodal_input(rom_m3):
+    """AffineROMFin.forward(k) from host fields: sub-fin averaging + affine kernel per pipelined chunk, bit-identical."""
+    rng = np.random.default_rng(52)
+    k = np.exp(0.3 * rng.standard_normal((11, rom_m3.dofs)))
+    h = rom_m3.handle
+    try:
+        h.set_int("host_chunk", 0)
+        ref = h.fom_affine(k, 1, want_w=True)
+        for chunk in (3, 4, 10):
+            h.set_int("host_chunk", chunk)
+            out = h.fom_affine(k, 1, want_w=True)
+            for key in ("w", "qoi", "iters", "status", "relres"):
+                assert np.array_equal(out[key], ref[key]), (chunk, key)
+    finally:
+        h.set_int("host_chunk", 8192)
+
+
 def test_sampler_ops_perform_protocol(space_m2, oracle_m2):
     """Theano-style ``perform(node, inputs, outputs)`` shims: ParamToObsFOM (inference.py:21-57, exp(k) model) and
     SqErrorOpFOM / SqErrorOpROM (pymc_func_bayes_inverse.py:106-151), single proposal and a batch of chains."""
