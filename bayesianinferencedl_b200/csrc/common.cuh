@@ -146,6 +146,13 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// D (8x8) += A (8x4, row) * B (4x8, col) on the FP64 tensor path (DMMA).  Lane l = 4 g + t holds A[g][t], B[t][g] and
+// C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
 #endif  // __CUDACC__
 
 }  // namespace tfin

@@ -169,8 +169,9 @@ __global__ void __launch_bounds__(256) field_normal_kernel(unsigned long long se
 
 // ------------------------------------------------------------------------------------------- F4 sampler
 // K[s][j] = exp(0.5 * sum_{i <= j} Z[s][i] L[j][i]):  fp64 "NT" GEMM restricted to the lower triangle, exp fused in
-// the epilogue.  128 x 64 tile, BK = 8, 256 threads x (8 x 4): three 16-byte shared loads feed 32 FMAs; operands are
-// stored k-major in shared memory and the next k-slab is prefetched into registers while the current one is consumed.
+// the epilogue, on the FP64 tensor cores (DMMA m8n8k4).  128 x 64 tile, BK = 8, 8 warps x (32 x 32): 4 + 4 shared loads
+// feed 16 MMAs per k-step of 4; operands are stored k-major in shared memory and the next k-slab is prefetched into
+// registers while the current one is consumed.
 constexpr int FS_BM = 128, FS_BN = 64, FS_BK = 8;
 
 __global__ void __launch_bounds__(256) field_sample_kernel(const double* __restrict__ Z, long long N, int n,
@@ -199,11 +200,14 @@ __global__ void __launch_bounds__(256) field_sample_kernel(const double* __restr
 #pragma unroll
         for (int q = 0; q < 2; ++q) Bs[buf][bk + q][br] = rb[q];
     };
-    double acc[8][4];
+    // warp (wm, wn) of the 4 x 2 warp grid owns 32 samples x 32 columns = 4 x 4 DMMA blocks; the row strides of As / Bs
+    // (132, 68) are 4 (mod 16) doubles, so the one-element-per-lane fragment loads are bank-conflict free
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3, wm = warp >> 1, wn = warp & 1;
+    double acc[4][4][2];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
     fetch(0);
     stash(0);
     __syncthreads();
@@ -211,27 +215,29 @@ __global__ void __launch_bounds__(256) field_sample_kernel(const double* __restr
         const int buf = slab & 1;
         if (slab + 1 < nslab) fetch(slab + 1);
 #pragma unroll
-        for (int k = 0; k < FS_BK; ++k) {
-            const double4 a0 = *reinterpret_cast<const double4*>(&As[buf][k][8 * ty]);
-            const double4 a1 = *reinterpret_cast<const double4*>(&As[buf][k][8 * ty + 4]);
-            const double4 b4 = *reinterpret_cast<const double4*>(&Bs[buf][k][4 * tx]);
-            const double av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int k0 = 0; k0 < FS_BK; k0 += 4) {
+            double a[4], b[4];
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int mb = 0; mb < 4; ++mb) a[mb] = As[buf][k0 + t][32 * wm + 8 * mb + g];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+            for (int nb = 0; nb < 4; ++nb) b[nb] = Bs[buf][k0 + t][32 * wn + 8 * nb + g];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
         }
         if (slab + 1 < nslab) stash(buf ^ 1);
         __syncthreads();
     }
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const long long s = s0 + 8 * ty + a;
+    for (int mb = 0; mb < 4; ++mb) {
+        const long long s = s0 + 32 * wm + 8 * mb + g;
         if (s >= N) continue;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int j = j0 + 4 * tx + b;
-            if (j < n) K[s * n + j] = exp(0.5 * acc[a][b]);
+        for (int nb = 0; nb < 4; ++nb) {
+            const int j = j0 + 32 * wn + 8 * nb + 2 * t;
+            if (j < n) K[s * n + j] = exp(0.5 * acc[mb][nb][0]);
+            if (j + 1 < n) K[s * n + j + 1] = exp(0.5 * acc[mb][nb][1]);
         }
     }
 }

@@ -29,14 +29,6 @@ __host__ __device__ inline size_t rom_combine_smem(int n_terms) {
     return (size_t)rom_combine_k4(n_terms) * (ROM_LDA + 2 * ROM_LDB) * sizeof(double);
 }
 
-// D (8x8) += A (8x4, row) * B (4x8, col) on the FP64 tensor path (DMMA).  Lane l = 4 g + t holds A[g][t], B[t][g] and
-// C[g][2t], C[g][2t+1].
-__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
 // ------------------------------------------------------------------------------------------- R1
 // C[s][t] = sum_pq coef[s][pq] * S[pq][t],  coef[s][(p,q)] = th_p th_q -- the one real dense contraction of the path, on
 // the FP64 tensor cores (mma.sync m8n8k4, the only FP64 tensor instruction of sm_100a).  One CTA owns 64 samples and
