@@ -220,6 +220,8 @@ def run_b200(args):
                "sample": f"first {args.cpu_fom_sample} samples of the FOM workload: oracle port of the reference "
                          f"path (numpy assembly + scipy splu + B_obs), {pool.cores} single-threaded processes, "
                          f"{dt_f:.1f} s",
+               "reference_published": "the reference publishes no benchmark; its stored notebook outputs show ~7.4 FOM "
+                                      "solves/s (MUQ chain, 1 CPU process) and 13.6-14.4 it/s (PyMC3 Metropolis), BASELINE.md",
                "rom_value": args.cpu_rom_sample / dt_r,
                "rom_sample": f"first {args.cpu_rom_sample} ROM samples, literal averaged_affine_ROM.py:292-304 "
                              f"(A phi, psi^T psi, np.linalg.solve), {dt_r:.1f} s"}
