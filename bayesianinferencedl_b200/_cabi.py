@@ -57,6 +57,10 @@ SIGNATURES = {
                                   C.c_double, C.c_uint64, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfin_subfin_avg": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "tfin_frontal_analyze": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tfin_frontal_array": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "tfin_frontal_free": (None, [C.c_void_p]),
     "tfin_kernel_launches": (C.c_int64, [_handle]),
     "tfin_get_int": (C.c_int64, [_handle, C.c_char_p]),
     "tfin_set_int": (C.c_int, [_handle, C.c_char_p, C.c_int64]),

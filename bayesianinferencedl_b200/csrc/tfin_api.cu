@@ -16,6 +16,8 @@
 #include "rom_nodal.cuh"
 #include "field.cuh"
 #include "chains.cuh"
+#include "frontal_host.h"
+#include "frontal.cuh"
 
 using namespace tfin;
 
@@ -125,6 +127,40 @@ static void align_ell_slots(int n, int W, const int32_t* col_idx, std::vector<st
     }
 }
 
+// Device copy of one frontal program (frontal_host.h) -- the sparse-direct solver D1 / D2.
+struct FrontalSet {
+    bool ok = false;
+    std::string why = "no operator";
+    FrontalProgram host;
+    FrontalStreams streams;
+    int ncv = 0;
+    DevBuf<unsigned char> fwd, bwd;
+    void release() {
+        fwd.release();
+        bwd.release();
+        ok = false;
+    }
+    // (re)pack the instruction streams from the host program and copy them to the device
+    int upload(cudaStream_t st) {
+        frontal_pack_streams(host, &streams);
+        if (int e = fwd.upload(streams.fwd, st)) return e;
+        return bwd.upload(streams.bwd, st);
+    }
+    FrontalDev dev() const {
+        FrontalDev d{};
+        d.n = host.n;
+        d.nslots = host.nslots;
+        d.cmax = host.cmax;
+        d.ncv = ncv;
+        d.ntri = host.nslots * (host.nslots + 1) / 2;
+        d.ring_bytes = streams.ring_bytes;
+        d.nnzL = host.nnzL;
+        d.fwd = fwd.p;
+        d.bwd = bwd.p;
+        return d;
+    }
+};
+
 struct tfin_ctx {
     int device = 0;
     int sm_count = 0;
@@ -197,6 +233,17 @@ struct tfin_ctx {
     int64_t host_chunk = 8192;  // samples per pipelined chunk (0 disables the pipeline)
     DevBuf<int> d_iters, d_status;
     DevBuf<unsigned long long> d_counter;
+    // ---- sparse-direct solver (D1 / D2): programs of the affine and of the nodal operator, workspaces, knobs
+    FrontalSet fr_aff, fr_nod;
+    std::vector<int32_t> h_obs_ptr, h_obs_idx;
+    std::vector<double> h_obs_val;
+    DevBuf<double> d_fwork, d_fcv;
+    int fom_solver = 0;      // 0 auto (direct where the front fits on chip), 1 PCG, 2 direct
+    int frontal_kernel = 0;  // 0 auto, 1 = D1 (sample per thread), 2 = D2 (sample per CTA)
+    int frontal_threads = 0; // D2 threads per CTA, 0 = auto
+    int frontal_mode = -1;   // D2: -1 auto, 0 = QOI (extra right-hand sides), 1 = SOLVE (factor to HBM + backward)
+    int last_solver = 0, last_fkernel = 0, last_fthreads = 0, last_focc = 0;
+    size_t last_fsmem = 0;
     // ---- tuning
     int pcg_R = 0;    // rows per thread, 0 = auto
     int pcg_WR = -1;  // -1 auto, 0 = ELL values in shared memory, 1 = in registers
@@ -273,6 +320,10 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
         if (h->ev_comp[b]) cudaEventDestroy(h->ev_comp[b]);
         if (h->ev_out[b]) cudaEventDestroy(h->ev_out[b]);
     }
+    h->fr_aff.release();
+    h->fr_nod.release();
+    h->d_fwork.release();
+    h->d_fcv.release();
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -410,7 +461,35 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
         if (int e = h->d_sperm.upload(perm, h->stream)) return e;
     }
     TFIN_CUDA(cudaStreamSynchronize(h->stream));
-    h->n_cells = 0;  // a new operator invalidates the nodal structures
+    // a new operator invalidates everything that was indexed by the previous one
+    h->n_cells = 0;
+    h->n_obs = 0;
+    h->n_avg = 0;
+    h->b_nr = 0;
+    h->n_r = 0;
+    h->rg_ob = 0;
+    h->f_n = 0;
+    h->h_obs_ptr.clear();
+    h->fr_nod.release();
+    h->fr_nod.why = "tfin_set_cells not called";
+    // sparse-direct solver: symbolic analysis of the shared pattern, affine terms as the assembly list
+    h->fr_aff.release();
+    {
+        const int32_t nnz_ = nnz;
+        auto terms = [&](int e, std::vector<FrontalTermEntry>& out) {
+            for (int t = 0; t < n_terms; ++t) {
+                const double v = vals[(size_t)t * nnz_ + e];
+                if (v != 0.0) out.push_back(FrontalTermEntry{t, v});
+            }
+        };
+        h->fr_aff.why = frontal_build(n, row_ptr, col_idx, rhs, terms, &h->fr_aff.host);
+        if (h->fr_aff.why.empty()) {
+            h->fr_aff.ncv = n_terms;
+            if (int e = h->fr_aff.upload(h->stream)) return e;
+            TFIN_CUDA(cudaStreamSynchronize(h->stream));
+            h->fr_aff.ok = true;
+        }
+    }
     return 0;
 }
 
@@ -461,6 +540,15 @@ extern "C" int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_
     if (int e = upload_csr(h, "tfin_set_observation", n_obs, ptr, idx, val, h->d_obs_ptr, h->d_obs_idx, h->d_obs_val))
         return e;
     h->n_obs = n_obs;
+    h->h_obs_ptr.assign(ptr, ptr + n_obs + 1);
+    h->h_obs_idx.assign(idx, idx + ptr[n_obs]);
+    h->h_obs_val.assign(val, val + ptr[n_obs]);
+    for (FrontalSet* fs : {&h->fr_aff, &h->fr_nod})
+        if (fs->ok) {
+            frontal_set_obs(fs->host, n_obs, ptr, idx, val);
+            if (int e = fs->upload(h->stream)) return e;
+            TFIN_CUDA(cudaStreamSynchronize(h->stream));
+        }
     // B_obs^T as CSR over the n dofs: right-hand sides of the adjoint solves
     if (int e = upload_csr_transpose(h, n_obs, ptr, idx, val, h->d_obsT_ptr, h->d_obsT_idx, h->d_obsT_val)) return e;
     if (h->stream_ok) {  // the streaming path works in its own row numbering
@@ -487,8 +575,6 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
     CHECK_HANDLE(h);
     if (h->n <= 0) return fail(TFIN_E_STATE, "tfin_set_cells: call tfin_set_operator first");
     if (n_cells <= 0 || !cells || !Ke) return fail(TFIN_E_ARG, "tfin_set_cells: bad argument");
-    if (!h->small_ok)
-        return fail(TFIN_E_STATE, "tfin_set_cells: the nodal-conductivity kernel is on-chip only (n <= 8191), n = %d", h->n);
     const int n = h->n, ld = h->ld;
     const std::vector<int32_t>& rp = h->h_row_ptr;
     const std::vector<int32_t>& ci = h->h_col_idx;
@@ -513,6 +599,41 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
                 if (j < 0) return fail(TFIN_E_ARG, "tfin_set_cells: entry (%d,%d) not in the operator pattern", r, c);
                 contrib[j].push_back({e, Ke[9 * (size_t)e + 3 * a + b]});
             }
+    // sparse-direct solver: same pattern, assembly list = constant (Robin) part + cell contributions
+    h->fr_nod.release();
+    {
+        auto terms = [&](int e, std::vector<FrontalTermEntry>& out) {
+            if (h->h_const[e] != 0.0) out.push_back(FrontalTermEntry{0, h->h_const[e]});
+            for (auto& pc : contrib[e])
+                if (pc.second != 0.0) out.push_back(FrontalTermEntry{1 + pc.first, pc.second});
+        };
+        std::vector<double> rhs_host(n);
+        TFIN_CUDA(cudaMemcpy(rhs_host.data(), h->d_rhs.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        h->fr_nod.why = frontal_build(n, rp.data(), ci.data(), rhs_host.data(), terms, &h->fr_nod.host);
+        if (h->fr_nod.why.empty()) {
+            h->fr_nod.ncv = n_cells + 1;
+            if (!h->h_obs_ptr.empty())
+                frontal_set_obs(h->fr_nod.host, h->n_obs, h->h_obs_ptr.data(), h->h_obs_idx.data(), h->h_obs_val.data());
+            if (int e = h->fr_nod.upload(h->stream)) return e;
+            TFIN_CUDA(cudaStreamSynchronize(h->stream));
+            h->fr_nod.ok = true;
+        }
+    }
+    {
+        std::vector<int> cl(cells, cells + 3 * (size_t)n_cells);
+        if (int e = h->d_cells.upload(cl, h->stream)) return e;
+        std::vector<double> ke(Ke, Ke + 9 * (size_t)n_cells);
+        if (int e = h->d_Ke.upload(ke, h->stream)) return e;
+        TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    if (!h->small_ok) {   // refined meshes: only the direct solver serves the nodal operator
+        if (!h->fr_nod.ok)
+            return fail(TFIN_E_STATE, "tfin_set_cells: n = %d is beyond the on-chip PCG (n <= 8191) and the direct solver is unavailable: %s",
+                        h->n, h->fr_nod.why.c_str());
+        h->Wn = 0;
+        h->n_cells = n_cells;
+        return 0;
+    }
     std::vector<std::vector<int>> keep(n);
     std::vector<int> diag_pos(n, -1);
     int W = 0;
@@ -864,6 +985,162 @@ static int launch_pcg_stream(tfin_ctx* h, const double* d_in, int in_stride, int
     return 0;
 }
 
+// ---- sparse-direct solver (frontal.cuh).  Geometry of the kernel that would serve this operator; kernel = 0 if none.
+static const void* frontal_lane_fn(int cmax) {
+    return cmax <= 8 ? (const void*)frontal_lane_kernel<8> : cmax <= 16 ? (const void*)frontal_lane_kernel<16>
+           : cmax <= 24 ? (const void*)frontal_lane_kernel<24> : (const void*)frontal_lane_kernel<32>;
+}
+
+struct FrontalGeom {
+    int kernel = 0;   // 1 = D1 sample per thread, 2 = D2 sample per CTA
+    int mode = 0;     // D2: FRONTAL_MODE_QOI / FRONTAL_MODE_SOLVE
+    int threads = 0, occ = 0;
+    size_t smem = 0;
+    FrontalCtaSmem cta{};
+};
+
+static FrontalGeom frontal_geom(tfin_ctx* h, bool nodal, bool want_w) {
+    FrontalGeom g;
+    const FrontalSet& fs = nodal ? h->fr_nod : h->fr_aff;
+    if (!fs.ok) return g;
+    const FrontalProgram& P = fs.host;
+    const int ntri = P.nslots * (P.nslots + 1) / 2;
+    const int ncv_smem = nodal ? 0 : fs.ncv;
+    const int ring = fs.streams.ring_bytes;
+    if (h->frontal_kernel != 2 && P.cmax <= 32) {
+        const void* fn = frontal_lane_fn(P.cmax);
+        const size_t sm = frontal_lane_smem(ntri, P.nslots, h->n_obs, ncv_smem, ring);
+        if (sm <= (size_t)h->max_smem_optin &&
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess) {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, sm) == cudaSuccess && occ >= 1) {
+                g.kernel = 1;
+                g.threads = 32;
+                g.occ = occ;
+                g.smem = sm;
+                return g;
+            }
+        }
+        cudaGetLastError();
+    }
+    if (h->frontal_kernel == 1) return g;
+    // D2: observables-only mode unless the solution is wanted (or there are too many observation rows to carry along)
+    int mode = (want_w || h->n_obs > 16) ? FRONTAL_MODE_SOLVE : FRONTAL_MODE_QOI;
+    if (h->frontal_mode == 0 && !want_w) mode = FRONTAL_MODE_QOI;
+    if (h->frontal_mode == 1) mode = FRONTAL_MODE_SOLVE;
+    const int R = mode == FRONTAL_MODE_QOI ? 1 + h->n_obs : 1;
+    const FrontalCtaSmem L = FrontalCtaSmem::make(ntri, P.nslots, std::max(P.cmax, 1), R, std::max(h->n_obs, 1), ncv_smem, ring);
+    if (L.total + 64 > (size_t)h->max_smem_optin) return g;
+    int T = h->frontal_threads;
+    if (T <= 0) {
+        const double pairs = 0.5 * P.cmax * (P.cmax + 1.0);
+        T = 32 * (int)std::min(16.0, std::max(1.0, std::ceil(pairs / (32.0 * 12.0))));
+    }
+    T = std::max(32, std::min(1024, (T + 31) & ~31));
+    const void* fn = mode == FRONTAL_MODE_QOI ? (const void*)frontal_cta_kernel<FRONTAL_MODE_QOI>
+                                              : (const void*)frontal_cta_kernel<FRONTAL_MODE_SOLVE>;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
+        cudaGetLastError();
+        return g;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, T, L.total) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return g;
+    }
+    g.kernel = 2;
+    g.mode = mode;
+    g.threads = T;
+    g.occ = occ;
+    g.smem = L.total;
+    g.cta = L;
+    return g;
+}
+
+// d_in: theta (N, in_stride) for the affine operator, nodal fields k (N, n) for the nodal one.
+static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const double* d_in, int in_stride, int64_t N,
+                          double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres, cudaStream_t st) {
+    FrontalSet& fs = nodal ? h->fr_nod : h->fr_aff;
+    if (!fs.ok || g.kernel == 0)
+        return fail(TFIN_E_STATE, "direct solver unavailable for this operator: %s", fs.ok ? "front does not fit shared memory" : fs.why.c_str());
+    const FrontalProgram& P = fs.host;
+    const FrontalDev dev = fs.dev();
+    const size_t per_sample_work = (size_t)P.nnzL + 2 * (size_t)P.n;
+    // the nodal operator needs the coefficient vector of every sample in HBM: bound that workspace by chunking
+    int64_t chunk = N;
+    if (nodal) {
+        const int64_t cap = std::max<int64_t>(32, ((int64_t)1 << 30) / ((int64_t)fs.ncv * 8) / 32 * 32);
+        chunk = std::min<int64_t>(N, cap);
+        if (int e = h->d_fcv.reserve((size_t)((chunk + 31) / 32 * 32) * fs.ncv)) return e;
+    }
+    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, N - s0);
+        FrontalIO io{};
+        io.in = d_in + (size_t)s0 * in_stride;
+        io.N = m;
+        io.in_stride = in_stride;
+        io.n_obs = h->n_obs;
+        io.w_out = d_w ? d_w + (size_t)s0 * P.n : nullptr;
+        io.qoi_out = d_qoi ? d_qoi + (size_t)s0 * h->n_obs : nullptr;
+        io.iters_out = d_iters ? d_iters + s0 : nullptr;
+        io.status_out = d_status ? d_status + s0 : nullptr;
+        io.relres_out = d_relres ? d_relres + s0 : nullptr;
+        io.counter = h->d_counter.p;
+        if (nodal) {
+            const dim3 cgrid((unsigned)((h->n_cells + 31) / 32), (unsigned)((m + 31) / 32));
+            frontal_cellcoef_kernel<<<cgrid, dim3(32, 8), 0, st>>>(io.in, (long long)m, P.n, h->n_cells, h->d_cells.p,
+                                                                  h->coef_mode, g.kernel == 1 ? 1 : 0, h->d_fcv.p);
+            h->launches += 1;
+            io.cv_global = h->d_fcv.p;
+        }
+        TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
+        if (g.kernel == 1) {
+            const int grid = (int)std::min<int64_t>((m + 31) / 32, (int64_t)h->sm_count * g.occ);
+            if (int e = h->d_fwork.reserve((size_t)grid * per_sample_work * 32)) return e;
+            io.work = h->d_fwork.p;
+            void* args[] = {(void*)&dev, (void*)&io};
+            TFIN_CUDA(cudaLaunchKernel(frontal_lane_fn(P.cmax), dim3(grid), dim3(32), args, g.smem, st));
+        } else {
+            const int grid = (int)std::min<int64_t>(m, (int64_t)h->sm_count * g.occ);
+            if (g.mode == FRONTAL_MODE_SOLVE) {
+                if (int e = h->d_fwork.reserve((size_t)grid * per_sample_work)) return e;
+                io.work = h->d_fwork.p;
+                frontal_cta_kernel<FRONTAL_MODE_SOLVE><<<grid, g.threads, g.smem, st>>>(dev, io, g.cta);
+            } else {
+                frontal_cta_kernel<FRONTAL_MODE_QOI><<<grid, g.threads, g.smem, st>>>(dev, io, g.cta);
+            }
+        }
+        TFIN_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    h->last_solver = 2;
+    h->last_fkernel = g.kernel == 1 ? 1 : (g.mode == FRONTAL_MODE_QOI ? 2 : 3);
+    h->last_fthreads = g.threads;
+    h->last_focc = g.occ;
+    h->last_fsmem = g.smem;
+    h->last_path = 4;
+    return 0;
+}
+
+// Forward solve of one device-resident batch with whichever solver the handle is set to: the sparse-direct kernels where
+// the front fits on chip (fom_solver 0 / 2), else the on-chip PCG.  Adjoint variants exist for the PCG only.
+static int launch_fom(tfin_ctx* h, bool nodal, const double* d_in, int in_stride, int64_t N, double tol, int maxit,
+                      double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres, cudaStream_t st,
+                      const PcgAdj* adjoint = nullptr) {
+    if (!adjoint && h->fom_solver != 1 && h->precision == 64) {
+        const FrontalGeom g = frontal_geom(h, nodal, d_w != nullptr);
+        if (g.kernel != 0)
+            return launch_frontal(h, nodal, g, d_in, in_stride, N, d_w, d_qoi, d_iters, d_status, d_relres, st);
+        if (h->fom_solver == 2) {
+            const FrontalSet& fs = nodal ? h->fr_nod : h->fr_aff;
+            return fail(TFIN_E_STATE, "fom_solver = 2 (direct) but the direct solver is unavailable: %s",
+                        fs.ok ? "front does not fit shared memory" : fs.why.c_str());
+        }
+    }
+    h->last_solver = 1;
+    return launch_pcg(h, nodal, d_in, in_stride, N, tol, maxit, d_w, d_qoi, d_iters, d_status, d_relres, st, adjoint);
+}
+
 static int launch_project(tfin_ctx* h, const CsrRows& op, const double* d_k, int64_t N, double* d_out,
                           cudaStream_t st) {
     const int64_t warps = N * op.rows;
@@ -1018,7 +1295,7 @@ static int fom_nodal_host_pipelined(tfin_ctx* h, const double* k, int64_t N, dou
             d_par = th;
             stride = nparam;
         }
-        if (int e = launch_pcg(h, !affine_avg, d_par, stride, m, tol, maxit, (w_out && !adj) ? h->d_pw[b].p : nullptr,
+        if (int e = launch_fom(h, !affine_avg, d_par, stride, m, tol, maxit, (w_out && !adj) ? h->d_pw[b].p : nullptr,
                                d_qoi ? d_qoi + (size_t)s0 * nobs : nullptr, d_iters ? d_iters + s0 : nullptr,
                                d_status ? d_status + s0 : nullptr, d_relres ? d_relres + s0 : nullptr, st,
                                adj ? &a : nullptr))
@@ -1085,6 +1362,26 @@ static int fom_common(tfin_handle_t h, bool nodal_op, const double* in, int64_t 
     if (int e = sg.out_alloc(iters_out, (size_t)N, h->d_iters, &d_iters)) return e;
     if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
     if (int e = sg.out_alloc(relres_out, (size_t)N, h->d_relres, &d_relres)) return e;
+    // sparse-direct solver first (fom_solver 0 = where available, 2 = required); pcg_path pins a PCG kernel
+    if (h->fom_solver != 1 && h->precision == 64 && (h->pcg_path == 0 || h->fom_solver == 2)) {
+        const FrontalGeom g = frontal_geom(h, nodal_op, d_w != nullptr);
+        if (g.kernel != 0) {
+            if (int e = launch_frontal(h, nodal_op, g, d_par, stride, N, d_w, d_qoi, d_iters, d_status, d_relres, st)) return e;
+            if (int e = sg.out_copy(w_out, (size_t)N * h->n, d_w)) return e;
+            if (int e = sg.out_copy(qoi_out, (size_t)N * h->n_obs, d_qoi)) return e;
+            if (int e = sg.out_copy(iters_out, (size_t)N, d_iters)) return e;
+            if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
+            if (int e = sg.out_copy(relres_out, (size_t)N, d_relres)) return e;
+            if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+            return 0;
+        }
+        if (h->fom_solver == 2) {
+            const FrontalSet& fs = nodal_op ? h->fr_nod : h->fr_aff;
+            return fail(TFIN_E_STATE, "fom_solver = 2 (direct) but the direct solver is unavailable: %s",
+                        fs.ok ? "front does not fit shared memory" : fs.why.c_str());
+        }
+    }
+    h->last_solver = 1;
     bool use_stream = !nodal_op && (h->pcg_path == 2 || (h->pcg_path == 0 && !h->small_ok));
     if (!use_stream && !h->small_ok)
         return fail(TFIN_E_STATE, "on-chip PCG needs n <= 8191 (n = %d); use the streaming path", h->n);
@@ -1693,6 +1990,17 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
     if (k == "pcg_reg_slots") return h->last_WR;
     if (k == "rom_chunk") return h->rom_chunk;
     if (k == "pcg_path") return h->last_path;
+    if (k == "fom_solver") return h->last_solver;          // solver of the last forward solve: 1 PCG, 2 direct
+    if (k == "frontal_kernel") return h->last_fkernel;     // 1 = D1, 2 = D2 observables mode, 3 = D2 solve mode
+    if (k == "frontal_threads") return h->last_fthreads;
+    if (k == "frontal_ctas_per_sm") return h->last_focc;
+    if (k == "frontal_smem_bytes") return (int64_t)h->last_fsmem;
+    if (k == "frontal_ok") return h->fr_aff.ok ? 1 : 0;
+    if (k == "frontal_nodal_ok") return h->fr_nod.ok ? 1 : 0;
+    if (k == "frontal_slots") return h->fr_aff.ok ? h->fr_aff.host.nslots : -1;
+    if (k == "frontal_cmax") return h->fr_aff.ok ? h->fr_aff.host.cmax : -1;
+    if (k == "frontal_nnz_factor") return h->fr_aff.ok ? h->fr_aff.host.nnzL : -1;
+    if (k == "frontal_pair_updates") return h->fr_aff.ok ? (int64_t)h->fr_aff.host.pair_updates : -1;
     if (k == "nodal_coef_mode") return h->coef_mode;
     if (k == "pcg_precision") return h->precision;
     if (k == "stream_tile") return h->last_tile;
@@ -1732,6 +2040,25 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
         h->pcg_path = (int)value;
         return 0;
     }
+    if (k == "fom_solver") {
+        if (value < 0 || value > 2) return fail(TFIN_E_ARG, "fom_solver must be 0 (auto), 1 (PCG) or 2 (direct)");
+        h->fom_solver = (int)value;
+        return 0;
+    }
+    if (k == "frontal_kernel") {
+        if (value < 0 || value > 2) return fail(TFIN_E_ARG, "frontal_kernel must be 0 (auto), 1 (D1) or 2 (D2)");
+        h->frontal_kernel = (int)value;
+        return 0;
+    }
+    if (k == "frontal_threads") {
+        h->frontal_threads = (int)value;
+        return 0;
+    }
+    if (k == "frontal_mode") {
+        if (value < -1 || value > 1) return fail(TFIN_E_ARG, "frontal_mode must be -1 (auto), 0 (observables) or 1 (solve)");
+        h->frontal_mode = (int)value;
+        return 0;
+    }
     if (k == "host_chunk") {
         if (value < 0) return fail(TFIN_E_ARG, "host_chunk must be >= 0");
         h->host_chunk = value;
@@ -1765,3 +2092,62 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
     }
     return fail(TFIN_E_ARG, "tfin_set_int: unknown key '%s'", key);
 }
+
+// ------------------------------------------------------------------------------------------------ diagnostics
+// Host-only view of the symbolic phase of the direct solver (no device needed): tests interpret the program on the CPU.
+struct tfin_frontal_program {
+    FrontalProgram P;
+};
+
+extern "C" int tfin_frontal_analyze(int32_t n, int32_t nnz, const int32_t* row_ptr, const int32_t* col_idx, int32_t n_terms,
+                                    const double* vals, const double* rhs, int32_t n_obs, const int32_t* obs_ptr,
+                                    const int32_t* obs_idx, const double* obs_val, void** out) {
+    if (n <= 0 || nnz <= 0 || !row_ptr || !col_idx || !vals || !rhs || !out || n_terms < 1)
+        return fail(TFIN_E_ARG, "tfin_frontal_analyze: bad argument");
+    auto* fp = new tfin_frontal_program();
+    auto terms = [&](int e, std::vector<FrontalTermEntry>& o) {
+        for (int t = 0; t < n_terms; ++t) {
+            const double v = vals[(size_t)t * nnz + e];
+            if (v != 0.0) o.push_back(FrontalTermEntry{t, v});
+        }
+    };
+    const std::string why = frontal_build(n, row_ptr, col_idx, rhs, terms, &fp->P);
+    if (!why.empty()) {
+        delete fp;
+        return fail(TFIN_E_STATE, "tfin_frontal_analyze: %s", why.c_str());
+    }
+    if (n_obs > 0 && obs_ptr && obs_idx && obs_val) frontal_set_obs(fp->P, n_obs, obs_ptr, obs_idx, obs_val);
+    *out = fp;
+    return 0;
+}
+
+extern "C" int64_t tfin_frontal_array(void* prog, const char* name, void* dst, int64_t dst_bytes) {
+    if (!prog || !name) return -1;
+    const FrontalProgram& P = static_cast<tfin_frontal_program*>(prog)->P;
+    const std::string k(name);
+    auto give = [&](const void* src, size_t bytes) -> int64_t {
+        if (dst && (int64_t)bytes <= dst_bytes) std::memcpy(dst, src, bytes);
+        return (int64_t)bytes;
+    };
+    if (k == "n") return P.n;
+    if (k == "nslots") return P.nslots;
+    if (k == "cmax") return P.cmax;
+    if (k == "nnzL") return P.nnzL;
+    if (k == "pair_updates") return (int64_t)P.pair_updates;
+    if (k == "perm") return give(P.perm.data(), P.perm.size() * 4);
+    if (k == "piv_slot") return give(P.piv_slot.data(), P.piv_slot.size() * 2);
+    if (k == "col_ptr") return give(P.col_ptr.data(), P.col_ptr.size() * 4);
+    if (k == "col_slot") return give(P.col_slot.data(), P.col_slot.size() * 2);
+    if (k == "rhs") return give(P.rhs.data(), P.rhs.size() * 8);
+    if (k == "asm_ptr") return give(P.asm_ptr.data(), P.asm_ptr.size() * 4);
+    if (k == "asm_addr") return give(P.asm_addr.data(), P.asm_addr.size() * 4);
+    if (k == "asm_eptr") return give(P.asm_eptr.data(), P.asm_eptr.size() * 4);
+    if (k == "ent_term") return give(P.ent_term.data(), P.ent_term.size() * 4);
+    if (k == "ent_coef") return give(P.ent_coef.data(), P.ent_coef.size() * 8);
+    if (k == "obs_ptr") return give(P.obs_ptr.data(), P.obs_ptr.size() * 4);
+    if (k == "obs_row") return give(P.obs_row.data(), P.obs_row.size() * 4);
+    if (k == "obs_val") return give(P.obs_val.data(), P.obs_val.size() * 8);
+    return -1;
+}
+
+extern "C" void tfin_frontal_free(void* prog) { delete static_cast<tfin_frontal_program*>(prog); }

@@ -239,6 +239,22 @@ int tfin_pcn_chains(tfin_handle_t h, int32_t model, int64_t C, int64_t first_cha
 int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double* theta_out,
                     void* stream);
 
+/*
+ * Diagnostics of the sparse-direct solver (host only, no device needed).  The direct solve replaces dolfin's default
+ * sparse LU (fom/forward_solve.py:286, rom/averaged_affine_ROM.py:256): the symbolic phase (ordering, elimination tree,
+ * fill, front storage) is shared by all samples and compiled into a per-pivot program that the kernels interpret.
+ * tfin_frontal_analyze runs that phase for an affine operator given like tfin_set_operator (+ optional B_obs CSR) and
+ * returns an opaque program; tfin_frontal_array copies one of its arrays ("perm", "piv_slot", "col_ptr", "col_slot",
+ * "rhs", "asm_ptr", "asm_addr", "asm_eptr", "ent_term", "ent_coef", "obs_ptr", "obs_row", "obs_val") into dst if
+ * dst_bytes suffices and returns its size in bytes, or the value of a scalar ("n", "nslots", "cmax", "nnzL",
+ * "pair_updates"); -1 for an unknown name.  tests/frontal_emulator.py interprets the program on the CPU.
+ */
+int tfin_frontal_analyze(int32_t n, int32_t nnz, const int32_t* row_ptr, const int32_t* col_idx, int32_t n_terms,
+                         const double* vals, const double* rhs, int32_t n_obs, const int32_t* obs_ptr,
+                         const int32_t* obs_idx, const double* obs_val, void** out);
+int64_t tfin_frontal_array(void* prog, const char* name, void* dst, int64_t dst_bytes);
+void tfin_frontal_free(void* prog);
+
 /* Number of CUDA kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t tfin_kernel_launches(tfin_handle_t h);
 
@@ -247,6 +263,11 @@ int64_t tfin_kernel_launches(tfin_handle_t h);
 int64_t tfin_get_int(tfin_handle_t h, const char* key);
 
 /* Knobs (before the next solve call): "pcg_rows_per_thread" (0 = auto), "rom_chunk", "pcg_path", "stream_tile" ...;
+ * "fom_solver": 0 (default) = sparse-direct frontal Cholesky wherever the active front fits in shared memory, PCG
+ * otherwise; 1 = always PCG (tol / maxit apply); 2 = direct required (fails if unavailable).  With the direct solver
+ * tol / maxit are ignored, iters_out is 0 and relres_out is the consistency |b.w - y.y| / y.y of the two substitutions
+ * (0 in the observables-only mode of the wide-front kernel, which has no backward substitution);
+ * "frontal_kernel" (0 auto, 1 = sample per thread, 2 = sample per CTA), "frontal_threads", "frontal_mode";
  * "nodal_coef_mode": 0 = conductivity k (fom/forward_solve.py:160), 1 = conductivity exp(k) integrated with the
  * degree-3 rule of dolfin's form compiler (fom/forward_solve_exp.py:160) in tfin_fom_nodal / tfin_rom_nodal /
  * tfin_pcn_chains(model 0), and the gradient form k_hat exp(k) grad z . grad v with its degree-4 rule (:299, :328) in

@@ -44,17 +44,29 @@ def test_config1_five_param_single(rom_m3, oracle_m3, pod_m3):
     assert relerr(q_r, q_r_ref) <= RTOL_ROM
 
 
-def test_affine_fom_batch_vs_oracle(rom_m3, oracle_m3):
+@pytest.mark.parametrize("solver", ["direct", "pcg"])
+def test_affine_fom_batch_vs_oracle(rom_m3, oracle_m3, solver):
+    """Affine FOM (AffineROMFin.forward_nine_param + qoi) with the default sparse-direct solver (D1) and with the
+    on-chip Jacobi-PCG (K1, fom_solver = 1)."""
     rng = np.random.default_rng(11)
     theta = rng.uniform(0.1, 3.5, (24, 9))
-    q, stats = rom_m3.forward_nine_param_qoi(theta, return_stats=True)
+    h = rom_m3.handle
+    h.set_int("fom_solver", 1 if solver == "pcg" else 0)
+    try:
+        q, stats = rom_m3.forward_nine_param_qoi(theta, return_stats=True)
+        assert h.get_int("fom_solver") == (1 if solver == "pcg" else 2)
+        w = rom_m3.forward_nine_param(theta[:3])
+    finally:
+        h.set_int("fom_solver", 0)
     assert np.all(stats["status"] == 0)
     assert np.all(stats["relres"] < 1e-10)
-    assert 200 < stats["iters"].mean() < 1000
+    if solver == "pcg":
+        assert 200 < stats["iters"].mean() < 1000
+    else:
+        assert np.all(stats["iters"] == 0) and h.get_int("frontal_kernel") == 1
     for s in range(len(theta)):
         ref = oracle_m3.qoi_operator(oracle_m3.forward_nine_param(theta[s]))
         assert relerr(q[s], ref) <= RTOL_FOM, s
-    w = rom_m3.forward_nine_param(theta[:3])
     for s in range(3):
         w_ref = oracle_m3.forward_nine_param(theta[s])
         assert np.max(np.abs(w[s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref))
@@ -156,8 +168,12 @@ def test_edge_cases(rom_m3, fin_m3):
         fin_m3.forward(np.ones(fin_m3.dofs + 1))
     with pytest.raises(RuntimeError):
         rom_m3.forward_nine_param(-np.ones(9))       # not SPD -> breakdown reported, not silently wrong
-    # maxit cap is reported per sample
-    out = rom_m3.handle.fom_affine(np.ones((2, 9)), maxit=5)
+    # maxit cap of the PCG path is reported per sample
+    rom_m3.handle.set_int("fom_solver", 1)
+    try:
+        out = rom_m3.handle.fom_affine(np.ones((2, 9)), maxit=5)
+    finally:
+        rom_m3.handle.set_int("fom_solver", 0)
     assert np.all(out["status"] == 1) and np.all(out["iters"] == 5)
 
 
@@ -189,7 +205,11 @@ def test_stream_kernel_matches_onchip_and_oracle(rom_m3, oracle_m3, tile, ring):
     rng = np.random.default_rng(31)
     theta = rng.uniform(0.1, 10.0, (70, 9))
     h = rom_m3.handle
-    ref = h.fom_affine(theta)
+    h.set_int("fom_solver", 1)
+    try:
+        ref = h.fom_affine(theta)
+    finally:
+        h.set_int("fom_solver", 0)
     try:
         h.set_int("pcg_path", 2)
         h.set_int("stream_tile", tile)
@@ -210,7 +230,8 @@ def test_stream_kernel_matches_onchip_and_oracle(rom_m3, oracle_m3, tile, ring):
 
 
 def test_stream_kernel_refined_mesh():
-    """n = 10 017 (m = 8) exceeds the on-chip limit -> the streaming kernel is selected automatically."""
+    """n = 10 017 (m = 8) exceeds the on-chip PCG limit -> with fom_solver = 1 the streaming kernel is selected
+    automatically."""
     from bayesianinferencedl_b200 import _cabi, get_space
     from bayesianinferencedl_b200.assembly import build_operators
     from oracle.thermal_fin_oracle import FinOracle
@@ -222,8 +243,9 @@ def test_stream_kernel_refined_mesh():
     h.set_observation(*ops.obs_csr())
     rng = np.random.default_rng(2)
     theta = rng.uniform(0.1, 10.0, (12, 9))
+    h.set_int("fom_solver", 1)
     out = h.fom_affine(theta, want_w=True)
-    assert h.get_int("pcg_path") == 2
+    assert h.get_int("pcg_path") == 2 and h.get_int("fom_solver") == 1
     assert np.all(out["status"] == 0)
     orc = FinOracle(ops.coords, ops.cells)
     for s in (0, 5, 11):
@@ -744,8 +766,9 @@ def test_rom_too_many_terms_fails_loudly():
 
 
 def test_mid_size_meshes_pick_a_working_path():
-    """Meshes between the on-chip limit of the compiled variants (~4100 dofs) and the uint16 limit (8191): the affine
-    solve falls back to the streaming kernel automatically; the nodal solve (on-chip only) fails loudly."""
+    """PCG path (fom_solver = 1) on meshes between the on-chip limit of the compiled variants (~4100 dofs) and the uint16
+    limit (8191): the affine solve falls back to the streaming kernel automatically; the nodal PCG (on-chip only) fails
+    loudly.  (The default direct solver serves all of them: test_direct_solver_mid_and_refined_meshes.)"""
     from bayesianinferencedl_b200 import _cabi, get_space
     from bayesianinferencedl_b200.assembly import build_operators
     from oracle.thermal_fin_oracle import FinOracle
@@ -755,6 +778,7 @@ def test_mid_size_meshes_pick_a_working_path():
         h = _cabi.TfinHandle(0)
         h.set_operator(ops.row_ptr, ops.col_idx, ops.vals, ops.rhs)
         h.set_observation(*ops.obs_csr())
+        h.set_int("fom_solver", 1)
         theta = rng.uniform(0.1, 3.5, (5, 9))
         out = h.fom_affine(theta)
         assert h.get_int("pcg_path") == path and np.all(out["status"] == 0)
@@ -770,3 +794,126 @@ def test_mid_size_meshes_pick_a_working_path():
             with pytest.raises(_cabi.TfinError, match="about 4100"):
                 h.fom_nodal(k)
         h.close()
+
+
+# ------------------------------------------------------------------------------------------------ sparse-direct solver
+def _handle_for(ops, cells=False):
+    from bayesianinferencedl_b200 import _cabi
+    h = _cabi.TfinHandle(0)
+    h.set_operator(ops.row_ptr, ops.col_idx, ops.vals, ops.rhs)
+    h.set_observation(*ops.obs_csr())
+    if cells:
+        h.set_cells(ops.cells, ops.Ke)
+    return h
+
+
+@pytest.mark.parametrize("kernel,mode", [(1, -1), (2, 0), (2, 1)])
+def test_direct_solver_kernels_vs_oracle(space_m2, oracle_m2, kernel, mode):
+    """D1 (sample per thread) and D2 (sample per CTA; observables mode with extra right-hand sides, and solve mode with the
+    factor in HBM) on the same inputs: affine and nodal operators against the oracle's sparse LU; 70 samples = partial
+    last group of 32."""
+    from bayesianinferencedl_b200.assembly import build_operators
+    ops = build_operators(space_m2)
+    h = _handle_for(ops, cells=True)
+    h.set_int("fom_solver", 2)
+    h.set_int("frontal_kernel", kernel)
+    h.set_int("frontal_mode", mode)
+    rng = np.random.default_rng(41)
+    theta = rng.uniform(0.1, 10.0, (70, 9))
+    out = h.fom_affine(theta, want_w=(mode != 0))
+    assert h.get_int("fom_solver") == 2
+    assert h.get_int("frontal_kernel") == (1 if kernel == 1 else (2 if mode == 0 else 3))
+    assert np.all(out["status"] == 0) and np.all(out["iters"] == 0) and np.all(out["relres"] < 1e-12)
+    for s in (0, 31, 32, 69):
+        w_ref = oracle_m2.forward_nine_param(theta[s])
+        assert relerr(out["qoi"][s], oracle_m2.qoi_operator(w_ref)) <= RTOL_FOM, s
+        if mode != 0:
+            assert np.max(np.abs(out["w"][s] - w_ref)) <= 1e-11 * np.max(np.abs(w_ref)), s
+    k = np.exp(0.5 * rng.standard_normal((37, ops.n)))
+    outn = h.fom_nodal(k, want_w=(mode != 0))
+    assert np.all(outn["status"] == 0)
+    for s in (0, 17, 36):
+        w_ref = oracle_m2.forward(k[s])
+        assert relerr(outn["qoi"][s], oracle_m2.qoi_operator(w_ref)) <= RTOL_FOM, s
+        if mode != 0:
+            assert np.max(np.abs(outn["w"][s] - w_ref)) <= 1e-11 * np.max(np.abs(w_ref)), s
+    # a non-SPD sample is reported, not silently wrong, and does not disturb its neighbours
+    bad = theta[:5].copy()
+    bad[2] = -1.0
+    outb = h.fom_affine(bad)
+    assert outb["status"][2] == 2 and np.all(np.delete(outb["status"], 2) == 0)
+    assert np.array_equal(outb["qoi"][[0, 1, 3, 4]], out["qoi"][[0, 1, 3, 4]])
+    h.close()
+
+
+def test_direct_and_pcg_agree_bitwise_on_indexing(rom_m3):
+    """The direct solver's result for a sample does not depend on its position in the batch (lane, group, CTA)."""
+    rng = np.random.default_rng(43)
+    theta = rng.uniform(0.1, 3.5, (333, 9))
+    q1 = rom_m3.forward_nine_param_qoi(theta)
+    assert rom_m3.handle.get_int("fom_solver") == 2
+    perm = rng.permutation(len(theta))
+    assert np.array_equal(q1[perm], rom_m3.forward_nine_param_qoi(theta[perm]))
+    assert np.array_equal(q1[5:6], rom_m3.forward_nine_param_qoi(theta[5:6]))
+    rom_m3.handle.set_int("fom_solver", 1)
+    try:
+        q_pcg = rom_m3.forward_nine_param_qoi(theta)
+    finally:
+        rom_m3.handle.set_int("fom_solver", 0)
+    assert relerr(q_pcg, q1) < 1e-10
+
+
+def test_direct_solver_mid_and_refined_meshes():
+    """Meshes the on-chip PCG could not serve (nodal operator above ~4100 dofs) go through the wide-front kernel D2."""
+    from bayesianinferencedl_b200 import get_space
+    from bayesianinferencedl_b200.assembly import build_operators
+    from oracle.thermal_fin_oracle import FinOracle
+    rng = np.random.default_rng(44)
+    for m in (4, 5, 8):
+        ops = build_operators(get_space(40, m=m))
+        h = _handle_for(ops, cells=True)
+        orc = FinOracle(ops.coords, ops.cells)
+        theta = rng.uniform(0.1, 10.0, (6, 9))
+        out = h.fom_affine(theta, want_w=True)
+        assert h.get_int("fom_solver") == 2 and np.all(out["status"] == 0)
+        k = np.exp(0.3 * rng.standard_normal((5, ops.n)))
+        outn = h.fom_nodal(k, want_w=True)
+        qn = h.fom_nodal(k)["qoi"]
+        assert h.get_int("fom_solver") == 2 and np.all(outn["status"] == 0)
+        for s in (0, 5):
+            w_ref = orc.forward_nine_param(theta[s])
+            assert np.max(np.abs(out["w"][s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref)), (m, s)
+            assert relerr(out["qoi"][s], orc.qoi_operator(w_ref)) <= RTOL_FOM, (m, s)
+        for s in (0, 4):
+            w_ref = orc.forward(k[s])
+            assert np.max(np.abs(outn["w"][s] - w_ref)) <= 1e-10 * np.max(np.abs(w_ref)), (m, s)
+            assert relerr(qn[s], orc.qoi_operator(w_ref)) <= RTOL_FOM, (m, s)
+        h.close()
+
+
+def test_config4_refined_mesh_at_full_size():
+    """BASELINE config 4 at its own size: m = 26, n = 99 945, theta ~ U(0.1, 10)^9.  Direct solver (D2, both modes) and the
+    streaming PCG (K4) against the oracle's sparse LU: observables to 1e-10 relative, w to 1e-10 of its maximum."""
+    from bayesianinferencedl_b200 import get_space
+    from bayesianinferencedl_b200.assembly import build_operators
+    from oracle.thermal_fin_oracle import FinOracle
+    ops = build_operators(get_space(40, m=26))
+    assert ops.n == 99945
+    h = _handle_for(ops)
+    orc = FinOracle(ops.coords, ops.cells)
+    theta = np.random.default_rng(2).uniform(0.1, 10.0, (3, 9))
+    w_ref = [orc.forward_nine_param(t) for t in theta]
+    q_ref = [orc.qoi_operator(w) for w in w_ref]
+    q_direct = h.fom_affine(theta)
+    assert h.get_int("fom_solver") == 2 and h.get_int("frontal_kernel") == 2 and np.all(q_direct["status"] == 0)
+    full = h.fom_affine(theta, want_w=True)
+    assert h.get_int("frontal_kernel") == 3 and np.all(full["status"] == 0) and np.all(full["relres"] < 1e-10)
+    h.set_int("fom_solver", 1)
+    pcg = h.fom_affine(theta, want_w=True)
+    assert h.get_int("pcg_path") == 2 and np.all(pcg["status"] == 0)
+    for s in range(3):
+        for name, out in (("direct qoi", q_direct), ("direct solve", full), ("stream pcg", pcg)):
+            assert relerr(out["qoi"][s], q_ref[s]) <= RTOL_FOM, (name, s)
+        for name, out in (("direct solve", full), ("stream pcg", pcg)):
+            assert np.max(np.abs(out["w"][s] - w_ref[s])) <= 1e-10 * np.max(np.abs(w_ref[s])), (name, s)
+    h.close()
