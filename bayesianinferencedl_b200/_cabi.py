@@ -61,6 +61,7 @@ SIGNATURES = {
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tfin_frontal_array": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "tfin_frontal_free": (None, [C.c_void_p]),
+    "tfin_smem_bandwidth": (C.c_int, [_handle, C.POINTER(C.c_double)]),
     "tfin_kernel_launches": (C.c_int64, [_handle]),
     "tfin_get_int": (C.c_int64, [_handle, C.c_char_p]),
     "tfin_set_int": (C.c_int, [_handle, C.c_char_p, C.c_int64]),
@@ -365,6 +366,12 @@ class TfinHandle:
         rc = self._lib.tfin_rom(self._h, in_ptr, N, in_kind, mem, wr or None, qoi or None, status or None,
                                 stream or None)
         _check(self._lib, rc, "tfin_rom")
+
+    def smem_bandwidth(self):
+        """Measured aggregate shared-memory read bandwidth of the device (GB/s): roofline denominator of the on-chip kernels."""
+        out = C.c_double()
+        _check(self._lib, self._lib.tfin_smem_bandwidth(self._h, C.byref(out)), "tfin_smem_bandwidth")
+        return float(out.value)
 
     # ---- introspection / tuning
     def kernel_launches(self):

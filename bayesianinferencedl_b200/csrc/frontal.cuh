@@ -31,7 +31,8 @@ namespace tfin {
 struct FrontalDev {
     int n, nslots, cmax, ncv;      // ncv = length of the coefficient vector (incl. the leading 1)
     int ntri;                      // nslots (nslots + 1) / 2
-    int ring_bytes;                // power of two >= 2 * largest record + 512
+    int ring_bytes;                // power of two, see frontal_pack_streams
+    int lr_rows;                   // D1: rows of the factor-row ring of the backward substitution
     long long nnzL;
     const unsigned char* fwd;      // forward stream (frontal_host.h: frontal_pack_streams)
     const unsigned char* bwd;      // backward stream
@@ -64,13 +65,13 @@ struct StreamRing {
         fetched = 0;
         rd = 0;
     }
-    // prefetch whole 512-byte chunks while they fit ahead of the reader; `issue` selects the lanes that copy (one warp)
+    // prefetch whole 512-byte chunks while they fit ahead of the reader; `issue` selects the lanes that copy (one warp).
+    // The caller commits the copy group.
     __device__ __forceinline__ void fill(int lane, bool issue) {
         while (fetched + 512u - rd <= mask + 1u) {
             if (issue) cp_async16(buf + ((fetched + lane * 16u) & mask), src + fetched + lane * 16u);
             fetched += 512u;
         }
-        if (issue) cp_async_commit();
     }
     __device__ __forceinline__ unsigned u32(unsigned off) const {
         return *reinterpret_cast<const unsigned*>(buf + ((rd + off) & mask));
@@ -84,28 +85,51 @@ struct StreamRing {
 };
 
 // ------------------------------------------------------------------------------------------------ D1
-// shared memory per warp:  F[ntri][32] | yv[nslots][32] | qacc[n_obs][32] | cvec[ncv][32] (affine only) | ring
-__host__ __device__ inline size_t frontal_lane_smem(int ntri, int nslots, int n_obs, int ncv_smem, int ring_bytes) {
-    return (size_t)(ntri + nslots + n_obs + ncv_smem) * 32 * sizeof(double) + (size_t)ring_bytes;
+// shared memory per warp:  F[ntri][32] | yv[nslots][32] | qacc[n_obs][32] | cvec[ncv][32] (affine only) |
+//                          factor-row ring [lr_rows][32] (backward substitution) | instruction ring
+__host__ __device__ inline size_t frontal_lane_smem(int ntri, int nslots, int n_obs, int ncv_smem, int lr_rows, int ring_bytes) {
+    return (size_t)(ntri + nslots + n_obs + ncv_smem + lr_rows) * 32 * sizeof(double) + (size_t)ring_bytes;
+}
+
+#define FRONTAL_DMAX 7   // the backward substitution prefetches the factor rows of up to DMAX pivots ahead
+
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(unsigned k) {   // k <= FRONTAL_DMAX, warp-uniform
+    switch (k) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        case 6: cp_async_wait<6>(); break;
+        default: cp_async_wait<7>(); break;
+    }
 }
 
 template <int CM>
 __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalIO io) {
+    static_assert(CM % 4 == 0, "columns are read four entries at a time");
     extern __shared__ __align__(16) double fsm[];
     const int lane = threadIdx.x;
-    double* F = fsm + lane;                            // F[e * 32]
-    double* yv = F + (size_t)P.ntri * 32;
-    double* qacc = yv + (size_t)P.nslots * 32;
-    double* cvs = qacc + (size_t)io.n_obs * 32;        // affine only
+    // byte-addressed views of this lane's column of every [row][lane] array (one row = 256 bytes)
+    char* F = reinterpret_cast<char*>(fsm + lane);
+    char* yv = F + (size_t)P.ntri * 256;
+    char* qacc = yv + (size_t)P.nslots * 256;
+    char* cvs = qacc + (size_t)io.n_obs * 256;        // affine only
+    char* Lring = cvs + (size_t)(io.cv_global ? 0 : P.ncv) * 256;
     StreamRing ring;
-    ring.buf = reinterpret_cast<unsigned char*>(fsm + (size_t)(P.ntri + P.nslots + io.n_obs + (io.cv_global ? 0 : P.ncv)) * 32);
+    ring.buf = reinterpret_cast<unsigned char*>(Lring - lane * 8 + (size_t)P.lr_rows * 256);
     ring.mask = (unsigned)P.ring_bytes - 1u;
     const unsigned full = 0xffffffffu;
     const long long n_groups = (io.N + 31) / 32;
     const int n = P.n;
-    const size_t wstride = ((size_t)P.nnzL + 2 * (size_t)n) * 32;   // per-CTA workspace (doubles)
-    double* Lw = io.work + (size_t)blockIdx.x * wstride + lane;
-    double* RY = Lw + (size_t)P.nnzL * 32;
+    const size_t wrows = (size_t)P.nnzL + 2 * (size_t)n;   // per-CTA workspace rows: per pivot [1/L_jj, y_j, column]
+    char* Lw = reinterpret_cast<char*>(io.work + (size_t)blockIdx.x * wrows * 32 + lane);
+    auto ld = [](const char* base, unsigned off) { return *reinterpret_cast<const double*>(base + off); };
+    auto st = [](char* base, unsigned off, double v) { *reinterpret_cast<double*>(base + off) = v; };
 
     for (;;) {
         long long g = 0;
@@ -117,77 +141,108 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
         const long long sc = valid ? s : io.N - 1;
         ring.reset(P.fwd);
         ring.fill(lane, true);
-        const double* cv;      // coefficient vector of this lane: cv[t * 32]
+        cp_async_commit();
+        const char* cv;      // coefficient vector of this lane, row t at byte offset 256 t
         if (io.cv_global) {
-            cv = io.cv_global + (size_t)g * P.ncv * 32 + lane;
+            cv = reinterpret_cast<const char*>(io.cv_global + (size_t)g * P.ncv * 32 + lane);
         } else {
-            cvs[0] = 1.0;
-            for (int t = 1; t < P.ncv; ++t) cvs[t * 32] = io.in[sc * io.in_stride + (t - 1)];
+            st(cvs, 0, 1.0);
+            for (int t = 1; t < P.ncv; ++t) st(cvs, 256u * t, io.in[sc * io.in_stride + (t - 1)]);
             cv = cvs;
         }
-        for (int e = 0; e < P.ntri; ++e) F[e * 32] = 0.0;
-        for (int e = 0; e < P.nslots; ++e) yv[e * 32] = 0.0;
-        for (int o = 0; o < io.n_obs; ++o) qacc[o * 32] = 0.0;
+        for (int e = 0; e < P.ntri; ++e) st(F, 256u * e, 0.0);
+        for (int e = 0; e < P.nslots; ++e) st(yv, 256u * e, 0.0);
+        for (int o = 0; o < io.n_obs; ++o) st(qacc, 256u * o, 0.0);
 
         bool bad = false;
         double yy = 0.0;
-        size_t cp = 0;
+        char* Lj = Lw;   // workspace block of the current pivot
         for (int j = -1; j < n; ++j) {
             cp_async_wait<0>();
             __syncwarp();
             ring.fill(lane, true);
-            const unsigned c = ring.u32(0), p = ring.u32(4), npos = ring.u32(8), nent = ring.u32(12);
-            const unsigned reclen = ring.u32(20);
-            unsigned sl[CM];   // slots of the column (uniform values)
-            double l[CM];      // scaled pivot column
+            cp_async_commit();
+            const unsigned char* rec = ring.buf + (ring.rd & ring.mask);   // records never straddle the wrap point
+            const uint4 h0 = *reinterpret_cast<const uint4*>(rec);        // c | 256 p | 256 (tri(p) + p) | npos
+            const uint4 h1 = *reinterpret_cast<const uint4*>(rec + 16);   // nent | bytes | rhs
+            const unsigned c = h0.x, npos = h0.w, nent = h1.x, reclen = h1.y;
+            const unsigned c4 = (c + 3u) & ~3u;
+            unsigned sr[CM], sc_[CM];   // 256 tri(s_a), 256 s_a  (uniform values)
+            double l[CM];               // scaled pivot column
             if (j >= 0) {
+                const double dd = ld(F, h0.z);
+                const double ypre = ld(yv, h0.y);
+                st(F, h0.z, 0.0);
+                st(yv, h0.y, 0.0);
+                // gather the pivot column and the right-hand-side entries it updates (independent loads first)
+                double yo[CM];
 #pragma unroll
-                for (int a = 0; a < CM; ++a) {
-                    if (a >= (int)c) break;
-                    sl[a] = ring.u16(32 + 2 * a);
-                }
-                const unsigned pd = tri_u(p) + p;
-                const double dd = F[pd * 32];
-                F[pd * 32] = 0.0;
-                // gather the pivot column (independent loads first, then the zeroing stores)
-#pragma unroll
-                for (int a = 0; a < CM; ++a) {
-                    if (a >= (int)c) break;
-                    const unsigned ad = sl[a] > p ? tri_u(sl[a]) + p : tri_u(p) + sl[a];
-                    l[a] = F[ad * 32];
-                }
-#pragma unroll
-                for (int a = 0; a < CM; ++a) {
-                    if (a >= (int)c) break;
-                    const unsigned ad = sl[a] > p ? tri_u(sl[a]) + p : tri_u(p) + sl[a];
-                    F[ad * 32] = 0.0;
+                for (int q = 0; q < CM / 4; ++q) {
+                    if (4 * q >= (int)c) break;
+                    const uint4 ga = *reinterpret_cast<const uint4*>(rec + 32 + 16 * q);
+                    const uint4 r4 = *reinterpret_cast<const uint4*>(rec + 32 + 4 * c4 + 16 * q);
+                    const uint4 c4v = *reinterpret_cast<const uint4*>(rec + 32 + 8 * c4 + 16 * q);
+                    sr[4 * q] = r4.x; sr[4 * q + 1] = r4.y; sr[4 * q + 2] = r4.z; sr[4 * q + 3] = r4.w;
+                    sc_[4 * q] = c4v.x; sc_[4 * q + 1] = c4v.y; sc_[4 * q + 2] = c4v.z; sc_[4 * q + 3] = c4v.w;
+                    // entries past c read address 0 / slot 0: harmless loads, never stored back
+                    l[4 * q] = ld(F, ga.x); l[4 * q + 1] = ld(F, ga.y); l[4 * q + 2] = ld(F, ga.z); l[4 * q + 3] = ld(F, ga.w);
+                    yo[4 * q] = ld(yv, c4v.x); yo[4 * q + 1] = ld(yv, c4v.y); yo[4 * q + 2] = ld(yv, c4v.z); yo[4 * q + 3] = ld(yv, c4v.w);
+                    st(F, ga.x, 0.0);
+                    if (4 * q + 1 < (int)c) st(F, ga.y, 0.0);
+                    if (4 * q + 2 < (int)c) st(F, ga.z, 0.0);
+                    if (4 * q + 3 < (int)c) st(F, ga.w, 0.0);
                 }
                 bad |= !(dd > 0.0);
                 const double rinv = rsqrt(dd);
-                const double yp = (yv[p * 32] + ring.f64(24)) * rinv;
-                yv[p * 32] = 0.0;
+                const double yp = (ypre + __longlong_as_double(((long long)h1.w << 32) | h1.z)) * rinv;
                 yy = fma(yp, yp, yy);
-                double* Lj = Lw + cp * 32;
-                RY[(size_t)(2 * j) * 32] = rinv;
-                RY[(size_t)(2 * j + 1) * 32] = yp;
+                st(Lj, 0, rinv);
+                st(Lj, 256, yp);
 #pragma unroll
                 for (int a = 0; a < CM; ++a) {
                     if (a >= (int)c) break;
                     l[a] *= rinv;
-                    Lj[a * 32] = l[a];
-                    yv[sl[a] * 32] = fma(-l[a], yp, yv[sl[a] * 32]);
+                    st(Lj, 512u + 256u * a, l[a]);
+                    st(yv, sc_[a], fma(-l[a], yp, yo[a]));
                 }
-                cp += c;
+                Lj += (size_t)(c + 2) * 256;
             }
-            {   // assembly of column j + 1
-                const unsigned off_pos = 32 + ((2 * c + 7) & ~7u), off_coef = off_pos + 8 * npos, off_term = off_coef + 8 * nent;
-                unsigned e = 0;
-                for (unsigned q = 0; q < npos; ++q) {
-                    const unsigned ad = ring.u32(off_pos + 8 * q), cnt = ring.u32(off_pos + 8 * q + 4);
-                    double sum = 0.0;
-                    for (unsigned k = 0; k < cnt; ++k, ++e)
-                        sum = fma(ring.f64(off_coef + 8 * e), cv[(size_t)ring.u32(off_term + 4 * e) * 32], sum);
-                    F[ad * 32] += sum;
+            {   // assembly of column j + 1: positions in chunks of 4 (loads first), the first two entries of a position unrolled
+                const unsigned char* pos = rec + 32 + 12 * c4;
+                const unsigned char* coef = pos + ((8 * npos + 15) & ~15u);
+                const unsigned char* term = coef + ((8 * nent + 15) & ~15u);
+                unsigned e0 = 0;
+                for (unsigned q0 = 0; q0 < npos; q0 += 4) {
+                    unsigned ad[4], cnt[4], eb[4];
+                    double sum[4], fv[4];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint4 pp = *reinterpret_cast<const uint4*>(pos + 8 * (q0 + 2 * u));   // padded: reads past npos are zeros/other fields, masked below
+                        ad[2 * u] = pp.x; cnt[2 * u] = q0 + 2 * u < npos ? pp.y : 0u;
+                        ad[2 * u + 1] = pp.z; cnt[2 * u + 1] = q0 + 2 * u + 1 < npos ? pp.w : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        eb[u] = e0;
+                        e0 += cnt[u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (q0 + u >= npos) break;
+                        fv[u] = ld(F, ad[u]);
+                        double s0 = 0.0, s1 = 0.0;
+                        if (cnt[u] > 0) s0 = *reinterpret_cast<const double*>(coef + 8 * eb[u]) * ld(cv, *reinterpret_cast<const unsigned*>(term + 4 * eb[u]));
+                        if (cnt[u] > 1) s1 = *reinterpret_cast<const double*>(coef + 8 * eb[u] + 8) * ld(cv, *reinterpret_cast<const unsigned*>(term + 4 * eb[u] + 4));
+                        sum[u] = s0 + s1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (q0 + u >= npos) break;
+                        for (unsigned k = 2; k < cnt[u]; ++k)
+                            sum[u] = fma(*reinterpret_cast<const double*>(coef + 8 * (eb[u] + k)),
+                                         ld(cv, *reinterpret_cast<const unsigned*>(term + 4 * (eb[u] + k))), sum[u]);
+                        st(F, ad[u], fv[u] + sum[u]);
+                    }
                 }
             }
             if (j >= 0) {
@@ -196,80 +251,88 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
 #pragma unroll
                 for (int a = 0; a < CM; ++a) {
                     if (a >= (int)c) break;
-                    double* Fr = F + (size_t)tri_u(sl[a]) * 32;
+                    char* Fr = F + sr[a];
                     double f[CM];
 #pragma unroll
-                    for (int b = 0; b <= a; ++b) f[b] = Fr[sl[b] * 32];
+                    for (int b = 0; b <= a; ++b) f[b] = ld(Fr, sc_[b]);
 #pragma unroll
-                    for (int b = 0; b <= a; ++b) Fr[sl[b] * 32] = fma(-l[a], l[b], f[b]);
+                    for (int b = 0; b <= a; ++b) st(Fr, sc_[b], fma(-l[a], l[b], f[b]));
                 }
             }
             ring.rd += reclen;
         }
-        // backward substitution L^T w = y (yv doubles as the slot-indexed solution), observables on the fly; the factor
-        // column and (1/L_jj, y_j) of the next pivot are prefetched into registers while the current one is reduced
+        // ---- backward substitution L^T w = y (yv doubles as the slot-indexed solution), observables on the fly.  The
+        // factor blocks [1/L_jj, y_j, column] come back from HBM through a block ring in shared memory that cp.async fills
+        // up to DMAX pivots ahead; the host simulated that ring and wrote into every record which blocks to request and
+        // how many of the youngest copy groups may still be in flight when the record is consumed (kw).
+        cp_async_wait<0>();
+        __syncwarp();
         ring.reset(P.bwd);
         ring.fill(lane, true);
+        cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
         double bw = 0.0;
-        double lA[CM], lB[CM], rA, yA, rB = 0.0, yB = 0.0;
-        {
-            const unsigned c0 = ring.u32(0);
-            cp -= c0;
-#pragma unroll
-            for (int a = 0; a < CM; ++a) {
-                if (a >= (int)c0) break;
-                lA[a] = Lw[(cp + a) * 32];
+        const unsigned lring_s = smem_u32(Lring);
+        auto request = [&](const unsigned char* rq, unsigned count) {
+            for (unsigned i = 0; i < count; ++i) {
+                const uint4 r = *reinterpret_cast<const uint4*>(rq + 16 * i);   // 256 ring row | rows | source row
+                unsigned dst = lring_s + r.x;
+                const char* src = Lw + (size_t)r.z * 256;
+                for (unsigned k = 0; k < r.y; ++k, dst += 256, src += 256)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
             }
-            rA = RY[(size_t)(2 * (n - 1)) * 32];
-            yA = RY[(size_t)(2 * (n - 1) + 1) * 32];
-        }
-        auto bstep = [&](int j, double (&lc)[CM], double (&ln)[CM], double rc, double yc, double& rn, double& yn) {
-            ring.fill(lane, true);
-            const unsigned c = ring.u32(0), p = ring.u32(4), nobs = ring.u32(8), dof = ring.u32(12);
-            const unsigned reclen = ring.u32(16), cnext = ring.u32(20);
-            if (j > 0) {
-                cp -= cnext;
-#pragma unroll
-                for (int a = 0; a < CM; ++a) {
-                    if (a >= (int)cnext) break;
-                    ln[a] = Lw[(cp + a) * 32];
-                }
-                rn = RY[(size_t)(2 * (j - 1)) * 32];
-                yn = RY[(size_t)(2 * (j - 1) + 1) * 32];
-            }
-            double acc = yc;
-#pragma unroll
-            for (int a = 0; a < CM; ++a) {
-                if (a >= (int)c) break;
-                acc = fma(-lc[a], yv[ring.u16(32 + 2 * a) * 32], acc);
-            }
-            const double wj = acc * rc;
-            yv[p * 32] = wj;
-            bw = fma(ring.f64(24), wj, bw);
-            if (io.w_out && valid) io.w_out[(size_t)s * n + dof] = wj;
-            const unsigned off_val = 32 + ((2 * c + 7) & ~7u), off_row = off_val + 8 * nobs;
-            for (unsigned o = 0; o < nobs; ++o) {
-                const unsigned row = ring.u32(off_row + 4 * o);
-                qacc[row * 32] = fma(ring.f64(off_val + 8 * o), wj, qacc[row * 32]);
-            }
-            ring.rd += reclen;
-            cp_async_wait<0>();
-            __syncwarp();
         };
-        for (int j = n - 1; j >= 0; j -= 2) {
-            bstep(j, lA, lB, rA, yA, rB, yB);
-            if (j >= 1) bstep(j - 1, lB, lA, rB, yB, rA, yA);
+        for (int j = n; j >= 0; --j) {   // j == n: prologue record (initial requests only)
+            ring.fill(lane, true);
+            const unsigned char* rec = ring.buf + (ring.rd & ring.mask);
+            const uint4 h0 = *reinterpret_cast<const uint4*>(rec);        // c | 256 p | nobs | dof
+            const uint4 h1 = *reinterpret_cast<const uint4*>(rec + 16);   // bytes | npf, kw | rhs
+            const unsigned c = h0.x, nobs = h0.z, npf = h1.y & 0xffffu, kw = h1.y >> 16;
+            request(rec + 48, npf);
+            cp_async_commit();
+            if (j < n) {
+                cp_async_wait_dyn(kw);
+                __syncwarp();
+                const char* blk = Lring + *reinterpret_cast<const unsigned*>(rec + 32);
+                const unsigned char* cols = rec + 48 + 16 * npf;
+                const double rinv = ld(blk, 0);
+                double acc = ld(blk, 256);
+#pragma unroll
+                for (int q = 0; q < CM / 4; ++q) {
+                    if (4 * q >= (int)c) break;
+                    const uint4 cc = *reinterpret_cast<const uint4*>(cols + 16 * q);   // padded entries: slot 0, masked
+                    const double l0 = ld(blk, 512u + 1024u * q), w0 = ld(yv, cc.x);
+                    const double l1 = 4 * q + 1 < (int)c ? ld(blk, 768u + 1024u * q) : 0.0, w1 = ld(yv, cc.y);
+                    const double l2 = 4 * q + 2 < (int)c ? ld(blk, 1024u + 1024u * q) : 0.0, w2 = ld(yv, cc.z);
+                    const double l3 = 4 * q + 3 < (int)c ? ld(blk, 1280u + 1024u * q) : 0.0, w3 = ld(yv, cc.w);
+                    acc = fma(-l0, w0, acc);
+                    acc = fma(-l1, w1, acc);
+                    acc = fma(-l2, w2, acc);
+                    acc = fma(-l3, w3, acc);
+                }
+                const double wj = acc * rinv;
+                st(yv, h0.y, wj);
+                bw = fma(__longlong_as_double(((long long)h1.w << 32) | h1.z), wj, bw);
+                if (io.w_out && valid) io.w_out[(size_t)s * n + h0.w] = wj;
+                const unsigned char* oval = cols + 4 * ((c + 3u) & ~3u);
+                const unsigned char* orow = oval + ((8 * nobs + 15) & ~15u);
+                for (unsigned o = 0; o < nobs; ++o) {
+                    const unsigned row = *reinterpret_cast<const unsigned*>(orow + 4 * o);
+                    st(qacc, row, fma(*reinterpret_cast<const double*>(oval + 8 * o), wj, ld(qacc, row)));
+                }
+            }
+            ring.rd += h1.x;
         }
         if (valid) {
             if (io.qoi_out)
-                for (int o = 0; o < io.n_obs; ++o) io.qoi_out[(size_t)s * io.n_obs + o] = qacc[o * 32];
+                for (int o = 0; o < io.n_obs; ++o) io.qoi_out[(size_t)s * io.n_obs + o] = ld(qacc, 256u * o);
             const bool nan = !(bw == bw);
             if (io.status_out) io.status_out[s] = (bad || nan) ? TFIN_STATUS_BREAKDOWN : TFIN_STATUS_CONVERGED;
             if (io.iters_out) io.iters_out[s] = 0;
             if (io.relres_out) io.relres_out[s] = fabs(bw - yy) / yy;
         }
+        cp_async_wait<0>();
         __syncwarp();
     }
 }
@@ -302,7 +365,7 @@ struct FrontalCtaSmem {
     }
 };
 
-template <int MODE>
+template <int MODE, int NU>   // NU: the column fits 32 * NU entries
 __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L) {
     extern __shared__ __align__(16) unsigned char fsm_raw[];
     double* F = reinterpret_cast<double*>(fsm_raw + L.F);
@@ -338,6 +401,7 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
         if (s >= io.N) break;
         ring.reset(P.fwd);
         ring.fill(lane, loader);
+        if (loader) cp_async_commit();
         const double* cv;
         if (io.cv_global) {
             cv = io.cv_global + (size_t)s * P.ncv;
@@ -358,18 +422,27 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
             // ---- G_j: pivot, scaled column (zeroing the consumed entries), pivot row of the right-hand sides,
             //      and the assembly of column j + 1 (disjoint entries)
             ring.fill(lane, loader);
-            const unsigned c = ring.u32(0), p = ring.u32(4), npos = ring.u32(8), nent = ring.u32(12), nobs = ring.u32(16);
-            const unsigned reclen = ring.u32(20);
-            const unsigned off_pos = 32 + ((2 * c + 7) & ~7u), off_coef = off_pos + 8 * npos, off_term = off_coef + 8 * nent;
-            const unsigned off_oval = (off_term + 4 * nent + 7) & ~7u, off_orow = off_oval + 8 * nobs;
+            if (loader) cp_async_commit();
+            const unsigned char* rec = ring.buf + (ring.rd & ring.mask);   // records never straddle the wrap point
+            const uint4 h0 = *reinterpret_cast<const uint4*>(rec);         // c | pivot slot | npos | nent
+            const uint4 h1 = *reinterpret_cast<const uint4*>(rec + 16);    // nobs | bytes | rhs
+            const unsigned c = h0.x, p = h0.y, npos = h0.z, nent = h0.w, nobs = h1.x, reclen = h1.y;
+            const unsigned short* slots = reinterpret_cast<const unsigned short*>(rec + 32);
+            const unsigned* posv = reinterpret_cast<const unsigned*>(rec + 32 + ((2 * c + 7) & ~7u));
+            const double* coefv = reinterpret_cast<const double*>(posv + 2 * npos);
+            const unsigned* termv = reinterpret_cast<const unsigned*>(coefv + nent);
+            const double* ovalv = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(termv) + ((4 * nent + 7) & ~7u));
+            const unsigned* orowv = reinterpret_cast<const unsigned*>(ovalv + nobs);
             const unsigned pd = tri_u(p) + p;
             double rinv = 0.0;
-            if (j >= 0) {
+            // only the threads that scale something need 1/sqrt(pivot): the gatherers, the right-hand-side threads, and
+            // thread 0 (which keeps the breakdown flag)
+            if (j >= 0 && (tid < (int)c || rtid < R || tid == 0)) {
                 const double dd = F[pd];
                 bad |= !(dd > 0.0);
                 rinv = rsqrt(dd);
                 for (int a = tid; a < (int)c; a += NT) {
-                    const unsigned sa = ring.u16(32 + 2 * a);
+                    const unsigned sa = slots[a];
                     const unsigned ad = sa > p ? tri_u(sa) + p : tri_u(p) + sa;
                     const double l = F[ad] * rinv;
                     F[ad] = 0.0;
@@ -381,21 +454,21 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
                     double v = yv[p * R + rtid];
                     yv[p * R + rtid] = 0.0;
                     if (rtid == 0) {
-                        v += ring.f64(24);
+                        v += __longlong_as_double(((long long)h1.w << 32) | h1.z);
                     } else {
                         for (unsigned o = 0; o < nobs; ++o)
-                            if ((int)ring.u32(off_orow + 4 * o) == rtid - 1) v += ring.f64(off_oval + 8 * o);
+                            if ((int)orowv[o] == rtid - 1) v += ovalv[o];
                     }
                     ypiv[rtid] = v * rinv;
                 }
             }
             for (unsigned q = (unsigned)rtid; q < npos; q += NT) {   // threads from the top: one assembly position each
                 unsigned e = 0;
-                for (unsigned q2 = 0; q2 < q; ++q2) e += ring.u32(off_pos + 8 * q2 + 4);
-                const unsigned cnt = ring.u32(off_pos + 8 * q + 4);
+                for (unsigned q2 = 0; q2 < q; ++q2) e += posv[2 * q2 + 1];
+                const unsigned cnt = posv[2 * q + 1];
                 double sum = 0.0;
-                for (unsigned k = 0; k < cnt; ++k, ++e) sum = fma(ring.f64(off_coef + 8 * e), cv[ring.u32(off_term + 4 * e)], sum);
-                F[ring.u32(off_pos + 8 * q)] += sum;
+                for (unsigned k = 0; k < cnt; ++k, ++e) sum = fma(coefv[e], cv[termv[e]], sum);
+                F[posv[2 * q]] += sum;
             }
             __syncthreads();
             // ---- U_j: rank-1 update of the front and of the right-hand sides
@@ -414,26 +487,45 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
                     const unsigned ys = cslot[a] * R + r;
                     yv[ys] = fma(-lcol[a], ypiv[r], yv[ys]);
                 }
-                // folded triangle: combined row q = (row c-1-q, then row q) has c + 1 elements for every q
-                const int half = ((int)c + 1) >> 1;
-                for (int q = warp; q < half; q += nw) {
-                    const int rowA = (int)c - 1 - q, rowB = q;
-                    const double laA = lcol[rowA], laB = lcol[rowB];
-                    const unsigned trA = tri_u(cslot[rowA]), trB = tri_u(cslot[rowB]);
-                    const int xend = rowA == rowB ? rowA : (int)c;
-                    for (int x = lane; x <= xend; x += 32) {
-                        const bool first = x <= rowA;
-                        const int b = first ? x : x - rowA - 1;
-                        const unsigned ad = (first ? trA : trB) + cslot[b];
-                        F[ad] = fma(-(first ? laA : laB), lcol[b], F[ad]);
+                // row a of the triangle (b = 0..a) goes to warp a mod nw; lane holds the column entries b = lane + 32 u in
+                // registers, so an update costs one shared load, one FMA and one store.  Two rows are in flight at a time
+                // (all loads before the stores) to overlap the shared-memory latency.
+                double lb[NU];
+                unsigned sb[NU];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    if (32 * u >= (int)c) break;
+                    const int b = lane + 32 * u;
+                    lb[u] = b < (int)c ? lcol[b] : 0.0;
+                    sb[u] = b < (int)c ? cslot[b] : 0u;
+                }
+                for (int a = warp; a < (int)c; a += 2 * nw) {
+                    const int a2 = a + nw;
+                    const bool two = a2 < (int)c;
+                    const double la = lcol[a], la2 = two ? lcol[a2] : 0.0;
+                    const unsigned tr = tri_u(cslot[a]), tr2 = two ? tri_u(cslot[a2]) : 0u;
+                    double f[NU], f2[NU];
+                    const int amax = two ? a2 : a;   // rows ascend: a2 > a
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) {
+                        if (32 * u > amax) break;
+                        if (lane + 32 * u <= a) f[u] = F[tr + sb[u]];
+                        if (two && lane + 32 * u <= a2) f2[u] = F[tr2 + sb[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) {
+                        if (32 * u > amax) break;
+                        if (lane + 32 * u <= a) F[tr + sb[u]] = fma(-la, lb[u], f[u]);
+                        if (two && lane + 32 * u <= a2) F[tr2 + sb[u]] = fma(-la2, lb[u], f2[u]);
                     }
                 }
             }
-            if (loader) cp_async_wait<0>();   // the chunks requested at the top of this step have had the whole step to land
+            if (loader) cp_async_wait<1>();   // chunks requested one step ago must have landed; this step's may still fly
             __syncthreads();
             cp += (j >= 0 ? c : 0u);
             ring.rd += reclen;
         }
+        if (loader) cp_async_wait<0>();   // nothing may land in the ring after it is re-armed
         if (MODE == FRONTAL_MODE_QOI) {
             if (rtid >= 1 && rtid < R && io.qoi_out) io.qoi_out[(size_t)s * io.n_obs + (rtid - 1)] = myq;
             if (tid == 0) {
@@ -447,8 +539,12 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
         if (rtid == 0) ypiv[0] = myq;   // y.y, read by thread 0 after the loop (barriers inside)
         ring.reset(P.bwd);
         ring.fill(lane, loader);
-        if (loader) cp_async_wait<0>();
+        if (loader) {
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
         __syncthreads();
+        ring.rd += ring.u32(16);   // skip the prologue record (D1's prefetch schedule)
         double bw = 0.0;
         // factor entries of the next pivot are prefetched while the current one is reduced (thread a holds entry a, a + NT, ..)
         constexpr int LPF = 2;   // columns of up to LPF * NT entries are prefetched, longer ones read in place
@@ -463,8 +559,12 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
         }
         for (int j = n - 1; j >= 0; --j) {
             ring.fill(lane, loader);
-            const unsigned c = ring.u32(0), p = ring.u32(4), nobs = ring.u32(8), dof = ring.u32(12);
-            const unsigned reclen = ring.u32(16), cnext = ring.u32(20);
+            if (loader) cp_async_commit();
+            const unsigned char* rec = ring.buf + (ring.rd & ring.mask);
+            const uint4 h0 = *reinterpret_cast<const uint4*>(rec);         // c | pivot slot | nobs | dof
+            const uint4 h1 = *reinterpret_cast<const uint4*>(rec + 16);    // bytes | next c | rhs
+            const unsigned c = h0.x, p = h0.y, nobs = h0.z, dof = h0.w, reclen = h1.x, cnext = h1.y;
+            const unsigned short* slots = reinterpret_cast<const unsigned short*>(rec + 40);
             const size_t cpj = cp;
             double lnext[LPF], rnext = 0.0, ynext = 0.0;
 #pragma unroll
@@ -479,8 +579,8 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
             double part = 0.0;
 #pragma unroll
             for (int u = 0; u < LPF; ++u)
-                if (tid + u * NT < (int)c) part = fma(lpre[u], yv[ring.u16(32 + 2 * (tid + u * NT))], part);
-            for (int a = tid + LPF * NT; a < (int)c; a += NT) part = fma(Lw[cpj + a], yv[ring.u16(32 + 2 * a)], part);
+                if (tid + u * NT < (int)c) part = fma(lpre[u], yv[slots[tid + u * NT]], part);
+            for (int a = tid + LPF * NT; a < (int)c; a += NT) part = fma(Lw[cpj + a], yv[slots[a]], part);
             part = warp_sum(part);
             double* rd = red + (j & 1) * 32;
             if (lane == 0) rd[warp] = part;
@@ -490,10 +590,11 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
             const double wj = (ycur - acc) * rcur;
             if (tid == 0) {
                 yv[p] = wj;
-                bw = fma(ring.f64(24), wj, bw);
+                bw = fma(__longlong_as_double(((long long)h1.w << 32) | h1.z), wj, bw);
                 if (io.w_out) io.w_out[(size_t)s * n + dof] = wj;
-                const unsigned off_val = 32 + ((2 * c + 7) & ~7u), off_row = off_val + 8 * nobs;
-                for (unsigned o = 0; o < nobs; ++o) qacc[ring.u32(off_row + 4 * o)] += ring.f64(off_val + 8 * o) * wj;
+                const double* oval = reinterpret_cast<const double*>(rec + 40 + ((2 * c + 7) & ~7u));
+                const unsigned* orow = reinterpret_cast<const unsigned*>(oval + nobs);
+                for (unsigned o = 0; o < nobs; ++o) qacc[orow[o]] += oval[o] * wj;
             }
 #pragma unroll
             for (int u = 0; u < LPF; ++u) lpre[u] = lnext[u];

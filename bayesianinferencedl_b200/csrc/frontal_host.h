@@ -329,99 +329,263 @@ inline void frontal_set_obs(FrontalProgram& P, int n_obs, const int32_t* obs_ptr
 // Packed instruction streams.  The kernels never chase the program's CSR arrays (every dependent global load would cost
 // a full L2 round trip per pivot with one or two resident warps): the program is flattened into one byte stream per
 // direction, read strictly sequentially through a small shared-memory ring that cp.async keeps filled ahead of use.
+// A record never straddles the wrap point of the ring (the previous record is padded instead), so a kernel addresses the
+// fields of a record from ONE base pointer.
 //
-// forward record (prologue j = -1 with c = 0, then j = 0 .. n-1), 16-byte aligned, little endian:
-//    +0 u32 c | +4 u32 pivot slot | +8 u32 npos | +12 u32 nent | +16 u32 nobs | +20 u32 record bytes | +24 f64 rhs_j
-//    +32 c x u16 slots (padded to 8) | npos x {u32 address, u32 entries} | nent x f64 coef | nent x u32 term (padded to 8)
-//    | nobs x f64 weight | nobs x u32 row (padded to 8) | pad to 16
-//    (npos / nent describe the assembly of column j + 1, which step j performs; nobs the observation weights of pivot j)
-// backward record (j = n-1 .. 0):
-//    +0 u32 c | +4 u32 pivot slot | +8 u32 nobs | +12 u32 dof (perm_j) | +16 u32 record bytes | +20 u32 c of the NEXT record
-//    +24 f64 rhs_j | +32 slots | weights | rows | pad to 16
+// D2 (sample per CTA) streams
+//   forward record (prologue j = -1 with c = 0, then j = 0 .. n-1), 16-byte aligned, little endian:
+//      +0 u32 c | +4 u32 pivot slot | +8 u32 npos | +12 u32 nent | +16 u32 nobs | +20 u32 record bytes | +24 f64 rhs_j
+//      +32 c x u16 slots (padded to 8) | npos x {u32 address, u32 entries} | nent x f64 coef | nent x u32 term (padded
+//      to 8) | nobs x f64 weight | nobs x u32 row (padded to 8) | pad to 16
+//      (npos / nent describe the assembly of column j + 1, which step j performs; nobs the observation weights of pivot j)
+//   backward record (a prologue with c = 0, then j = n-1 .. 0):
+//      +0 u32 c | +4 u32 pivot slot | +8 u32 nobs | +12 u32 dof (perm_j) | +16 u32 record bytes | +20 u32 c of the NEXT
+//      record | +24 f64 rhs_j | +32 pad | +40 slots | weights | rows | pad to 16
+// D1 (sample per thread) streams: everything the kernel would otherwise compute per use is stored pre-scaled to BYTE offsets
+// of its [entry][lane] shared-memory layout (one row = 256 bytes), in 16-byte groups that one LDS.128 fetches
+//   forward record:
+//      +0 u32 c | +4 u32 256 p | +8 u32 256 (tri(p) + p) | +12 u32 npos | +16 u32 nent | +20 u32 record bytes | +24 f64 rhs_j
+//      +32 u32 gather[c4] (256 x address of entry (s_a, p)) | u32 row[c4] (256 tri(s_a)) | u32 col[c4] (256 s_a), c4 = c
+//      rounded up to 4 | npos x {u32 256 address, u32 entries} padded to 16 | nent x f64 coef padded to 16 | nent x u32
+//      256 term padded to 16
+//   backward record (prologue, then j = n-1 .. 0):
+//      +0 u32 c | +4 u32 256 p | +8 u32 nobs | +12 u32 dof | +16 u32 record bytes | +20 u32 npf | kw << 16 | +24 f64 rhs_j
+//      +32 u32 256 x first ring row of this pivot's factor block | +36 pad | +48 npf x {u32 256 ring row, u32 rows, u32
+//      source row, pad} (blocks to request now) | u32 col[c4] | nobs x f64 weight padded to 16 | nobs x u32 256 row pad 16
 struct FrontalStreams {
-    std::vector<unsigned char> fwd, bwd;
-    int max_record = 0;   // largest record of either stream (bytes)
-    int ring_bytes = 0;   // power of two >= 2 * max_record + 512
+    std::vector<unsigned char> fwd, bwd;     // D2
+    std::vector<unsigned char> fwd1, bwd1;   // D1 (empty if the front is too wide for it)
+    int max_record = 0;   // largest record of any stream (bytes)
+    int ring_bytes = 0;   // power of two
+    int lr_rows = 0;      // rows of D1's factor-row ring the backward schedule was simulated for
 };
 
-inline void frontal_pack_streams(const FrontalProgram& P, FrontalStreams* out) {
-    FrontalStreams& S = *out;
-    S = FrontalStreams();
-    auto put32 = [](std::vector<unsigned char>& v, uint32_t x) {
+namespace frontal_detail {
+struct ByteStream {
+    std::vector<unsigned char> v;
+    std::vector<size_t> starts;   // record starts
+    void put32(uint32_t x) {
         for (int k = 0; k < 4; ++k) v.push_back((unsigned char)(x >> (8 * k)));
-    };
-    auto put16 = [](std::vector<unsigned char>& v, uint16_t x) {
+    }
+    void put16(uint16_t x) {
         v.push_back((unsigned char)(x & 255));
         v.push_back((unsigned char)(x >> 8));
-    };
-    auto put64 = [](std::vector<unsigned char>& v, double d) {
+    }
+    void put64(double d) {
         unsigned char b[8];
         std::memcpy(b, &d, 8);
         v.insert(v.end(), b, b + 8);
-    };
-    auto pad = [](std::vector<unsigned char>& v, size_t a) {
+    }
+    void pad(size_t a) {
         while (v.size() % a) v.push_back(0);
-    };
-    auto set32 = [](std::vector<unsigned char>& v, size_t at, uint32_t x) {
+    }
+    void set32(size_t at, uint32_t x) {
         for (int k = 0; k < 4; ++k) v[at + k] = (unsigned char)(x >> (8 * k));
-    };
+    }
+    void begin() { starts.push_back(v.size()); }
+};
+// Re-lay the records so that none straddles a multiple of `ring` (pad the previous record, whose length field sits at
+// `len_off`), then append the zero padding the ring loader may prefetch beyond the last record.
+inline std::vector<unsigned char> finish_stream(const ByteStream& in, size_t len_off, int ring) {
+    std::vector<unsigned char> out;
+    size_t prev = (size_t)-1;
+    for (size_t r = 0; r < in.starts.size(); ++r) {
+        const size_t b = in.starts[r], e = r + 1 < in.starts.size() ? in.starts[r + 1] : in.v.size();
+        const size_t len = e - b;
+        if (out.size() % ring + len > (size_t)ring && prev != (size_t)-1) {
+            const size_t target = (out.size() / ring + 1) * ring;
+            out.resize(target, 0);
+            uint32_t plen = (uint32_t)(target - prev);
+            for (int k = 0; k < 4; ++k) out[prev + len_off + k] = (unsigned char)(plen >> (8 * k));
+        }
+        prev = out.size();
+        out.insert(out.end(), in.v.begin() + b, in.v.begin() + e);
+        uint32_t l32 = (uint32_t)len;
+        for (int k = 0; k < 4; ++k) out[prev + len_off + k] = (unsigned char)(l32 >> (8 * k));
+    }
+    out.resize((out.size() + 511) / 512 * 512 + (size_t)ring + 512, 0);
+    return out;
+}
+}  // namespace frontal_detail
+
+inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax, FrontalStreams* out) {
+    using frontal_detail::ByteStream;
+    FrontalStreams& S = *out;
+    S = FrontalStreams();
     const int n = P.n;
+    const bool lane_ok = lr_rows >= P.cmax + 2 && P.cmax <= 32;
+    S.lr_rows = lane_ok ? lr_rows : 0;
+    auto tri = [](uint32_t s) { return s * (s + 1) / 2; };
+    auto max_len = [](const ByteStream& b) {
+        size_t m = 0;
+        for (size_t r = 0; r < b.starts.size(); ++r)
+            m = std::max(m, (r + 1 < b.starts.size() ? b.starts[r + 1] : b.v.size()) - b.starts[r]);
+        return (int)m;
+    };
+    // ------------------------------------------------------------------ D2 forward / backward
+    ByteStream f2, b2;
     for (int j = -1; j < n; ++j) {
-        const size_t start = S.fwd.size();
+        f2.begin();
         const int c = j >= 0 ? P.col_ptr[j + 1] - P.col_ptr[j] : 0;
         const int q0 = j + 1 < n ? P.asm_ptr[j + 1] : 0, q1 = j + 1 < n ? P.asm_ptr[j + 2] : 0;
         const int e0 = q1 > q0 ? P.asm_eptr[q0] : 0, e1 = q1 > q0 ? P.asm_eptr[q1] : 0;
         const int o0 = j >= 0 ? P.obs_ptr[j] : 0, o1 = j >= 0 ? P.obs_ptr[j + 1] : 0;
-        put32(S.fwd, (uint32_t)c);
-        put32(S.fwd, j >= 0 ? P.piv_slot[j] : 0u);
-        put32(S.fwd, (uint32_t)(q1 - q0));
-        put32(S.fwd, (uint32_t)(e1 - e0));
-        put32(S.fwd, (uint32_t)(o1 - o0));
-        put32(S.fwd, 0u);
-        put64(S.fwd, j >= 0 ? P.rhs[j] : 0.0);
-        for (int a = 0; a < c; ++a) put16(S.fwd, P.col_slot[P.col_ptr[j] + a]);
-        pad(S.fwd, 8);
+        f2.put32((uint32_t)c);
+        f2.put32(j >= 0 ? P.piv_slot[j] : 0u);
+        f2.put32((uint32_t)(q1 - q0));
+        f2.put32((uint32_t)(e1 - e0));
+        f2.put32((uint32_t)(o1 - o0));
+        f2.put32(0u);
+        f2.put64(j >= 0 ? P.rhs[j] : 0.0);
+        for (int a = 0; a < c; ++a) f2.put16(P.col_slot[P.col_ptr[j] + a]);
+        f2.pad(8);
         for (int q = q0; q < q1; ++q) {
-            put32(S.fwd, P.asm_addr[q]);
-            put32(S.fwd, (uint32_t)(P.asm_eptr[q + 1] - P.asm_eptr[q]));
+            f2.put32(P.asm_addr[q]);
+            f2.put32((uint32_t)(P.asm_eptr[q + 1] - P.asm_eptr[q]));
         }
-        for (int e = e0; e < e1; ++e) put64(S.fwd, P.ent_coef[e]);
-        for (int e = e0; e < e1; ++e) put32(S.fwd, (uint32_t)P.ent_term[e]);
-        pad(S.fwd, 8);
-        for (int o = o0; o < o1; ++o) put64(S.fwd, P.obs_val[o]);
-        for (int o = o0; o < o1; ++o) put32(S.fwd, (uint32_t)P.obs_row[o]);
-        pad(S.fwd, 16);
-        const size_t len = S.fwd.size() - start;
-        set32(S.fwd, start + 20, (uint32_t)len);
-        S.max_record = std::max(S.max_record, (int)len);
+        for (int e = e0; e < e1; ++e) f2.put64(P.ent_coef[e]);
+        for (int e = e0; e < e1; ++e) f2.put32((uint32_t)P.ent_term[e]);
+        f2.pad(8);
+        for (int o = o0; o < o1; ++o) f2.put64(P.obs_val[o]);
+        for (int o = o0; o < o1; ++o) f2.put32((uint32_t)P.obs_row[o]);
+        f2.pad(16);
     }
-    for (int j = n - 1; j >= 0; --j) {
-        const size_t start = S.bwd.size();
-        const int c = P.col_ptr[j + 1] - P.col_ptr[j];
-        const int cn = j > 0 ? P.col_ptr[j] - P.col_ptr[j - 1] : 0;
-        const int o0 = P.obs_ptr[j], o1 = P.obs_ptr[j + 1];
-        put32(S.bwd, (uint32_t)c);
-        put32(S.bwd, P.piv_slot[j]);
-        put32(S.bwd, (uint32_t)(o1 - o0));
-        put32(S.bwd, (uint32_t)P.perm[j]);
-        put32(S.bwd, 0u);
-        put32(S.bwd, (uint32_t)cn);
-        put64(S.bwd, P.rhs[j]);
-        for (int a = 0; a < c; ++a) put16(S.bwd, P.col_slot[P.col_ptr[j] + a]);
-        pad(S.bwd, 8);
-        for (int o = o0; o < o1; ++o) put64(S.bwd, P.obs_val[o]);
-        for (int o = o0; o < o1; ++o) put32(S.bwd, (uint32_t)P.obs_row[o]);
-        pad(S.bwd, 16);
-        const size_t len = S.bwd.size() - start;
-        set32(S.bwd, start + 16, (uint32_t)len);
-        S.max_record = std::max(S.max_record, (int)len);
+    for (int j = n; j >= 0; --j) {   // j == n: prologue record
+        b2.begin();
+        const bool pro = j == n;
+        const int c = pro ? 0 : P.col_ptr[j + 1] - P.col_ptr[j];
+        const int cn = (!pro && j > 0) ? P.col_ptr[j] - P.col_ptr[j - 1] : (pro ? P.col_ptr[n] - P.col_ptr[n - 1] : 0);
+        const int o0 = pro ? 0 : P.obs_ptr[j], o1 = pro ? 0 : P.obs_ptr[j + 1];
+        b2.put32((uint32_t)c);
+        b2.put32(pro ? 0u : P.piv_slot[j]);
+        b2.put32((uint32_t)(o1 - o0));
+        b2.put32(pro ? 0u : (uint32_t)P.perm[j]);
+        b2.put32(0u);
+        b2.put32((uint32_t)cn);
+        b2.put64(pro ? 0.0 : P.rhs[j]);
+        b2.put64(0.0);
+        for (int a = 0; a < c; ++a) b2.put16(P.col_slot[P.col_ptr[j] + a]);
+        b2.pad(8);
+        for (int o = o0; o < o1; ++o) b2.put64(P.obs_val[o]);
+        for (int o = o0; o < o1; ++o) b2.put32((uint32_t)P.obs_row[o]);
+        b2.pad(16);
     }
-    int ring = 1024;
-    while (ring < 2 * S.max_record + 512) ring *= 2;
+    // ------------------------------------------------------------------ D1 forward / backward
+    ByteStream f1, b1;
+    if (lane_ok) {
+        for (int j = -1; j < n; ++j) {
+            f1.begin();
+            const int c = j >= 0 ? P.col_ptr[j + 1] - P.col_ptr[j] : 0, c4 = (c + 3) & ~3;
+            const uint32_t p = j >= 0 ? P.piv_slot[j] : 0u;
+            const int q0 = j + 1 < n ? P.asm_ptr[j + 1] : 0, q1 = j + 1 < n ? P.asm_ptr[j + 2] : 0;
+            const int e0 = q1 > q0 ? P.asm_eptr[q0] : 0, e1 = q1 > q0 ? P.asm_eptr[q1] : 0;
+            f1.put32((uint32_t)c);
+            f1.put32(256u * p);
+            f1.put32(256u * (tri(p) + p));
+            f1.put32((uint32_t)(q1 - q0));
+            f1.put32((uint32_t)(e1 - e0));
+            f1.put32(0u);
+            f1.put64(j >= 0 ? P.rhs[j] : 0.0);
+            for (int a = 0; a < c4; ++a) {
+                const uint32_t sa = a < c ? P.col_slot[P.col_ptr[j] + a] : 0u;
+                f1.put32(a < c ? 256u * frontal_tri(sa, p) : 0u);
+            }
+            for (int a = 0; a < c4; ++a) f1.put32(a < c ? 256u * tri(P.col_slot[P.col_ptr[j] + a]) : 0u);
+            for (int a = 0; a < c4; ++a) f1.put32(a < c ? 256u * P.col_slot[P.col_ptr[j] + a] : 0u);
+            for (int q = q0; q < q1; ++q) {
+                f1.put32(256u * P.asm_addr[q]);
+                f1.put32((uint32_t)(P.asm_eptr[q + 1] - P.asm_eptr[q]));
+            }
+            f1.pad(16);
+            for (int e = e0; e < e1; ++e) f1.put64(P.ent_coef[e]);
+            f1.pad(16);
+            for (int e = e0; e < e1; ++e) f1.put32(256u * (uint32_t)P.ent_term[e]);
+            f1.pad(16);
+        }
+        // factor-block ring of the backward substitution: simulate it so that every record says which blocks to request
+        // (up to dmax pivots ahead, as many as fit) and how many of the youngest copy groups may still be pending when it
+        // is consumed.  Step t handles pivot n-1-t; its block [1/L_jj, y_j, column] has c + 2 rows and is contiguous in
+        // the ring (the tail is skipped when it does not fit).  One group is committed per step (group 0 = prologue).
+        struct Blk {
+            int row, rows;
+        };
+        struct Req {
+            uint32_t row, rows, src;
+        };
+        std::vector<Blk> blk(n);
+        std::vector<std::vector<Req>> reqs(n + 1);   // reqs[0] = prologue, reqs[t + 1] = step t
+        std::vector<int> grp(n, -1);
+        std::vector<uint32_t> kw(n, 0);
+        auto rows_of = [&](int t) { const int jj = n - 1 - t; return P.col_ptr[jj + 1] - P.col_ptr[jj] + 2; };
+        auto src_of = [&](int t) { const int jj = n - 1 - t; return (uint32_t)(P.col_ptr[jj] + 2 * jj); };
+        int f = 0, head = 0, oldest = 0;   // frontier step, next free ring row, oldest live step
+        auto try_alloc = [&](int t, int g) -> bool {
+            const int rows = rows_of(t);
+            int cand = head + rows <= lr_rows ? head : 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                bool clash = false;
+                for (int u = oldest; u < t; ++u)
+                    if (cand < blk[u].row + blk[u].rows && blk[u].row < cand + rows) clash = true;
+                if (!clash) {
+                    blk[t] = Blk{cand, rows};
+                    head = cand + rows;
+                    grp[t] = g;
+                    reqs[g].push_back(Req{(uint32_t)cand, (uint32_t)rows, src_of(t)});
+                    return true;
+                }
+                if (cand == 0) break;
+                cand = 0;   // also try the start of the ring
+            }
+            return false;
+        };
+        while (f < n && f < dmax && try_alloc(f, 0)) ++f;
+        for (int t = 0; t < n; ++t) {
+            oldest = t;
+            while (f < n && f <= t + dmax && try_alloc(f, t + 1)) ++f;
+            kw[t] = (uint32_t)(t + 1 - grp[t]);   // grp[t] >= 0: once the ring has drained a block of <= lr_rows rows fits
+        }
+        for (int j = n; j >= 0; --j) {
+            b1.begin();
+            const bool pro = j == n;
+            const int t = n - 1 - j;
+            const int c = pro ? 0 : P.col_ptr[j + 1] - P.col_ptr[j], c4 = (c + 3) & ~3;
+            const int o0 = pro ? 0 : P.obs_ptr[j], o1 = pro ? 0 : P.obs_ptr[j + 1];
+            const std::vector<Req>& rq = reqs[pro ? 0 : t + 1];
+            b1.put32((uint32_t)c);
+            b1.put32(pro ? 0u : 256u * P.piv_slot[j]);
+            b1.put32((uint32_t)(o1 - o0));
+            b1.put32(pro ? 0u : (uint32_t)P.perm[j]);
+            b1.put32(0u);
+            b1.put32((uint32_t)rq.size() | ((pro ? 0u : kw[t]) << 16));
+            b1.put64(pro ? 0.0 : P.rhs[j]);
+            b1.put32(pro ? 0u : 256u * (uint32_t)blk[t].row);
+            b1.put32(0u);
+            b1.put64(0.0);
+            for (const Req& r : rq) {
+                b1.put32(256u * r.row);
+                b1.put32(r.rows);
+                b1.put32(r.src);
+                b1.put32(0u);
+            }
+            for (int a = 0; a < c4; ++a) b1.put32(a < c ? 256u * P.col_slot[P.col_ptr[j] + a] : 0u);
+            for (int o = o0; o < o1; ++o) b1.put64(P.obs_val[o]);
+            b1.pad(16);
+            for (int o = o0; o < o1; ++o) b1.put32(256u * (uint32_t)P.obs_row[o]);
+            b1.pad(16);
+        }
+    }
+    S.max_record = std::max(std::max(max_len(f2), max_len(b2)), std::max(max_len(f1), max_len(b1)));
+    // ring: the reader needs the current record complete while the loader runs up to one ring ahead in 512-byte chunks;
+    // the records consumed under a wait that leaves dmax + 1 copy groups pending must be older than those groups
+    int ring = 2048;
+    while (ring < 3 * S.max_record + 1024 || ring < (dmax + 4) * std::max(max_len(b1), max_len(b2)) + 2048) ring *= 2;
     S.ring_bytes = ring;
-    // the ring loader fetches whole 512-byte chunks up to one ring ahead of the reader: zero padding behind the streams
-    S.fwd.resize((S.fwd.size() + 511) / 512 * 512 + (size_t)ring + 512, 0);
-    S.bwd.resize((S.bwd.size() + 511) / 512 * 512 + (size_t)ring + 512, 0);
+    S.fwd = frontal_detail::finish_stream(f2, 20, ring);
+    S.bwd = frontal_detail::finish_stream(b2, 16, ring);
+    if (lane_ok) {
+        S.fwd1 = frontal_detail::finish_stream(f1, 20, ring);
+        S.bwd1 = frontal_detail::finish_stream(b1, 16, ring);
+    }
 }
 
 }  // namespace tfin

@@ -134,19 +134,31 @@ struct FrontalSet {
     FrontalProgram host;
     FrontalStreams streams;
     int ncv = 0;
-    DevBuf<unsigned char> fwd, bwd;
+    DevBuf<unsigned char> fwd, bwd, fwd1, bwd1;
     void release() {
         fwd.release();
         bwd.release();
+        fwd1.release();
+        bwd1.release();
         ok = false;
     }
-    // (re)pack the instruction streams from the host program and copy them to the device
-    int upload(cudaStream_t st) {
-        frontal_pack_streams(host, &streams);
+    // (re)pack the instruction streams from the host program and copy them to the device.  D1's factor-row ring gets the
+    // shared memory that two resident warps per SM leave free (n_obs and the affine coefficient rows are known here).
+    int upload(cudaStream_t st, int n_obs, int smem_optin) {
+        const int ntri = host.nslots * (host.nslots + 1) / 2;
+        const int base_rows = ntri + host.nslots + n_obs + (ncv <= TFIN_MAX_TERMS ? ncv : 0);
+        const long long half = ((long long)smem_optin + 1024) / 2 - 1024 - 8192;   // two CTAs per SM, instruction ring <= 8 KB
+        long long lr = half / 256 - base_rows;
+        if (lr < host.cmax + 2) lr = ((long long)smem_optin - 8192) / 256 - base_rows;   // one CTA per SM
+        lr = std::min<long long>(lr, 160);
+        if (lr < host.cmax + 2) lr = 0;   // D1 cannot serve this front (D2 will)
+        frontal_pack_streams(host, (int)lr, FRONTAL_DMAX, &streams);
         if (int e = fwd.upload(streams.fwd, st)) return e;
-        return bwd.upload(streams.bwd, st);
+        if (int e = bwd.upload(streams.bwd, st)) return e;
+        if (int e = fwd1.upload(streams.fwd1, st)) return e;
+        return bwd1.upload(streams.bwd1, st);
     }
-    FrontalDev dev() const {
+    FrontalDev dev(bool lane_kernel) const {
         FrontalDev d{};
         d.n = host.n;
         d.nslots = host.nslots;
@@ -154,9 +166,10 @@ struct FrontalSet {
         d.ncv = ncv;
         d.ntri = host.nslots * (host.nslots + 1) / 2;
         d.ring_bytes = streams.ring_bytes;
+        d.lr_rows = streams.lr_rows;
         d.nnzL = host.nnzL;
-        d.fwd = fwd.p;
-        d.bwd = bwd.p;
+        d.fwd = lane_kernel ? fwd1.p : fwd.p;
+        d.bwd = lane_kernel ? bwd1.p : bwd.p;
         return d;
     }
 };
@@ -485,7 +498,7 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
         h->fr_aff.why = frontal_build(n, row_ptr, col_idx, rhs, terms, &h->fr_aff.host);
         if (h->fr_aff.why.empty()) {
             h->fr_aff.ncv = n_terms;
-            if (int e = h->fr_aff.upload(h->stream)) return e;
+            if (int e = h->fr_aff.upload(h->stream, 0, h->max_smem_optin)) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
             h->fr_aff.ok = true;
         }
@@ -546,7 +559,7 @@ extern "C" int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_
     for (FrontalSet* fs : {&h->fr_aff, &h->fr_nod})
         if (fs->ok) {
             frontal_set_obs(fs->host, n_obs, ptr, idx, val);
-            if (int e = fs->upload(h->stream)) return e;
+            if (int e = fs->upload(h->stream, n_obs, h->max_smem_optin)) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
         }
     // B_obs^T as CSR over the n dofs: right-hand sides of the adjoint solves
@@ -614,7 +627,7 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
             h->fr_nod.ncv = n_cells + 1;
             if (!h->h_obs_ptr.empty())
                 frontal_set_obs(h->fr_nod.host, h->n_obs, h->h_obs_ptr.data(), h->h_obs_idx.data(), h->h_obs_val.data());
-            if (int e = h->fr_nod.upload(h->stream)) return e;
+            if (int e = h->fr_nod.upload(h->stream, h->n_obs, h->max_smem_optin)) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
             h->fr_nod.ok = true;
         }
@@ -991,6 +1004,14 @@ static const void* frontal_lane_fn(int cmax) {
            : cmax <= 24 ? (const void*)frontal_lane_kernel<24> : (const void*)frontal_lane_kernel<32>;
 }
 
+static const void* frontal_cta_fn(int mode, int cmax) {
+#define TFIN_CTA_FN(M)                                                                                        \
+    (cmax <= 32 ? (const void*)frontal_cta_kernel<M, 1> : cmax <= 64 ? (const void*)frontal_cta_kernel<M, 2>   \
+     : cmax <= 128 ? (const void*)frontal_cta_kernel<M, 4> : cmax <= 256 ? (const void*)frontal_cta_kernel<M, 8> : nullptr)
+    return mode == FRONTAL_MODE_QOI ? TFIN_CTA_FN(FRONTAL_MODE_QOI) : TFIN_CTA_FN(FRONTAL_MODE_SOLVE);
+#undef TFIN_CTA_FN
+}
+
 struct FrontalGeom {
     int kernel = 0;   // 1 = D1 sample per thread, 2 = D2 sample per CTA
     int mode = 0;     // D2: FRONTAL_MODE_QOI / FRONTAL_MODE_SOLVE
@@ -1007,9 +1028,9 @@ static FrontalGeom frontal_geom(tfin_ctx* h, bool nodal, bool want_w) {
     const int ntri = P.nslots * (P.nslots + 1) / 2;
     const int ncv_smem = nodal ? 0 : fs.ncv;
     const int ring = fs.streams.ring_bytes;
-    if (h->frontal_kernel != 2 && P.cmax <= 32) {
+    if (h->frontal_kernel != 2 && P.cmax <= 32 && fs.streams.lr_rows > 0) {
         const void* fn = frontal_lane_fn(P.cmax);
-        const size_t sm = frontal_lane_smem(ntri, P.nslots, h->n_obs, ncv_smem, ring);
+        const size_t sm = frontal_lane_smem(ntri, P.nslots, h->n_obs, ncv_smem, fs.streams.lr_rows, ring);
         if (sm <= (size_t)h->max_smem_optin &&
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess) {
             int occ = 0;
@@ -1037,8 +1058,8 @@ static FrontalGeom frontal_geom(tfin_ctx* h, bool nodal, bool want_w) {
         T = 32 * (int)std::min(16.0, std::max(1.0, std::ceil(pairs / (32.0 * 12.0))));
     }
     T = std::max(32, std::min(1024, (T + 31) & ~31));
-    const void* fn = mode == FRONTAL_MODE_QOI ? (const void*)frontal_cta_kernel<FRONTAL_MODE_QOI>
-                                              : (const void*)frontal_cta_kernel<FRONTAL_MODE_SOLVE>;
+    const void* fn = frontal_cta_fn(mode, P.cmax);
+    if (!fn) return g;   // columns of more than 256 entries: PCG
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
         cudaGetLastError();
         return g;
@@ -1064,7 +1085,7 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
     if (!fs.ok || g.kernel == 0)
         return fail(TFIN_E_STATE, "direct solver unavailable for this operator: %s", fs.ok ? "front does not fit shared memory" : fs.why.c_str());
     const FrontalProgram& P = fs.host;
-    const FrontalDev dev = fs.dev();
+    const FrontalDev dev = fs.dev(g.kernel == 1);
     const size_t per_sample_work = (size_t)P.nnzL + 2 * (size_t)P.n;
     // the nodal operator needs the coefficient vector of every sample in HBM: bound that workspace by chunking
     int64_t chunk = N;
@@ -1105,10 +1126,10 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
             if (g.mode == FRONTAL_MODE_SOLVE) {
                 if (int e = h->d_fwork.reserve((size_t)grid * per_sample_work)) return e;
                 io.work = h->d_fwork.p;
-                frontal_cta_kernel<FRONTAL_MODE_SOLVE><<<grid, g.threads, g.smem, st>>>(dev, io, g.cta);
-            } else {
-                frontal_cta_kernel<FRONTAL_MODE_QOI><<<grid, g.threads, g.smem, st>>>(dev, io, g.cta);
             }
+            FrontalCtaSmem cta = g.cta;
+            void* args[] = {(void*)&dev, (void*)&io, (void*)&cta};
+            TFIN_CUDA(cudaLaunchKernel(frontal_cta_fn(g.mode, P.cmax), dim3(grid), dim3(g.threads), args, g.smem, st));
         }
         TFIN_CUDA(cudaGetLastError());
         h->launches += 1;
@@ -2151,3 +2172,50 @@ extern "C" int64_t tfin_frontal_array(void* prog, const char* name, void* dst, i
 }
 
 extern "C" void tfin_frontal_free(void* prog) { delete static_cast<tfin_frontal_program*>(prog); }
+
+// ------------------------------------------------------------------------------------------------ micro-benchmarks
+// Shared-memory read bandwidth of the device (all SMs): the roofline denominator of the on-chip kernels (K1/K2 PCG, D1 /
+// D2 frontal solver), which never touch HBM in their inner loops.  Conflict-free 16-byte loads, 16 per iteration.
+__global__ void __launch_bounds__(1024) smem_bandwidth_kernel(int iters, double* sink) {
+    extern __shared__ __align__(16) double2 sm_bw[];
+    const int t = threadIdx.x, T = blockDim.x;
+    for (int i = t; i < 4 * T; i += T) sm_bw[i] = make_double2(1.0 + i, 2.0);
+    __syncthreads();
+    double2 acc = make_double2(0.0, 0.0);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const double2 v = sm_bw[t + T * ((u + it) & 3)];
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+    }
+    if (acc.x + acc.y == -1.0) sink[blockIdx.x] = acc.x;   // never true: keeps the loads alive
+}
+
+extern "C" int tfin_smem_bandwidth(tfin_handle_t h, double* gbs_out) {
+    CHECK_HANDLE(h);
+    if (!gbs_out) return fail(TFIN_E_ARG, "tfin_smem_bandwidth: gbs_out is NULL");
+    const int T = 1024, iters = 20000;
+    const size_t smem = (size_t)4 * T * sizeof(double2);
+    TFIN_CUDA(cudaFuncSetAttribute(smem_bandwidth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    TFIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smem_bandwidth_kernel, T, smem));
+    const int grid = h->sm_count * std::max(occ, 1);
+    if (int e = h->d_relres.reserve((size_t)grid)) return e;
+    cudaEvent_t e0, e1;
+    TFIN_CUDA(cudaEventCreate(&e0));
+    TFIN_CUDA(cudaEventCreate(&e1));
+    smem_bandwidth_kernel<<<grid, T, smem, h->stream>>>(200, h->d_relres.p);   // warm-up
+    TFIN_CUDA(cudaEventRecord(e0, h->stream));
+    smem_bandwidth_kernel<<<grid, T, smem, h->stream>>>(iters, h->d_relres.p);
+    TFIN_CUDA(cudaEventRecord(e1, h->stream));
+    TFIN_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    TFIN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    h->launches += 2;
+    *gbs_out = (double)grid * T * iters * 16.0 * 16.0 / (ms * 1e-3) / 1e9;
+    return 0;
+}

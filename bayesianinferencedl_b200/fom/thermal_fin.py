@@ -14,7 +14,8 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["get_space", "FinSpace", "FinMesh", "Function", "resolution_to_m"]
+__all__ = ["get_space", "get_space_unstructured", "unstructured_fin_mesh", "FinSpace", "FinMesh", "Function",
+           "resolution_to_m"]
 
 # Geometry of fom/thermal_fin.py:7-15 in units of 0.25 (all corners are multiples of 0.25).
 _POST_X = (10, 14)          # x in [2.5, 3.5]
@@ -173,3 +174,72 @@ def get_space(resolution, m=None):
         m = resolution_to_m(resolution)
     coords, cells = _build_structured(int(m))
     return FinSpace(FinMesh(coords, cells), m=int(m))
+
+
+def _inside_fin(p):
+    x, y = p[:, 0], p[:, 1]
+    post = (x >= 2.5) & (x <= 3.5) & (y >= 0) & (y <= 4)
+    band = np.zeros(len(p), dtype=bool)
+    for yb in (0.75, 1.75, 2.75, 3.75):
+        band |= (y >= yb) & (y <= yb + 0.25)
+    return post | (band & (x >= 0) & (x <= 6))
+
+
+def unstructured_fin_mesh(h=0.125, seed=0, jitter=0.3):
+    """UNSTRUCTURED, non-conforming triangulation of the fin (Delaunay of jittered lattice points): the stand-in for the
+    reference's mshr mesh (``mshr.generate_mesh(geometry, 40)``, fom/thermal_fin.py:17, not shipped and not reproducible
+    without CGAL).  Like that mesh it has varying vertex degrees (6-7 non-zeros per row on average, up to 9-10) and cells
+    that straddle x = 2.5 / 3.5, which keep marker 0 under dolfin's ``SubDomain.mark`` (SURVEY Q-1).  h = 0.0925 gives
+    1439 dofs (the reference mesh has 1446).  Returns (coords, cells)."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    nx, ny = int(round(6 / h)), int(round(4 / h))
+    X, Y = np.meshgrid(np.arange(nx + 1) * (6.0 / nx), np.arange(ny + 1) * (4.0 / ny))
+    pts = np.stack([X.ravel(), Y.ravel()], axis=1)
+    # lattice lines rarely hit the band edges y = 0.75 + 0.25 i exactly: add the geometry's own boundary points
+    hx, hy = 6.0 / nx, 4.0 / ny
+    extra = []
+    for yb in (0.75, 1.0, 1.75, 2.0, 2.75, 3.0, 3.75, 4.0):
+        xs = np.concatenate([np.arange(0, 2.5 + 1e-9, hx), np.arange(3.5, 6 + 1e-9, hx)])
+        extra.append(np.stack([xs, np.full_like(xs, yb)], axis=1))
+    for xb in (0.0, 2.5, 3.5, 6.0):
+        ys = np.arange(0, 4 + 1e-9, hy)
+        extra.append(np.stack([np.full_like(ys, xb), ys], axis=1))
+    pts = np.concatenate([pts] + extra)
+    pts = pts[_inside_fin(pts)]
+    # drop lattice points that crowd a boundary point (closer than 0.4 h), keeping the boundary ones
+    pts = np.unique(np.round(pts, 12), axis=0)
+    on_edge = np.zeros(len(pts), dtype=bool)
+    for yb in (0.75, 1.0, 1.75, 2.0, 2.75, 3.0, 3.75, 4.0, 0.0):
+        on_edge |= np.abs(pts[:, 1] - yb) < 1e-12
+    for xb in (0.0, 2.5, 3.5, 6.0):
+        on_edge |= np.abs(pts[:, 0] - xb) < 1e-12
+    from scipy.spatial import cKDTree
+    tree = cKDTree(pts[on_edge])
+    d, _ = tree.query(pts, k=1)
+    pts = pts[on_edge | (d > 0.4 * min(hx, hy))]
+    eps = 1e-9
+    interior = np.ones(len(pts), dtype=bool)
+    for dx, dy in ((hx, 0), (-hx, 0), (0, hy), (0, -hy), (hx, hy), (-hx, -hy), (hx, -hy), (-hx, hy)):
+        interior &= _inside_fin(pts + np.array([dx, dy]) * (1 - eps))
+    pts = pts.copy()
+    pts[interior] += rng.uniform(-jitter, jitter, (int(interior.sum()), 2)) * np.array([hx, hy])
+    cells = Delaunay(pts).simplices
+    cen = pts[cells].mean(axis=1)
+    keep = _inside_fin(cen)
+    for a, b in ((0, 1), (1, 2), (2, 0)):
+        keep &= _inside_fin((pts[cells[:, a]] + pts[cells[:, b]]) / 2)
+    cells = cells[keep]
+    a, b, c = pts[cells[:, 0]], pts[cells[:, 1]], pts[cells[:, 2]]
+    det = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0])
+    cells, det = cells[np.abs(det) > 1e-10], det[np.abs(det) > 1e-10]
+    cells[det < 0] = cells[det < 0][:, [0, 2, 1]]
+    used = np.unique(cells)
+    remap = -np.ones(len(pts), dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    return pts[used], remap[cells].astype(np.int32)
+
+
+def get_space_unstructured(h=0.0925, seed=0):
+    """P1 space on :func:`unstructured_fin_mesh` -- a reference-like (mshr-like) mesh of about 1446 dofs by default."""
+    return FinSpace.from_mesh(*unstructured_fin_mesh(h=h, seed=seed))

@@ -255,6 +255,13 @@ int tfin_frontal_analyze(int32_t n, int32_t nnz, const int32_t* row_ptr, const i
 int64_t tfin_frontal_array(void* prog, const char* name, void* dst, int64_t dst_bytes);
 void tfin_frontal_free(void* prog);
 
+/*
+ * Micro-benchmark: aggregate shared-memory read bandwidth of the device in GB/s (conflict-free 16-byte loads on every
+ * SM).  The on-chip kernels (PCG K1/K2, frontal D1/D2) keep their working set in shared memory, so this -- not HBM -- is
+ * the roofline denominator bench.py reports them against.
+ */
+int tfin_smem_bandwidth(tfin_handle_t h, double* gbs_out);
+
 /* Number of CUDA kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t tfin_kernel_launches(tfin_handle_t h);
 

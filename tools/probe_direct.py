@@ -73,7 +73,7 @@ if "big" in which:
     N = 592
     theta = torch.tensor(np.random.default_rng(2).uniform(0.1, 10.0, (N, 9)), device="cuda")
     q = torch.empty((N, 9), device="cuda", dtype=torch.float64)
-    for thr in (0, 256, 1024):
+    for thr in (0, 128, 256, 384):
         h.set_int("fom_solver", 2); h.set_int("frontal_threads", thr)
         ms = timeit(lambda: h.fom_affine_raw(theta.data_ptr(), N, 0, 1, 1e-12, 50000, qoi=q.data_ptr(), stream=st), reps=1, warm=0)
         print(f"m=26 direct D2 qoi threads={h.get_int('frontal_threads')} ctas/sm={h.get_int('frontal_ctas_per_sm')}: {N/ms*1e3:.1f} solves/s ({ms:.0f} ms)", flush=True)
