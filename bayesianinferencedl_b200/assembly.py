@@ -78,6 +78,28 @@ def classify_facets(coords, facets):
     return mark
 
 
+def classify_facets_affine(coords, facets):
+    """Exterior-facet markers of ``AffineROMFin`` exactly as rom/averaged_affine_ROM.py:116-138 applies them: sub-domain
+    objects 1..9 in order (1 = SubFinBoundary of sub-fin 1, 5 = CenterFinBoundary, the others the plain SubFin boxes),
+    then ``bottom`` = 10; a facet is marked iff both vertices and the midpoint satisfy ``inside``.  Markers 1..9 carry the
+    Robin term (:156-162), 10 the root flux (:163), 0 nothing.  Differs from :func:`classify_facets` only on boundary facets
+    that straddle x = 2.5 / 3.5, which no sub-domain box contains."""
+    p0, p1 = coords[facets[:, 0]], coords[facets[:, 1]]
+    pts = (p0, p1, 0.5 * (p0 + p1))
+    near0 = lambda y: np.abs(y) < DOLFIN_EPS
+    mark = np.zeros(len(facets), dtype=np.int8)
+    for q in range(1, NUM_SUBDOMAINS + 1):
+        ok = np.ones(len(facets), dtype=bool)
+        for p in pts:
+            ok &= _inside_subdomain(q, p[:, 0], p[:, 1])
+            if q == 5:
+                ok &= ~near0(p[:, 1])
+        mark[ok] = q
+    bottom = near0(pts[0][:, 1]) & near0(pts[1][:, 1]) & near0(pts[2][:, 1])
+    mark[bottom] = 10
+    return mark
+
+
 @dataclass
 class FinOperators:
     n: int
@@ -87,7 +109,8 @@ class FinOperators:
     cell_markers: np.ndarray
     row_ptr: np.ndarray            # (n+1,) int32
     col_idx: np.ndarray            # (nnz,) int32, sorted within each row
-    vals: np.ndarray               # (10, nnz) float64: [Bi*M_Gamma, K_1 .. K_9]
+    vals: np.ndarray               # (10, nnz) float64: [Bi*M_Gamma, K_1 .. K_9]; M_Gamma with Fin's facet markers
+    robin_affine: np.ndarray       # (nnz,) Bi*M_Gamma with AffineROMFin's own facet markers (averaged_affine_ROM.py:116-138)
     k_unmarked: np.ndarray         # (nnz,) stiffness of marker-0 cells (SURVEY Q-1; zero on conforming meshes)
     rhs: np.ndarray                # (n,)
     Ke: np.ndarray                 # (n_cells, 3, 3)
@@ -110,7 +133,13 @@ class FinOperators:
     def affine_values(self, theta):
         """CSR values of A(theta) = sum_q theta_q K_q + Bi M (host helper, not the product path)."""
         theta = np.asarray(theta, dtype=np.float64)
-        return self.vals[0] + theta @ self.vals[1:]
+        return self.robin_affine + theta @ self.vals[1:]
+
+    def affine_terms(self):
+        """(10, nnz) terms of the AFFINE model: its own Robin matrix, then K_1 .. K_9."""
+        if np.array_equal(self.robin_affine, self.vals[0]):
+            return self.vals
+        return np.concatenate([self.robin_affine[None, :], self.vals[1:]], axis=0)
 
     def stiffness_values(self):
         """CSR values of the full stiffness K (all cells, marker 0 included)."""
@@ -195,11 +224,20 @@ def build_operators(V) -> FinOperators:
         assert np.all(ukey[p] == i * n + j)
         return p
 
-    r0, r1 = robin[:, 0], robin[:, 1]
-    np.add.at(vals[0], pos(r0, r0), BIOT * lrob / 3.0)
-    np.add.at(vals[0], pos(r1, r1), BIOT * lrob / 3.0)
-    np.add.at(vals[0], pos(r0, r1), BIOT * lrob / 6.0)
-    np.add.at(vals[0], pos(r1, r0), BIOT * lrob / 6.0)
+    def robin_values(edges, lengths):
+        out = np.zeros(nnz)
+        e0, e1 = edges[:, 0], edges[:, 1]
+        np.add.at(out, pos(e0, e0), BIOT * lengths / 3.0)
+        np.add.at(out, pos(e1, e1), BIOT * lengths / 3.0)
+        np.add.at(out, pos(e0, e1), BIOT * lengths / 6.0)
+        np.add.at(out, pos(e1, e0), BIOT * lengths / 6.0)
+        return out
+
+    vals[0] = robin_values(robin, lrob)
+    fmark_aff = classify_facets_affine(coords, facets)
+    sel_aff = (fmark_aff >= 1) & (fmark_aff <= 9)
+    assert np.array_equal(fmark_aff == 10, fmark == 2)
+    robin_affine = vals[0] if np.array_equal(sel_aff, fmark == 1) else robin_values(facets[sel_aff], flen[sel_aff])
 
     # --- observation / averaging operators, appendix A.2
     subfin_area = np.array([area[markers == q].sum() for q in range(1, NUM_SUBDOMAINS + 1)])
@@ -216,7 +254,8 @@ def build_operators(V) -> FinOperators:
 
     ops = FinOperators(
         n=n, n_cells=nc, coords=coords, cells=cells, cell_markers=markers,
-        row_ptr=row_ptr.astype(np.int32), col_idx=cols_u.astype(np.int32), vals=vals, k_unmarked=k0,
+        row_ptr=row_ptr.astype(np.int32), col_idx=cols_u.astype(np.int32), vals=vals, robin_affine=robin_affine,
+        k_unmarked=k0,
         rhs=rhs, Ke=Ke, cell_area=area, subfin_area=subfin_area, B_obs=B_obs, C=C,
         domain_measure=domain_measure, boundary_dofs=np.unique(robin.ravel()))
     try:

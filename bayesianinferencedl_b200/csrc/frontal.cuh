@@ -33,6 +33,7 @@ struct FrontalDev {
     int ntri;                      // nslots (nslots + 1) / 2
     int ring_bytes;                // power of two, see frontal_pack_streams
     int lr_rows;                   // D1: rows of the factor-row ring of the backward substitution
+    int lanes;                     // D1: samples per warp (32, 16 or 8): fewer lanes = narrower rows = more resident warps
     long long nnzL;
     const unsigned char* fwd;      // forward stream (frontal_host.h: frontal_pack_streams)
     const unsigned char* bwd;      // backward stream
@@ -87,8 +88,9 @@ struct StreamRing {
 // ------------------------------------------------------------------------------------------------ D1
 // shared memory per warp:  F[ntri][32] | yv[nslots][32] | qacc[n_obs][32] | cvec[ncv][32] (affine only) |
 //                          factor-row ring [lr_rows][32] (backward substitution) | instruction ring
-__host__ __device__ inline size_t frontal_lane_smem(int ntri, int nslots, int n_obs, int ncv_smem, int lr_rows, int ring_bytes) {
-    return (size_t)(ntri + nslots + n_obs + ncv_smem + lr_rows) * 32 * sizeof(double) + (size_t)ring_bytes;
+__host__ __device__ inline size_t frontal_lane_smem(int ntri, int nslots, int n_obs, int ncv_smem, int lr_rows, int lanes,
+                                                    int ring_bytes) {
+    return (size_t)(ntri + nslots + n_obs + ncv_smem + lr_rows) * lanes * sizeof(double) + (size_t)ring_bytes;
 }
 
 #define FRONTAL_DMAX 7   // the backward substitution prefetches the factor rows of up to DMAX pivots ahead
@@ -113,46 +115,51 @@ template <int CM>
 __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalIO io) {
     static_assert(CM % 4 == 0, "columns are read four entries at a time");
     extern __shared__ __align__(16) double fsm[];
-    const int lane = threadIdx.x;
-    // byte-addressed views of this lane's column of every [row][lane] array (one row = 256 bytes)
+    // A warp carries LPG = P.lanes samples (32, 16 or 8); with fewer than 32 the upper lanes shadow the lower ones (same
+    // addresses, same values), which costs nothing but lets 2-4 x more warps share the SM's shared memory: the kernel is
+    // bound by instruction latency, not by lanes.
+    const int LPG = P.lanes, xlane = threadIdx.x;
+    const int lane = xlane & (LPG - 1);
+    const unsigned rb = 8u * (unsigned)LPG;            // bytes of one [row][lane] row
+    // byte-addressed views of this lane's column of every [row][lane] array
     char* F = reinterpret_cast<char*>(fsm + lane);
-    char* yv = F + (size_t)P.ntri * 256;
-    char* qacc = yv + (size_t)P.nslots * 256;
-    char* cvs = qacc + (size_t)io.n_obs * 256;        // affine only
-    char* Lring = cvs + (size_t)(io.cv_global ? 0 : P.ncv) * 256;
+    char* yv = F + (size_t)P.ntri * rb;
+    char* qacc = yv + (size_t)P.nslots * rb;
+    char* cvs = qacc + (size_t)io.n_obs * rb;        // affine only
+    char* Lring = cvs + (size_t)(io.cv_global ? 0 : P.ncv) * rb;
     StreamRing ring;
-    ring.buf = reinterpret_cast<unsigned char*>(Lring - lane * 8 + (size_t)P.lr_rows * 256);
+    ring.buf = reinterpret_cast<unsigned char*>(Lring - lane * 8 + (size_t)P.lr_rows * rb);
     ring.mask = (unsigned)P.ring_bytes - 1u;
     const unsigned full = 0xffffffffu;
-    const long long n_groups = (io.N + 31) / 32;
+    const long long n_groups = (io.N + LPG - 1) / LPG;
     const int n = P.n;
     const size_t wrows = (size_t)P.nnzL + 2 * (size_t)n;   // per-CTA workspace rows: per pivot [1/L_jj, y_j, column]
-    char* Lw = reinterpret_cast<char*>(io.work + (size_t)blockIdx.x * wrows * 32 + lane);
+    char* Lw = reinterpret_cast<char*>(io.work + (size_t)blockIdx.x * wrows * LPG + lane);
     auto ld = [](const char* base, unsigned off) { return *reinterpret_cast<const double*>(base + off); };
     auto st = [](char* base, unsigned off, double v) { *reinterpret_cast<double*>(base + off) = v; };
 
     for (;;) {
         long long g = 0;
-        if (lane == 0) g = (long long)atomicAdd(io.counter, 1ULL);
+        if (xlane == 0) g = (long long)atomicAdd(io.counter, 1ULL);
         g = __shfl_sync(full, g, 0);
         if (g >= n_groups) break;
-        const long long s = g * 32 + lane;
-        const bool valid = s < io.N;
-        const long long sc = valid ? s : io.N - 1;
+        const long long s = g * LPG + lane;
+        const bool valid = s < io.N && xlane < LPG;
+        const long long sc = s < io.N ? s : io.N - 1;
         ring.reset(P.fwd);
-        ring.fill(lane, true);
+        ring.fill(xlane, true);
         cp_async_commit();
         const char* cv;      // coefficient vector of this lane, row t at byte offset 256 t
         if (io.cv_global) {
-            cv = reinterpret_cast<const char*>(io.cv_global + (size_t)g * P.ncv * 32 + lane);
+            cv = reinterpret_cast<const char*>(io.cv_global + (size_t)g * P.ncv * LPG + lane);
         } else {
             st(cvs, 0, 1.0);
-            for (int t = 1; t < P.ncv; ++t) st(cvs, 256u * t, io.in[sc * io.in_stride + (t - 1)]);
+            for (int t = 1; t < P.ncv; ++t) st(cvs, rb * t, io.in[sc * io.in_stride + (t - 1)]);
             cv = cvs;
         }
-        for (int e = 0; e < P.ntri; ++e) st(F, 256u * e, 0.0);
-        for (int e = 0; e < P.nslots; ++e) st(yv, 256u * e, 0.0);
-        for (int o = 0; o < io.n_obs; ++o) st(qacc, 256u * o, 0.0);
+        for (int e = 0; e < P.ntri; ++e) st(F, rb * e, 0.0);
+        for (int e = 0; e < P.nslots; ++e) st(yv, rb * e, 0.0);
+        for (int o = 0; o < io.n_obs; ++o) st(qacc, rb * o, 0.0);
 
         bool bad = false;
         double yy = 0.0;
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
         for (int j = -1; j < n; ++j) {
             cp_async_wait<0>();
             __syncwarp();
-            ring.fill(lane, true);
+            ring.fill(xlane, true);
             cp_async_commit();
             const unsigned char* rec = ring.buf + (ring.rd & ring.mask);   // records never straddle the wrap point
             const uint4 h0 = *reinterpret_cast<const uint4*>(rec);        // c | 256 p | 256 (tri(p) + p) | npos
@@ -197,15 +204,15 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
                 const double yp = (ypre + __longlong_as_double(((long long)h1.w << 32) | h1.z)) * rinv;
                 yy = fma(yp, yp, yy);
                 st(Lj, 0, rinv);
-                st(Lj, 256, yp);
+                st(Lj, rb, yp);
 #pragma unroll
                 for (int a = 0; a < CM; ++a) {
                     if (a >= (int)c) break;
                     l[a] *= rinv;
-                    st(Lj, 512u + 256u * a, l[a]);
+                    st(Lj, rb * (2u + a), l[a]);
                     st(yv, sc_[a], fma(-l[a], yp, yo[a]));
                 }
-                Lj += (size_t)(c + 2) * 256;
+                Lj += (size_t)(c + 2) * rb;
             }
             {   // assembly of column j + 1: positions in chunks of 4 (loads first), the first two entries of a position unrolled
                 const unsigned char* pos = rec + 32 + 12 * c4;
@@ -268,7 +275,7 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
         cp_async_wait<0>();
         __syncwarp();
         ring.reset(P.bwd);
-        ring.fill(lane, true);
+        ring.fill(xlane, true);
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
@@ -276,17 +283,17 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
         const unsigned lring_s = smem_u32(Lring);
         auto request = [&](const unsigned char* rq, unsigned count) {
             for (unsigned i = 0; i < count; ++i) {
-                const uint4 r = *reinterpret_cast<const uint4*>(rq + 16 * i);   // 256 ring row | rows | source row
+                const uint4 r = *reinterpret_cast<const uint4*>(rq + 16 * i);   // rb x ring row | rows | source row
                 unsigned dst = lring_s + r.x;
-                const char* src = Lw + (size_t)r.z * 256;
-                for (unsigned k = 0; k < r.y; ++k, dst += 256, src += 256)
+                const char* src = Lw + (size_t)r.z * rb;
+                for (unsigned k = 0; k < r.y; ++k, dst += rb, src += rb)
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
             }
         };
         for (int j = n; j >= 0; --j) {   // j == n: prologue record (initial requests only)
-            ring.fill(lane, true);
+            ring.fill(xlane, true);
             const unsigned char* rec = ring.buf + (ring.rd & ring.mask);
-            const uint4 h0 = *reinterpret_cast<const uint4*>(rec);        // c | 256 p | nobs | dof
+            const uint4 h0 = *reinterpret_cast<const uint4*>(rec);        // c | rb p | nobs | dof
             const uint4 h1 = *reinterpret_cast<const uint4*>(rec + 16);   // bytes | npf, kw | rhs
             const unsigned c = h0.x, nobs = h0.z, npf = h1.y & 0xffffu, kw = h1.y >> 16;
             request(rec + 48, npf);
@@ -297,15 +304,15 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
                 const char* blk = Lring + *reinterpret_cast<const unsigned*>(rec + 32);
                 const unsigned char* cols = rec + 48 + 16 * npf;
                 const double rinv = ld(blk, 0);
-                double acc = ld(blk, 256);
+                double acc = ld(blk, rb);
 #pragma unroll
                 for (int q = 0; q < CM / 4; ++q) {
                     if (4 * q >= (int)c) break;
                     const uint4 cc = *reinterpret_cast<const uint4*>(cols + 16 * q);   // padded entries: slot 0, masked
-                    const double l0 = ld(blk, 512u + 1024u * q), w0 = ld(yv, cc.x);
-                    const double l1 = 4 * q + 1 < (int)c ? ld(blk, 768u + 1024u * q) : 0.0, w1 = ld(yv, cc.y);
-                    const double l2 = 4 * q + 2 < (int)c ? ld(blk, 1024u + 1024u * q) : 0.0, w2 = ld(yv, cc.z);
-                    const double l3 = 4 * q + 3 < (int)c ? ld(blk, 1280u + 1024u * q) : 0.0, w3 = ld(yv, cc.w);
+                    const double l0 = ld(blk, rb * (2u + 4 * q)), w0 = ld(yv, cc.x);
+                    const double l1 = 4 * q + 1 < (int)c ? ld(blk, rb * (3u + 4 * q)) : 0.0, w1 = ld(yv, cc.y);
+                    const double l2 = 4 * q + 2 < (int)c ? ld(blk, rb * (4u + 4 * q)) : 0.0, w2 = ld(yv, cc.z);
+                    const double l3 = 4 * q + 3 < (int)c ? ld(blk, rb * (5u + 4 * q)) : 0.0, w3 = ld(yv, cc.w);
                     acc = fma(-l0, w0, acc);
                     acc = fma(-l1, w1, acc);
                     acc = fma(-l2, w2, acc);
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
         }
         if (valid) {
             if (io.qoi_out)
-                for (int o = 0; o < io.n_obs; ++o) io.qoi_out[(size_t)s * io.n_obs + o] = ld(qacc, 256u * o);
+                for (int o = 0; o < io.n_obs; ++o) io.qoi_out[(size_t)s * io.n_obs + o] = ld(qacc, rb * o);
             const bool nan = !(bw == bw);
             if (io.status_out) io.status_out[s] = (bad || nan) ? TFIN_STATUS_BREAKDOWN : TFIN_STATUS_CONVERGED;
             if (io.iters_out) io.iters_out[s] = 0;
@@ -621,7 +628,7 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
 // row) and the writes (along the fastest output axis) are coalesced.
 __global__ void frontal_cellcoef_kernel(const double* __restrict__ k, long long N, int n, int n_cells,
                                         const int* __restrict__ cells, int coef_mode, int lane_major,
-                                        double* __restrict__ cv) {
+                                        double* __restrict__ cv) {   // lane_major: 0 = [sample][ncv], else samples per group
     __shared__ double tile[32][33];
     const int ncv = n_cells + 1;
     const long long g = blockIdx.y;
@@ -646,12 +653,14 @@ __global__ void frontal_cellcoef_kernel(const double* __restrict__ k, long long 
         }
     }
     __syncthreads();
-    if (lane_major) {   // x = sample lane, y = cell
+    if (lane_major) {   // x = sample, y = cell; groups of `lane_major` samples: [group][ncv][lane]
+        const long long s = g * 32 + tx;
+        const size_t grp = (size_t)(s / lane_major), ln = (size_t)(s % lane_major);
         for (int cy = ty; cy < 32; cy += 8) {
             const int c = c0 + cy;
-            if (c < n_cells) cv[((size_t)g * ncv + 1 + c) * 32 + tx] = tile[tx][cy];
+            if (c < n_cells) cv[(grp * ncv + 1 + c) * lane_major + ln] = tile[tx][cy];
         }
-        if (blockIdx.x == 0 && ty == 0) cv[(size_t)g * ncv * 32 + tx] = 1.0;
+        if (blockIdx.x == 0 && ty == 0) cv[grp * ncv * lane_major + ln] = 1.0;
     } else {            // x = cell, y = sample
         for (int sy = ty; sy < 32; sy += 8) {
             const long long s = g * 32 + sy;

@@ -342,7 +342,8 @@ inline void frontal_set_obs(FrontalProgram& P, int n_obs, const int32_t* obs_ptr
 //      +0 u32 c | +4 u32 pivot slot | +8 u32 nobs | +12 u32 dof (perm_j) | +16 u32 record bytes | +20 u32 c of the NEXT
 //      record | +24 f64 rhs_j | +32 pad | +40 slots | weights | rows | pad to 16
 // D1 (sample per thread) streams: everything the kernel would otherwise compute per use is stored pre-scaled to BYTE offsets
-// of its [entry][lane] shared-memory layout (one row = 256 bytes), in 16-byte groups that one LDS.128 fetches
+// of its [entry][lane] shared-memory layout (one row = 8 * lanes bytes; written 256 below for lanes = 32), in 16-byte
+// groups that one LDS.128 fetches
 //   forward record:
 //      +0 u32 c | +4 u32 256 p | +8 u32 256 (tri(p) + p) | +12 u32 npos | +16 u32 nent | +20 u32 record bytes | +24 f64 rhs_j
 //      +32 u32 gather[c4] (256 x address of entry (s_a, p)) | u32 row[c4] (256 tri(s_a)) | u32 col[c4] (256 s_a), c4 = c
@@ -358,6 +359,7 @@ struct FrontalStreams {
     int max_record = 0;   // largest record of any stream (bytes)
     int ring_bytes = 0;   // power of two
     int lr_rows = 0;      // rows of D1's factor-row ring the backward schedule was simulated for
+    int lanes = 32;       // samples per warp the D1 streams were scaled for (row = 8 * lanes bytes)
 };
 
 namespace frontal_detail {
@@ -408,13 +410,14 @@ inline std::vector<unsigned char> finish_stream(const ByteStream& in, size_t len
 }
 }  // namespace frontal_detail
 
-inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax, FrontalStreams* out) {
+inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax, int lanes, FrontalStreams* out) {
     using frontal_detail::ByteStream;
     FrontalStreams& S = *out;
     S = FrontalStreams();
     const int n = P.n;
     const bool lane_ok = lr_rows >= P.cmax + 2 && P.cmax <= 32;
     S.lr_rows = lane_ok ? lr_rows : 0;
+    S.lanes = lanes;
     auto tri = [](uint32_t s) { return s * (s + 1) / 2; };
     auto max_len = [](const ByteStream& b) {
         size_t m = 0;
@@ -472,6 +475,7 @@ inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax,
     }
     // ------------------------------------------------------------------ D1 forward / backward
     ByteStream f1, b1;
+    const uint32_t rb = 8u * (uint32_t)lanes;   // bytes of one [row][lane] row: D1 keeps `lanes` samples per warp
     if (lane_ok) {
         for (int j = -1; j < n; ++j) {
             f1.begin();
@@ -480,26 +484,26 @@ inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax,
             const int q0 = j + 1 < n ? P.asm_ptr[j + 1] : 0, q1 = j + 1 < n ? P.asm_ptr[j + 2] : 0;
             const int e0 = q1 > q0 ? P.asm_eptr[q0] : 0, e1 = q1 > q0 ? P.asm_eptr[q1] : 0;
             f1.put32((uint32_t)c);
-            f1.put32(256u * p);
-            f1.put32(256u * (tri(p) + p));
+            f1.put32(rb * p);
+            f1.put32(rb * (tri(p) + p));
             f1.put32((uint32_t)(q1 - q0));
             f1.put32((uint32_t)(e1 - e0));
             f1.put32(0u);
             f1.put64(j >= 0 ? P.rhs[j] : 0.0);
             for (int a = 0; a < c4; ++a) {
                 const uint32_t sa = a < c ? P.col_slot[P.col_ptr[j] + a] : 0u;
-                f1.put32(a < c ? 256u * frontal_tri(sa, p) : 0u);
+                f1.put32(a < c ? rb * frontal_tri(sa, p) : 0u);
             }
-            for (int a = 0; a < c4; ++a) f1.put32(a < c ? 256u * tri(P.col_slot[P.col_ptr[j] + a]) : 0u);
-            for (int a = 0; a < c4; ++a) f1.put32(a < c ? 256u * P.col_slot[P.col_ptr[j] + a] : 0u);
+            for (int a = 0; a < c4; ++a) f1.put32(a < c ? rb * tri(P.col_slot[P.col_ptr[j] + a]) : 0u);
+            for (int a = 0; a < c4; ++a) f1.put32(a < c ? rb * P.col_slot[P.col_ptr[j] + a] : 0u);
             for (int q = q0; q < q1; ++q) {
-                f1.put32(256u * P.asm_addr[q]);
+                f1.put32(rb * P.asm_addr[q]);
                 f1.put32((uint32_t)(P.asm_eptr[q + 1] - P.asm_eptr[q]));
             }
             f1.pad(16);
             for (int e = e0; e < e1; ++e) f1.put64(P.ent_coef[e]);
             f1.pad(16);
-            for (int e = e0; e < e1; ++e) f1.put32(256u * (uint32_t)P.ent_term[e]);
+            for (int e = e0; e < e1; ++e) f1.put32(rb * (uint32_t)P.ent_term[e]);
             f1.pad(16);
         }
         // factor-block ring of the backward substitution: simulate it so that every record says which blocks to request
@@ -552,25 +556,25 @@ inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax,
             const int o0 = pro ? 0 : P.obs_ptr[j], o1 = pro ? 0 : P.obs_ptr[j + 1];
             const std::vector<Req>& rq = reqs[pro ? 0 : t + 1];
             b1.put32((uint32_t)c);
-            b1.put32(pro ? 0u : 256u * P.piv_slot[j]);
+            b1.put32(pro ? 0u : rb * P.piv_slot[j]);
             b1.put32((uint32_t)(o1 - o0));
             b1.put32(pro ? 0u : (uint32_t)P.perm[j]);
             b1.put32(0u);
             b1.put32((uint32_t)rq.size() | ((pro ? 0u : kw[t]) << 16));
             b1.put64(pro ? 0.0 : P.rhs[j]);
-            b1.put32(pro ? 0u : 256u * (uint32_t)blk[t].row);
+            b1.put32(pro ? 0u : rb * (uint32_t)blk[t].row);
             b1.put32(0u);
             b1.put64(0.0);
             for (const Req& r : rq) {
-                b1.put32(256u * r.row);
+                b1.put32(rb * r.row);
                 b1.put32(r.rows);
                 b1.put32(r.src);
                 b1.put32(0u);
             }
-            for (int a = 0; a < c4; ++a) b1.put32(a < c ? 256u * P.col_slot[P.col_ptr[j] + a] : 0u);
+            for (int a = 0; a < c4; ++a) b1.put32(a < c ? rb * P.col_slot[P.col_ptr[j] + a] : 0u);
             for (int o = o0; o < o1; ++o) b1.put64(P.obs_val[o]);
             b1.pad(16);
-            for (int o = o0; o < o1; ++o) b1.put32(256u * (uint32_t)P.obs_row[o]);
+            for (int o = o0; o < o1; ++o) b1.put32(rb * (uint32_t)P.obs_row[o]);
             b1.pad(16);
         }
     }

@@ -142,17 +142,31 @@ struct FrontalSet {
         bwd1.release();
         ok = false;
     }
-    // (re)pack the instruction streams from the host program and copy them to the device.  D1's factor-row ring gets the
-    // shared memory that two resident warps per SM leave free (n_obs and the affine coefficient rows are known here).
-    int upload(cudaStream_t st, int n_obs, int smem_optin) {
+    // (re)pack the instruction streams from the host program and copy them to the device.  D1 geometry is fixed here
+    // (n_obs and the affine coefficient rows are known): samples per warp `lanes` (rows of 8 * lanes bytes) and the rows of
+    // the factor-block ring, which gets the shared memory that the resident warps leave free.
+    int upload(cudaStream_t st, int n_obs, int smem_optin, int want_lanes) {
         const int ntri = host.nslots * (host.nslots + 1) / 2;
         const int base_rows = ntri + host.nslots + n_obs + (ncv <= TFIN_MAX_TERMS ? ncv : 0);
-        const long long half = ((long long)smem_optin + 1024) / 2 - 1024 - 8192;   // two CTAs per SM, instruction ring <= 8 KB
-        long long lr = half / 256 - base_rows;
-        if (lr < host.cmax + 2) lr = ((long long)smem_optin - 8192) / 256 - base_rows;   // one CTA per SM
-        lr = std::min<long long>(lr, 160);
-        if (lr < host.cmax + 2) lr = 0;   // D1 cannot serve this front (D2 will)
-        frontal_pack_streams(host, (int)lr, FRONTAL_DMAX, &streams);
+        // Throughput of the (latency-bound) kernel is samples in flight / pass latency, and samples in flight are bounded
+        // by shared memory whatever the row width, so 32 lanes is the default; 16 / 8 trade lanes for resident warps.
+        int lanes = (want_lanes == 8 || want_lanes == 16) ? want_lanes : 32;
+        const long long row = 8LL * lanes;
+        // factor-block ring: room for ~4 average blocks ahead, within an even share of the SM for as many warps as fit
+        long long lr = std::min<long long>(96, 4LL * (host.cmax + 2));
+        for (;;) {
+            const long long smem = (base_rows + lr) * row + 8192;   // instruction ring <= 8 KB
+            const long long warps = ((long long)smem_optin + 1024) / (smem + 1024);
+            const long long smem_min = (base_rows + host.cmax + 2) * row + 8192;
+            const long long warps_min = ((long long)smem_optin + 1024) / (smem_min + 1024);
+            if (warps >= warps_min && warps >= 1) break;   // the ring does not cost a resident warp
+            if (lr <= host.cmax + 2) {
+                if (warps_min < 1) lr = 0;                 // D1 cannot serve this front (D2 will)
+                break;
+            }
+            lr = std::max<long long>(host.cmax + 2, lr - 4);
+        }
+        frontal_pack_streams(host, (int)lr, FRONTAL_DMAX, lanes, &streams);
         if (int e = fwd.upload(streams.fwd, st)) return e;
         if (int e = bwd.upload(streams.bwd, st)) return e;
         if (int e = fwd1.upload(streams.fwd1, st)) return e;
@@ -167,6 +181,7 @@ struct FrontalSet {
         d.ntri = host.nslots * (host.nslots + 1) / 2;
         d.ring_bytes = streams.ring_bytes;
         d.lr_rows = streams.lr_rows;
+        d.lanes = streams.lanes;
         d.nnzL = host.nnzL;
         d.fwd = lane_kernel ? fwd1.p : fwd.p;
         d.bwd = lane_kernel ? bwd1.p : bwd.p;
@@ -255,6 +270,7 @@ struct tfin_ctx {
     int frontal_kernel = 0;  // 0 auto, 1 = D1 (sample per thread), 2 = D2 (sample per CTA)
     int frontal_threads = 0; // D2 threads per CTA, 0 = auto
     int frontal_mode = -1;   // D2: -1 auto, 0 = QOI (extra right-hand sides), 1 = SOLVE (factor to HBM + backward)
+    int frontal_lanes = 0;   // D1: samples per warp, 0 = auto, else 8 / 16 / 32 (takes effect at the next tfin_set_*)
     int last_solver = 0, last_fkernel = 0, last_fthreads = 0, last_focc = 0;
     size_t last_fsmem = 0;
     // ---- tuning
@@ -498,7 +514,7 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
         h->fr_aff.why = frontal_build(n, row_ptr, col_idx, rhs, terms, &h->fr_aff.host);
         if (h->fr_aff.why.empty()) {
             h->fr_aff.ncv = n_terms;
-            if (int e = h->fr_aff.upload(h->stream, 0, h->max_smem_optin)) return e;
+            if (int e = h->fr_aff.upload(h->stream, 0, h->max_smem_optin, h->frontal_lanes)) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
             h->fr_aff.ok = true;
         }
@@ -559,7 +575,7 @@ extern "C" int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_
     for (FrontalSet* fs : {&h->fr_aff, &h->fr_nod})
         if (fs->ok) {
             frontal_set_obs(fs->host, n_obs, ptr, idx, val);
-            if (int e = fs->upload(h->stream, n_obs, h->max_smem_optin)) return e;
+            if (int e = fs->upload(h->stream, n_obs, h->max_smem_optin, h->frontal_lanes)) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
         }
     // B_obs^T as CSR over the n dofs: right-hand sides of the adjoint solves
@@ -627,7 +643,7 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
             h->fr_nod.ncv = n_cells + 1;
             if (!h->h_obs_ptr.empty())
                 frontal_set_obs(h->fr_nod.host, h->n_obs, h->h_obs_ptr.data(), h->h_obs_idx.data(), h->h_obs_val.data());
-            if (int e = h->fr_nod.upload(h->stream, h->n_obs, h->max_smem_optin)) return e;
+            if (int e = h->fr_nod.upload(h->stream, h->n_obs, h->max_smem_optin, h->frontal_lanes)) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
             h->fr_nod.ok = true;
         }
@@ -1030,7 +1046,7 @@ static FrontalGeom frontal_geom(tfin_ctx* h, bool nodal, bool want_w) {
     const int ring = fs.streams.ring_bytes;
     if (h->frontal_kernel != 2 && P.cmax <= 32 && fs.streams.lr_rows > 0) {
         const void* fn = frontal_lane_fn(P.cmax);
-        const size_t sm = frontal_lane_smem(ntri, P.nslots, h->n_obs, ncv_smem, fs.streams.lr_rows, ring);
+        const size_t sm = frontal_lane_smem(ntri, P.nslots, h->n_obs, ncv_smem, fs.streams.lr_rows, fs.streams.lanes, ring);
         if (sm <= (size_t)h->max_smem_optin &&
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess) {
             int occ = 0;
@@ -1110,14 +1126,15 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
         if (nodal) {
             const dim3 cgrid((unsigned)((h->n_cells + 31) / 32), (unsigned)((m + 31) / 32));
             frontal_cellcoef_kernel<<<cgrid, dim3(32, 8), 0, st>>>(io.in, (long long)m, P.n, h->n_cells, h->d_cells.p,
-                                                                  h->coef_mode, g.kernel == 1 ? 1 : 0, h->d_fcv.p);
+                                                                  h->coef_mode, g.kernel == 1 ? fs.streams.lanes : 0, h->d_fcv.p);
             h->launches += 1;
             io.cv_global = h->d_fcv.p;
         }
         TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
         if (g.kernel == 1) {
-            const int grid = (int)std::min<int64_t>((m + 31) / 32, (int64_t)h->sm_count * g.occ);
-            if (int e = h->d_fwork.reserve((size_t)grid * per_sample_work * 32)) return e;
+            const int lanes = fs.streams.lanes;
+            const int grid = (int)std::min<int64_t>((m + lanes - 1) / lanes, (int64_t)h->sm_count * g.occ);
+            if (int e = h->d_fwork.reserve((size_t)grid * per_sample_work * lanes)) return e;
             io.work = h->d_fwork.p;
             void* args[] = {(void*)&dev, (void*)&io};
             TFIN_CUDA(cudaLaunchKernel(frontal_lane_fn(P.cmax), dim3(grid), dim3(32), args, g.smem, st));
@@ -2014,6 +2031,8 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
     if (k == "fom_solver") return h->last_solver;          // solver of the last forward solve: 1 PCG, 2 direct
     if (k == "frontal_kernel") return h->last_fkernel;     // 1 = D1, 2 = D2 observables mode, 3 = D2 solve mode
     if (k == "frontal_threads") return h->last_fthreads;
+    if (k == "frontal_lanes") return h->fr_aff.ok ? h->fr_aff.streams.lanes : -1;
+    if (k == "frontal_ring_rows") return h->fr_aff.ok ? h->fr_aff.streams.lr_rows : -1;
     if (k == "frontal_ctas_per_sm") return h->last_focc;
     if (k == "frontal_smem_bytes") return (int64_t)h->last_fsmem;
     if (k == "frontal_ok") return h->fr_aff.ok ? 1 : 0;
@@ -2073,6 +2092,17 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
     }
     if (k == "frontal_threads") {
         h->frontal_threads = (int)value;
+        return 0;
+    }
+    if (k == "frontal_lanes") {
+        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(TFIN_E_ARG, "frontal_lanes must be 0, 8, 16 or 32");
+        h->frontal_lanes = (int)value;
+        for (FrontalSet* fs : {&h->fr_aff, &h->fr_nod})   // repack the D1 streams for the new row width
+            if (fs->ok) {
+                DeviceGuard guard(h->device);
+                if (int e = fs->upload(h->stream, h->n_obs, h->max_smem_optin, h->frontal_lanes)) return e;
+                TFIN_CUDA(cudaStreamSynchronize(h->stream));
+            }
         return 0;
     }
     if (k == "frontal_mode") {

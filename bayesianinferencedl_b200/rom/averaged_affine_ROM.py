@@ -27,9 +27,9 @@ def rom_offline_tensors(ops, phi, B_obs):
     Psi_t = V_t phi (V_0 = Bi M, V_q = K_q);  S_pq = Psi_p^T Psi_q (+ transpose if p<q), packed lower
     row-major;  G_t = Psi_t^T b;  obs_phi = B_obs phi (averaged_affine_ROM.py:212)."""
     phi = np.ascontiguousarray(phi, dtype=np.float64)
-    n_terms = ops.vals.shape[0]
+    n_terms = ops.affine_terms().shape[0]
     n_r = phi.shape[1]
-    Psi = [ops.csr(ops.vals[t]) @ phi for t in range(n_terms)]
+    Psi = [ops.csr(ops.affine_terms()[t]) @ phi for t in range(n_terms)]
     il = np.tril_indices(n_r)
     S = np.empty((n_terms * (n_terms + 1) // 2, len(il[0])))
     pq = 0
@@ -48,8 +48,8 @@ def rom_gradient_tensors(ops, phi):
     """Offline Gram blocks of the reduced gradient: gram[t][q-1] = Psi_t^T Psi_q with Psi_t = V_t phi, so that
     psi^T dA_dsigmak_phi[q-1] = sum_t theta_t gram[t][q-1] (averaged_affine_ROM.py:215-220, 343-348)."""
     phi = np.ascontiguousarray(phi, dtype=np.float64)
-    n_terms = ops.vals.shape[0]
-    Psi = [ops.csr(ops.vals[t]) @ phi for t in range(n_terms)]
+    n_terms = ops.affine_terms().shape[0]
+    Psi = [ops.csr(ops.affine_terms()[t]) @ phi for t in range(n_terms)]
     return np.stack([np.stack([Psi[t].T @ Psi[q] for q in range(1, n_terms)]) for t in range(n_terms)])
 
 
@@ -100,7 +100,7 @@ class AffineROMFin:
 
         S, G, obs_phi = rom_offline_tensors(self.ops, self.phi, self.B_obs)
         self._h = _cabi.TfinHandle(device)
-        self._h.set_operator(self.ops.row_ptr, self.ops.col_idx, self.ops.vals, self.ops.rhs, prune_zeros)
+        self._h.set_operator(self.ops.row_ptr, self.ops.col_idx, self.ops.affine_terms(), self.ops.rhs, prune_zeros)
         self._h.set_observation(*self.ops.obs_csr(self.B_obs))
         self._h.set_averaging(*self.ops.obs_csr(self.ops.B_obs))
         self._h.set_rom(S, G, obs_phi)
@@ -118,7 +118,7 @@ class AffineROMFin:
         """:215-220: ``dA_dsigmak[q] @ phi`` = K_q phi, shape (9, n, n_r) (built on first use; the batched gradient
         kernels use the Gram blocks of :func:`rom_gradient_tensors` instead)."""
         if self._dA_phi is None:   # depends on phi: kept on this object (the operators are shared per space)
-            self._dA_phi = np.stack([self.ops.csr(self.ops.vals[q]) @ self.phi for q in range(1, self.num_params + 1)])
+            self._dA_phi = np.stack([self.ops.csr(self.ops.affine_terms()[q]) @ self.phi for q in range(1, self.num_params + 1)])
         return self._dA_phi
 
     # ------------------------------------------------------------------ full-order affine model

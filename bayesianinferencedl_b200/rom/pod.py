@@ -16,9 +16,9 @@ def generate_pod_basis(V, n_snapshots=200, basis_size=81, seed=0, lo=0.1, hi=3.5
     ops = build_operators(V)
     h = _cabi.TfinHandle(device)
     try:
-        h.set_operator(ops.row_ptr, ops.col_idx, ops.vals, ops.rhs, True)
+        h.set_operator(ops.row_ptr, ops.col_idx, ops.affine_terms(), ops.rhs, True)
         rng = np.random.default_rng(seed)
-        theta = rng.uniform(lo, hi, (n_snapshots, ops.vals.shape[0] - 1))
+        theta = rng.uniform(lo, hi, (n_snapshots, ops.affine_terms().shape[0] - 1))
         out = h.fom_affine(theta, _cabi.IN_PARAMS, tol=tol, want_w=True, want_qoi=False)
         if np.any(out["status"] != _cabi.STATUS_CONVERGED):
             raise RuntimeError("snapshot solve failed")

@@ -85,13 +85,45 @@ def exterior_facets(cells):
 def mark_facets(coords, cells):
     """forward_solve.py:147-152: exterior = "!near(x[1],0) && on_boundary" -> 1, bottom = "near(x[1],0)
     && on_boundary" -> 2, both tested on the two vertices and the midpoint.  Returns (robin, root) lists.
-    The per-sub-domain split of averaged_affine_ROM.py:116-138 has the same union (appendix A.1)."""
+    (``AffineROMFin`` marks its facets differently: mark_facets_affine.)"""
     robin, root = [], []
     for (a, b) in exterior_facets(cells):
         ys = [coords[a][1], coords[b][1], 0.5 * (coords[a][1] + coords[b][1])]
         if all(not near(y, 0.0) for y in ys):
             robin.append((a, b))
         elif all(near(y, 0.0) for y in ys):
+            root.append((a, b))
+    return robin, root
+
+
+def mark_facets_affine(coords, cells):
+    """Facet markers of ``AffineROMFin`` as written, rom/averaged_affine_ROM.py:116-138: nine sub-domain objects mark the
+    facet function in order 1..9, then ``bottom`` marks 10; ``ds(i)`` only ever integrates over EXTERIOR facets, so only
+    those are listed.  dolfin's ``SubDomain.mark`` marks a facet iff all its vertices AND its midpoint satisfy ``inside``:
+      1      SubFinBoundary([0.75, True])   on_boundary and inside the (over-tall) box of sub-fin 1      (:30-42, :118)
+      2-4, 6-9  SubFin(...)                 inside the box of the sub-fin -- note: the plain SubFin, not ...Boundary (:119-126)
+      5      CenterFinBoundary()            on_boundary and 2.5 <= x <= 3.5 and not near(y, 0)            (:48-50, :122)
+      10     bottom                         near(y, 0) and on_boundary                                     (:117, :138)
+    Returns (robin, root): exterior facets with a marker in 1..9 (they carry the Bi term, :156-162) and with marker 10.
+    This differs from ``Fin``'s single exterior marker (mark_facets) exactly on boundary facets that straddle x = 2.5 or
+    x = 3.5 (e.g. on the top edge y = 4 of a non-conforming mesh): no sub-domain box contains them, they keep marker 0 and
+    the affine model has NO Robin term there."""
+    robin, root = [], []
+    for (a, b) in exterior_facets(cells):
+        pts = [coords[a], coords[b], 0.5 * (coords[a] + coords[b])]
+        marker = 0
+        for q in range(1, 10):
+            if q == 5:
+                ok = all(centerfin_inside(p) and not near(p[1], 0.0) for p in pts)
+            else:
+                ok = all(inside(q, p) for p in pts)        # on_boundary is true for every point of an exterior facet
+            if ok:
+                marker = q
+        if all(near(p[1], 0.0) for p in pts):
+            marker = 10
+        if 1 <= marker <= 9:
+            robin.append((a, b))
+        elif marker == 10:
             root.append((a, b))
     return robin, root
 
@@ -128,6 +160,17 @@ class FinOracle:
             cols += [a, b, b, a]
             vals += [L / 3.0, L / 3.0, L / 6.0, L / 6.0]
         self.M_robin = sp.coo_matrix((vals, (rows, cols)), shape=(self.n, self.n)).tocsr()
+        # the affine model's own facet markers (averaged_affine_ROM.py:116-138); identical to M_robin unless a boundary
+        # facet straddles x = 2.5 / 3.5
+        self.robin_affine, root_affine = mark_facets_affine(self.coords, self.cells)
+        assert sorted(root_affine) == sorted(self.root)
+        rows, cols, vals = [], [], []
+        for a, b in self.robin_affine:
+            L = np.linalg.norm(self.coords[a] - self.coords[b])
+            rows += [a, b, a, b]
+            cols += [a, b, b, a]
+            vals += [L / 3.0, L / 3.0, L / 6.0, L / 6.0]
+        self.M_robin_affine = sp.coo_matrix((vals, (rows, cols)), shape=(self.n, self.n)).tocsr()
 
         # B = assemble(v * ds(2))   (forward_solve.py:162-163)
         self.B = np.zeros(self.n)
@@ -226,7 +269,7 @@ class FinOracle:
 
     def matrix_affine(self, theta):
         """A(theta) of ``AffineROMFin._F`` (averaged_affine_ROM.py:156-162)."""
-        A = self.Bi * self.M_robin
+        A = self.Bi * self.M_robin_affine
         for q in range(9):
             A = A + float(theta[q]) * self.K_q[q]
         return A.tocsc()

@@ -917,3 +917,25 @@ def test_config4_refined_mesh_at_full_size():
         for name, out in (("direct solve", full), ("stream pcg", pcg)):
             assert np.max(np.abs(out["w"][s] - w_ref[s])) <= 1e-10 * np.max(np.abs(w_ref[s])), (name, s)
     h.close()
+
+
+@pytest.mark.parametrize("lanes", [8, 16])
+def test_direct_solver_narrow_rows(space_m2, oracle_m2, lanes):
+    """D1 with 8 / 16 samples per warp (narrower shared-memory rows, more resident warps): same results bit for bit."""
+    from bayesianinferencedl_b200.assembly import build_operators
+    ops = build_operators(space_m2)
+    h = _handle_for(ops, cells=True)
+    h.set_int("fom_solver", 2)
+    h.set_int("frontal_kernel", 1)
+    rng = np.random.default_rng(45)
+    theta = rng.uniform(0.1, 10.0, (75, 9))
+    k = np.exp(0.5 * rng.standard_normal((21, ops.n)))
+    ref, refn = h.fom_affine(theta, want_w=True), h.fom_nodal(k)
+    assert h.get_int("frontal_lanes") == 32
+    h.set_int("frontal_lanes", lanes)
+    out, outn = h.fom_affine(theta, want_w=True), h.fom_nodal(k)
+    assert h.get_int("frontal_lanes") == lanes and h.get_int("frontal_kernel") == 1
+    assert np.array_equal(out["qoi"], ref["qoi"]) and np.array_equal(out["w"], ref["w"])
+    assert np.array_equal(outn["qoi"], refn["qoi"]) and np.all(out["status"] == 0)
+    assert relerr(out["qoi"][74], oracle_m2.qoi_operator(oracle_m2.forward_nine_param(theta[74]))) <= RTOL_FOM
+    h.close()

@@ -205,3 +205,44 @@ def test_exp_gradient_rule(oracle_m1):
     cost = lambda kk: 0.5 * np.sum((o.qoi_operator(o.forward_exp(kk)) - data) ** 2)
     fd = (cost(k + 1e-6 * d) - cost(k - 1e-6 * d)) / 2e-6
     assert abs(fd - o.gradient_exp(k, data) @ d) <= 5e-2 * abs(fd)
+
+
+def _mesh_with_straddling_top_facet():
+    """Unstructured fin mesh whose top edge y = 4 has a boundary facet crossing x = 2.5 (the vertex at the junction is
+    slid along the edge), which the reference's mshr mesh may well have."""
+    from meshes import unstructured_fin
+    coords, cells = unstructured_fin(h=0.2, seed=1)
+    coords = coords.copy()
+    j = int(np.argmin(np.abs(coords[:, 0] - 2.5) + np.abs(coords[:, 1] - 4.0)))
+    assert abs(coords[j, 0] - 2.5) < 1e-12 and abs(coords[j, 1] - 4.0) < 1e-12
+    coords[j, 0] = 2.43
+    return coords, cells
+
+
+def test_affine_model_uses_its_own_facet_markers():
+    """rom/averaged_affine_ROM.py:116-138 marks the Robin boundary with nine sub-domain objects; a boundary facet that
+    straddles x = 2.5 lies in none of their boxes and carries no Robin term in the AFFINE model, while Fin's single
+    exterior marker (forward_solve.py:147-152) still covers it.  Oracle and product assembly must agree on both."""
+    from oracle.thermal_fin_oracle import FinOracle, mark_facets, mark_facets_affine
+    from bayesianinferencedl_b200 import FinSpace
+    from bayesianinferencedl_b200.assembly import build_operators
+    coords, cells = _mesh_with_straddling_top_facet()
+    robin, root = mark_facets(coords, cells)
+    robin_a, root_a = mark_facets_affine(coords, cells)
+    assert sorted(root) == sorted(root_a)
+    missing = sorted(set(robin) - set(robin_a))
+    assert len(missing) >= 1 and set(robin_a) <= set(robin)
+    for a, b in missing:                                  # exactly the facets crossing x = 2.5 / 3.5
+        xs = sorted([coords[a][0], coords[b][0]])
+        assert (xs[0] < 2.5 < xs[1]) or (xs[0] < 3.5 < xs[1])
+    o = FinOracle(coords, cells)
+    ops = build_operators(FinSpace.from_mesh(coords, cells))
+    assert abs(ops.csr(ops.vals[0]) - o.Bi * o.M_robin).max() < 1e-15
+    assert abs(ops.csr(ops.robin_affine) - o.Bi * o.M_robin_affine).max() < 1e-15
+    assert abs(ops.csr(ops.robin_affine) - ops.csr(ops.vals[0])).max() > 1e-4
+    theta = np.random.default_rng(5).uniform(0.1, 3.5, 9)
+    assert abs(ops.csr(ops.affine_values(theta)) - o.matrix_affine(theta)).max() < 1e-13
+    # on the conforming structured mesh the two marker sets coincide
+    from bayesianinferencedl_b200 import get_space
+    ops2 = build_operators(get_space(40, m=1))
+    assert np.array_equal(ops2.robin_affine, ops2.vals[0])
