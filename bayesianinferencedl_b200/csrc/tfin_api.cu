@@ -2205,17 +2205,17 @@ extern "C" void tfin_frontal_free(void* prog) { delete static_cast<tfin_frontal_
 
 // ------------------------------------------------------------------------------------------------ micro-benchmarks
 // Shared-memory read bandwidth of the device (all SMs): the roofline denominator of the on-chip kernels (K1/K2 PCG, D1 /
-// D2 frontal solver), which never touch HBM in their inner loops.  Conflict-free 16-byte loads, 16 per iteration.
+// D2 frontal solver), which never touch HBM in their inner loops.  Conflict-free 16-byte loads, 8 per iteration.
 __global__ void __launch_bounds__(1024) smem_bandwidth_kernel(int iters, double* sink) {
     extern __shared__ __align__(16) double2 sm_bw[];
     const int t = threadIdx.x, T = blockDim.x;
-    for (int i = t; i < 4 * T; i += T) sm_bw[i] = make_double2(1.0 + i, 2.0);
+    for (int i = t; i < 8 * T; i += T) sm_bw[i] = make_double2(1.0 + i, 2.0);
     __syncthreads();
     double2 acc = make_double2(0.0, 0.0);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const double2 v = sm_bw[t + T * ((u + it) & 3)];
+        for (int u = 0; u < 8; ++u) {   // 8 DISTINCT rows per iteration, rotated with `it`: nothing to CSE or hoist
+            const double2 v = sm_bw[t + T * ((u + it) & 7)];
             acc.x += v.x;
             acc.y += v.y;
         }
@@ -2227,7 +2227,7 @@ extern "C" int tfin_smem_bandwidth(tfin_handle_t h, double* gbs_out) {
     CHECK_HANDLE(h);
     if (!gbs_out) return fail(TFIN_E_ARG, "tfin_smem_bandwidth: gbs_out is NULL");
     const int T = 1024, iters = 20000;
-    const size_t smem = (size_t)4 * T * sizeof(double2);
+    const size_t smem = (size_t)8 * T * sizeof(double2);
     TFIN_CUDA(cudaFuncSetAttribute(smem_bandwidth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     TFIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smem_bandwidth_kernel, T, smem));
@@ -2246,6 +2246,6 @@ extern "C" int tfin_smem_bandwidth(tfin_handle_t h, double* gbs_out) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     h->launches += 2;
-    *gbs_out = (double)grid * T * iters * 16.0 * 16.0 / (ms * 1e-3) / 1e9;
+    *gbs_out = (double)grid * T * iters * 8.0 * 16.0 / (ms * 1e-3) / 1e9;
     return 0;
 }

@@ -6,10 +6,15 @@
 
 One "step" = one pass of the hot path over one batch of synthetic conductivity samples per GPU:
   * FOM leg (headline `value`): BASELINE config "five-param batched FOM solves ... 10^5 samples on the reference
-    mesh, QoI = subfin averages" -> affine Jacobi-PCG kernel fused with B_obs (mesh: structured m=3, n = 1597)
-  * ROM leg (`rom` object): BASELINE config "nine-param batched ROM solves, 10^6 samples" (n_r = 81)
-Samples are sharded over ranks (weak scaling: the per-GPU batch is fixed); with N > 1 the step ends with the
-NCCL all-gather of the observables.  Prints ONE JSON line on rank 0.
+    mesh, QoI = subfin averages": batched sparse-direct (frontal Cholesky) solve fused with B_obs; the Jacobi-PCG kernel
+    of round 1 is timed next to it (`fom_pcg`)
+  * ROM leg (`rom`): BASELINE config "nine-param batched ROM solves, 10^6 samples" (n_r = 81)
+  * `fom_unstructured`: the same FOM workload on a reference-like unstructured mesh (~1446 dofs, 6-7 nnz per row)
+  * `fom_nodal`: nodal Gaussian-field conductivities; `fom_refined`: the 99 945-dof mesh (direct solver and streaming PCG)
+Samples are sharded over ranks (weak scaling: the per-GPU batch is fixed); with N > 1 the step ends with the NCCL
+all-gather of the observables.  Outside the timed regions the first outputs of every leg are compared with the CPU
+oracle (`parity`), and at N > 1 every rank re-solves rows of its neighbour's shard and checks the gathered array
+bit for bit (`gather_order_ok`).  Prints ONE JSON line on rank 0; exits non-zero if a parity bound is exceeded.
 """
 from __future__ import annotations
 
@@ -30,6 +35,10 @@ RESOLUTION = 40                 # reference's get_space(40); structured m = 3 ->
 FOM_SEED, ROM_SEED, REF_SEED, NODAL_SEED = 1, 0, 2, 3
 REFINED_M = 26                  # n = 99 945
 TOL = 1e-12
+PARITY_BOUND = {"fom": 1e-10, "fom_pcg": 1e-10, "fom_unstructured": 1e-10, "fom_nodal": 1e-10, "fom_refined": 1e-10,
+                "fom_refined_pcg": 1e-10, "rom": 1e-9}
+FOM_WORKLOAD = ("config[2] five-param batched FOM on the m=3 mesh (n=1597): k ~ U(0.1,1)^5 (seed 1) -> nine sub-fin "
+                "conductivities, QoI = 9 sub-fin averages")
 
 
 def parse_args():
@@ -42,10 +51,14 @@ def parse_args():
     ap.add_argument("--rom-batch", type=int, default=1_000_000, help="ROM samples per GPU per step")
     ap.add_argument("--refined-batch", type=int, default=2368,
                     help="refined-mesh (m=26, n=99 945) FOM samples per GPU per step; 0 disables the leg")
+    ap.add_argument("--refined-pcg-batch", type=int, default=592, help="samples of the streaming-PCG comparison on the refined mesh")
     ap.add_argument("--refined-steps", type=int, default=2)
+    ap.add_argument("--refined-strong-total", type=int, default=2368,
+                    help="strong-scaling line of config 4: this many samples IN TOTAL, split over the ranks")
     ap.add_argument("--nodal-batch", type=int, default=100_000,
                     help="nodal Gaussian-field FOM samples per GPU per step; 0 disables the leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-fom-sample", type=int, default=65536, help="CPU baseline FOM sample (~10 s on 16 cores)")
     ap.add_argument("--cpu-rom-sample", type=int, default=65536)
     ap.add_argument("--grad-batch", type=int, default=16384, help="samples per GPU per step of the gradient legs (0 = skip)")
@@ -64,8 +77,23 @@ def rom_inputs(n, seed):
     return np.random.default_rng(seed).uniform(0.1, 3.5, (n, 9))
 
 
+def refined_inputs(n, seed):
+    """config 4: theta ~ U(0.1, 10)^9 (bounds of rom/error_optimization.py:96)."""
+    return np.random.default_rng(seed).uniform(0.1, 10.0, (n, 9))
+
+
+def bench_config(args, world):
+    """The workload description both arms print (identical keys and values for the same flags)."""
+    return {
+        "workload": FOM_WORKLOAD,
+        "fom_samples_per_gpu_per_step": args.fom_batch, "rom_samples_per_gpu_per_step": args.rom_batch,
+        "mesh": "structured conforming fin mesh m=3, n=1597 dofs (the reference's mshr mesh is not shipped)",
+        "n_r": 81, "parallelism": f"samples sharded x{world}, NCCL all-gather of observables" if world > 1 else "1 GPU",
+    }
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU legs (the ONLY place bench.py touches oracle/): reported baseline + the --impl reference arm
+# CPU legs (the ONLY place bench.py touches oracle/): reported baseline, the --impl reference arm, and the parity check
 # ------------------------------------------------------------------------------------------------
 _W = {}
 
@@ -122,37 +150,41 @@ def cpu_pod_basis():
 
 
 def run_reference(args):
+    """Reference arm: the CPU port of the reference path on all host cores, each step a stated prefix of the SAME
+    workload the B200 arm runs (rank 0's fom_inputs / rom_inputs)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     phi = cpu_pod_basis()
     pool = CpuPool(phi)
-    per_step = max(pool.cores * 16, args.ref_step_samples)
-    th = fom_inputs(per_step * (args.steps + args.warmup), FOM_SEED)
-    thr = rom_inputs(per_step * (args.steps + args.warmup), ROM_SEED)
+    per_step = min(max(pool.cores * 16, args.ref_step_samples), args.fom_batch)
+    th = fom_inputs(args.fom_batch, FOM_SEED)[:per_step]
+    thr = rom_inputs(args.rom_batch, ROM_SEED)[:per_step]
     t_f = t_r = 0.0
     for s in range(args.steps + args.warmup):
-        _, dt = pool.run(_cpu_fom, th[s * per_step:(s + 1) * per_step])
-        _, dtr = pool.run(_cpu_rom, thr[s * per_step:(s + 1) * per_step])
+        _, dt = pool.run(_cpu_fom, th)
+        _, dtr = pool.run(_cpu_rom, thr)
         if s >= args.warmup:
             t_f += dt
             t_r += dtr
     pool.close()
     v = per_step * args.steps / t_f
     vr = per_step * args.steps / t_r
-    sample = f"{per_step} five-param FOM solves per step (assemble + scipy splu + B_obs), {pool.cores} processes"
+    sample = (f"every step = the first {per_step} samples of the {args.fom_batch}-sample FOM workload (assemble + scipy "
+              f"splu + B_obs per sample), {pool.cores} single-threaded processes")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_f / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config[2] five-param batched FOM on the m=3 mesh (n=1597), CPU port of the "
-                               "reference path: FEniCS/PETSc are not installable here (parity unpinned)",
-                   "samples_per_step": per_step},
-        "cpu_baseline": {"value": v, "unit": "solves/s", "cores": pool.cores, "kind": "port", "sample": sample},
+        "config": bench_config(args, world),
+        "cpu_baseline": {"value": v, "unit": "solves/s", "cores": pool.cores, "kind": "port", "sample": sample,
+                         "note": "CPU port of the reference path (oracle/): FEniCS/PETSc are not installable here, "
+                                 "parity unpinned by the reference (DESIGN.md section 0)"},
         "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "rom": {"value": vr, "unit": "solves/s", "ms_per_step": 1e3 * t_r / args.steps,
-                "sample": f"{per_step} literal LSPG ROM solves per step (A phi, psi^T psi, np.linalg.solve)"},
+                "sample": f"first {per_step} samples of the ROM workload per step, literal LSPG (A phi, psi^T psi, np.linalg.solve)"},
     }
     print(json.dumps(line), flush=True)
 
@@ -203,6 +235,11 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
 def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,17 +250,17 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         phi_cpu = cpu_pod_basis()
         pool = CpuPool(phi_cpu)
-        _, dt_f = pool.run(_cpu_fom, fom_inputs(args.cpu_fom_sample, FOM_SEED))
-        _, dt_r = pool.run(_cpu_rom, rom_inputs(args.cpu_rom_sample, ROM_SEED))
+        _, dt_f = pool.run(_cpu_fom, fom_inputs(args.fom_batch, FOM_SEED)[:args.cpu_fom_sample])
+        _, dt_r = pool.run(_cpu_rom, rom_inputs(args.rom_batch, ROM_SEED)[:args.cpu_rom_sample])
         pool.close()
-        cpu = {"value": args.cpu_fom_sample / dt_f, "unit": "solves/s", "cores": pool.cores, "kind": "port",
-               "sample": f"first {args.cpu_fom_sample} samples of the FOM workload: oracle port of the reference "
-                         f"path (numpy assembly + scipy splu + B_obs), {pool.cores} single-threaded processes, "
-                         f"{dt_f:.1f} s",
+        nf, nr_ = min(args.cpu_fom_sample, args.fom_batch), min(args.cpu_rom_sample, args.rom_batch)
+        cpu = {"value": nf / dt_f, "unit": "solves/s", "cores": pool.cores, "kind": "port",
+               "sample": f"first {nf} samples of the FOM workload: oracle port of the reference path (numpy assembly + "
+                         f"scipy splu + B_obs), {pool.cores} single-threaded processes, {dt_f:.1f} s",
                "reference_published": "the reference publishes no benchmark; its stored notebook outputs show ~7.4 FOM "
                                       "solves/s (MUQ chain, 1 CPU process) and 13.6-14.4 it/s (PyMC3 Metropolis), BASELINE.md",
-               "rom_value": args.cpu_rom_sample / dt_r,
-               "rom_sample": f"first {args.cpu_rom_sample} ROM samples, literal averaged_affine_ROM.py:292-304 "
+               "rom_value": nr_ / dt_r,
+               "rom_sample": f"first {nr_} ROM samples, literal averaged_affine_ROM.py:292-304 "
                              f"(A phi, psi^T psi, np.linalg.solve), {dt_r:.1f} s"}
 
     import torch
@@ -250,8 +287,10 @@ def run_b200(args):
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
     f64 = torch.float64
-    th_f_host = torch.from_numpy(fom_inputs(NF, FOM_SEED + rank)).pin_memory()
-    th_r_host = torch.from_numpy(rom_inputs(NR, ROM_SEED + rank)).pin_memory()
+    th_f_np = fom_inputs(NF, FOM_SEED + rank)
+    th_r_np = rom_inputs(NR, ROM_SEED + rank)
+    th_f_host = torch.from_numpy(th_f_np).pin_memory()
+    th_r_host = torch.from_numpy(th_r_np).pin_memory()
     th_f, th_r = th_f_host.to(dev), th_r_host.to(dev)
     q_f = torch.empty((NF, n_obs), dtype=f64, device=dev)
     q_r = torch.empty((NR, n_obs), dtype=f64, device=dev)
@@ -264,24 +303,6 @@ def run_b200(args):
     st_f_host = torch.empty(NF, dtype=torch.int32).pin_memory()
     st_r_host = torch.empty(NR, dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-    def fom_dev():
-        h.fom_affine_raw(th_f.data_ptr(), NF, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_f.data_ptr(),
-                         iters=it_f.data_ptr(), status=st_f.data_ptr(), stream=sp)
-        return gather_rows(q_f, NF * world) if world > 1 else q_f
-
-    def rom_dev():
-        h.rom_raw(th_r.data_ptr(), NR, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, qoi=q_r.data_ptr(),
-                  status=st_r.data_ptr(), stream=sp)
-        return gather_rows(q_r, NR * world) if world > 1 else q_r
-
-    def fom_e2e():     # the C-ABI call a user of the facade makes: HOST buffers in, HOST buffers out
-        h.fom_affine_raw(th_f_host.data_ptr(), NF, _cabi.IN_PARAMS, _cabi.MEM_HOST, TOL, 20000,
-                         qoi=q_f_host.data_ptr(), iters=it_f_host.data_ptr(), status=st_f_host.data_ptr(), stream=sp)
-
-    def rom_e2e():
-        h.rom_raw(th_r_host.data_ptr(), NR, _cabi.IN_PARAMS, _cabi.MEM_HOST, qoi=q_r_host.data_ptr(),
-                  status=st_r_host.data_ptr(), stream=sp)
 
     def barrier():
         if world > 1:
@@ -309,21 +330,155 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), hh.kernel_launches() - l0
 
+    def kernel_ms(fn, reps=3):
+        """Duration of ONE launch of the dominant kernel: events tight around the call on its stream, L2 flushed before."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out = []
+        for _ in range(reps):
+            flush.fill_(1)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return float(np.mean(out))
+
+    def affine_dev(hh, th, N, q, it=None, st=None, solver=0, maxit=20000):
+        def run():
+            hh.set_int("fom_solver", solver)
+            hh.fom_affine_raw(th.data_ptr(), N, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, maxit, qoi=q.data_ptr(),
+                              iters=it.data_ptr() if it is not None else 0, status=st.data_ptr() if st is not None else 0,
+                              stream=sp)
+            return gather_rows(q, N * world) if world > 1 else q
+        return run
+
+    def frontal_info(hh):
+        return {"kernel": {1: "D1 frontal_lane_kernel (sample per thread)", 2: "D2 frontal_cta_kernel (sample per CTA, "
+                           "observables through extra right-hand sides)", 3: "D2 frontal_cta_kernel (sample per CTA, "
+                           "factor in HBM + backward substitution)"}.get(hh.get_int("frontal_kernel"), "?"),
+                "threads": hh.get_int("frontal_threads"), "ctas_per_sm": hh.get_int("frontal_ctas_per_sm"),
+                "smem_bytes": hh.get_int("frontal_smem_bytes"), "front_slots": hh.get_int("frontal_slots"),
+                "max_column": hh.get_int("frontal_cmax"), "factor_nnz": hh.get_int("frontal_nnz_factor"),
+                "pair_updates": hh.get_int("frontal_pair_updates"), "samples_per_warp": hh.get_int("frontal_lanes")}
+
+    def rom_dev():
+        h.rom_raw(th_r.data_ptr(), NR, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, qoi=q_r.data_ptr(),
+                  status=st_r.data_ptr(), stream=sp)
+        return gather_rows(q_r, NR * world) if world > 1 else q_r
+
+    def fom_e2e():     # the C-ABI call the facade makes: HOST buffers in, HOST buffers out
+        h.set_int("fom_solver", 0)
+        h.fom_affine_raw(th_f_host.data_ptr(), NF, _cabi.IN_PARAMS, _cabi.MEM_HOST, TOL, 20000,
+                         qoi=q_f_host.data_ptr(), iters=it_f_host.data_ptr(), status=st_f_host.data_ptr(), stream=sp)
+
+    def rom_e2e():
+        h.rom_raw(th_r_host.data_ptr(), NR, _cabi.IN_PARAMS, _cabi.MEM_HOST, qoi=q_r_host.data_ptr(),
+                  status=st_r_host.data_ptr(), stream=sp)
+
     # flush cost (inside the bracket) measured once so it can be reported
     timed(lambda: None, 2, 1)
     flush_ms, _ = timed(lambda: None, 4, 1)
     flush_ms /= 4
+    smem_peak = h.smem_bandwidth()          # GB/s, measured on this GPU: roofline denominator of the on-chip kernels
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     K, Wm = args.steps, max(args.warmup, 3)
+    fom_dev = affine_dev(h, th_f, NF, q_f, it_f, st_f, solver=0)
     ms_f, launches_f = timed(fom_dev, K, Wm)
+    fom_solver_used = h.get_int("fom_solver")
+    fom_geo = frontal_info(h) if fom_solver_used == 2 else None
+    gathered_f = fom_dev()
+    torch.cuda.synchronize()
+    ok_f = bool((st_f == 0).all().item())
+    parity_in = {"fom": (th_f_np[:64].copy(), q_f[:64].cpu().numpy())}
+
+    # ---- gather order (N > 1): re-solve the first rows of the NEXT rank's shard here and compare with the gathered
+    # array bit for bit (the kernels are deterministic per sample, whichever GPU / lane solves it)
+    gather_ok = None
+    if world > 1:
+        nb = (rank + 1) % world
+        th_nb = torch.from_numpy(fom_inputs(NF, FOM_SEED + nb)[:256]).to(dev)
+        q_nb = torch.empty((256, n_obs), dtype=f64, device=dev)
+        h.fom_affine_raw(th_nb.data_ptr(), 256, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_nb.data_ptr(), stream=sp)
+        torch.cuda.synchronize()
+        mine = bool(torch.equal(gathered_f[nb * NF: nb * NF + 256], q_nb)) and \
+            bool(torch.equal(gathered_f[rank * NF: (rank + 1) * NF], q_f))
+        flag = torch.tensor([1 if mine else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item() == 1)
+
+    # ---- the round-1 Jacobi-PCG kernel (K1) on the same workload, for comparison and for its own roofline
+    q_p = torch.empty((NF, n_obs), dtype=f64, device=dev)
+    pcg_dev = affine_dev(h, th_f, NF, q_p, it_f, st_f, solver=1)
+    ms_p, launches_p = timed(pcg_dev, max(2, K // 2), 2)
+    k_ms_p = kernel_ms(pcg_dev)
+    iters_sum = int(it_f.to(torch.int64).sum().item())
+    ok_p = bool((st_f == 0).all().item())
+    pcg_geo = {"threads": h.get_int("pcg_threads"), "rows_per_thread": h.get_int("pcg_rows_per_thread"),
+               "ctas_per_sm": h.get_int("pcg_ctas_per_sm"), "smem_bytes": h.get_int("pcg_smem_bytes"),
+               "ell_width": h.get_int("ell_width")}
+    parity_in["fom_pcg"] = (th_f_np[:64].copy(), q_p[:64].cpu().numpy())
+    k_ms = kernel_ms(fom_dev)
+
     ms_r, launches_r = timed(rom_dev, K, Wm)
+    ok_r = bool((st_r == 0).all().item())
+    parity_in["rom"] = (th_r_np[:64].copy(), q_r[:64].cpu().numpy())
     ms_fe, launches_fe = timed(fom_e2e, K, Wm)
     ms_re, launches_re = timed(rom_e2e, K, Wm)
 
-    # ---- config[4] nodal Gaussian-field conductivity: k = exp(0.5 chol^T z), Matern-5/2, l = 1.6 (fields are
-    # generated on the device with torch -- input generation, not the measured path), in-kernel assembly + PCG
+    # ---- facade-level end to end: the call a user of the reference API makes, PAGEABLE numpy in and out (wall clock)
+    def facade_rate(fn, arr, reps=3):
+        fn(arr[:1024])
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn(arr)
+        dt = (time.perf_counter() - t0) / reps
+        t = torch.tensor([dt], dtype=f64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * len(arr) / float(t.item()), out
+    h.set_int("fom_solver", 0)
+    fac_f, qf_fac = facade_rate(model.forward_nine_param_qoi, th_f_np)
+    fac_r, _ = facade_rate(model.forward_reduced_qoi, th_r_np)
+    facade_same = bool(np.array_equal(qf_fac[:256], q_f[:256].cpu().numpy()))
+
+    # ---- the same FOM workload on a REFERENCE-LIKE mesh: unstructured, ~1446 dofs, 6-7 non-zeros per row (the
+    # structured mesh prunes to 5), marker-0 cells along x = 2.5 / 3.5 (SURVEY Q-1)
+    from bayesianinferencedl_b200.assembly import build_operators
+    from bayesianinferencedl_b200.fom.thermal_fin import get_space_unstructured
+    Vu = get_space_unstructured()
+    opsu = build_operators(Vu)
+    hu = _cabi.TfinHandle(local_rank)
+    hu.set_operator(opsu.row_ptr, opsu.col_idx, opsu.affine_terms(), opsu.rhs)
+    hu.set_observation(*opsu.obs_csr())
+    q_u = torch.empty((NF, 9), dtype=f64, device=dev)
+    it_u = torch.empty(NF, dtype=torch.int32, device=dev)
+    st_u = torch.empty(NF, dtype=torch.int32, device=dev)
+    un_dev = affine_dev(hu, th_f, NF, q_u, it_u, st_u, solver=0)
+    ms_u, l_u = timed(un_dev, K, Wm, hu)
+    un_geo = frontal_info(hu) if hu.get_int("fom_solver") == 2 else None
+    parity_in["fom_unstructured"] = (th_f_np[:64].copy(), q_u[:64].cpu().numpy())
+    ok_u = bool((st_u == 0).all().item())
+    un_pcg = affine_dev(hu, th_f, NF, q_u, it_u, st_u, solver=1)
+    ms_up, _ = timed(un_pcg, 2, 1, hu)
+    it_u_mean = float(it_u.double().mean().item())
+    unstructured = {
+        "value": world * NF / ((ms_u / K - flush_ms) * 1e-3), "unit": "solves/s", "ms_per_step": ms_u / K - flush_ms,
+        "workload": f"the headline FOM workload on a reference-like unstructured mesh (Delaunay stand-in for the mshr mesh): "
+                    f"n={opsu.n} dofs, {opsu.nnz / opsu.n:.2f} non-zeros per row (max {int(np.diff(opsu.row_ptr).max())}), "
+                    f"{int((opsu.cell_markers == 0).sum())} marker-0 cells",
+        "solver": "direct" if un_geo else "pcg", "frontal": un_geo, "all_converged": ok_u, "gpu_launches": l_u,
+        "pcg": {"value": world * NF / ((ms_up / 2 - flush_ms) * 1e-3), "unit": "solves/s", "mean_pcg_iters": it_u_mean,
+                "ell_width": hu.get_int("ell_width"), "rows_per_thread": hu.get_int("pcg_rows_per_thread"),
+                "threads": hu.get_int("pcg_threads"), "ctas_per_sm": hu.get_int("pcg_ctas_per_sm")},
+    }
+    hu.close()
+
+    # ---- config[4] nodal Gaussian-field conductivity: k = exp(0.5 chol^T z), Matern-5/2, l = 1.6; per-sample FEM
+    # assembly + solve (direct D1 by default, the K2 PCG kernel next to it)
     nodal = None
     if args.nodal_batch > 0:
         from bayesianinferencedl_b200 import Fin
@@ -356,35 +511,44 @@ def run_b200(args):
         st_n = torch.empty(NN, dtype=torch.int32, device=dev)
         hn = fin.handle
 
-        def nodal_dev():
-            hn.fom_nodal_raw(k_dev.data_ptr(), NN, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_n.data_ptr(),
-                             iters=it_n.data_ptr(), status=st_n.data_ptr(), stream=sp)
-            return gather_rows(q_n, NN * world) if world > 1 else q_n
+        def nodal_dev(solver=0):
+            def run():
+                hn.set_int("fom_solver", solver)
+                hn.fom_nodal_raw(k_dev.data_ptr(), NN, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_n.data_ptr(),
+                                 iters=it_n.data_ptr(), status=st_n.data_ptr(), stream=sp)
+                return gather_rows(q_n, NN * world) if world > 1 else q_n
+            return run
 
         q_n_host = torch.empty((NN, n_obs), dtype=f64).pin_memory()
         st_n_host = torch.empty(NN, dtype=torch.int32).pin_memory()
 
         def nodal_e2e():
+            hn.set_int("fom_solver", 0)
             hn.fom_nodal_raw(k_host.data_ptr(), NN, _cabi.MEM_HOST, TOL, 20000, qoi=q_n_host.data_ptr(),
                              status=st_n_host.data_ptr(), stream=sp)
 
         def nodal_pipeline():   # fields drawn ON the device (tfin_field_sample), only the observables cross PCIe
             draw()
+            hn.set_int("fom_solver", 0)
             hn.fom_nodal_raw(k_dev.data_ptr(), NN, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_n.data_ptr(),
                              status=st_n.data_ptr(), stream=sp)
             q_n_host.copy_(q_n, non_blocking=True)
 
-        ms_n, ln = timed(nodal_dev, K, Wm, hn)
+        ms_n, ln = timed(nodal_dev(0), K, Wm, hn)
+        nodal_geo = frontal_info(hn) if hn.get_int("fom_solver") == 2 else None
+        ok_n = bool((st_n == 0).all().item())
+        parity_in["fom_nodal"] = (k_dev[:64].cpu().numpy(), q_n[:64].cpu().numpy())
         ms_ne, _ = timed(nodal_e2e, K, Wm, hn)
         ms_np, lnp = timed(nodal_pipeline, K, Wm, hn)
+        ms_npcg, _ = timed(nodal_dev(1), 2, 1, hn)
         it_sum_n = int(it_n.to(torch.int64).sum().item())
         n_cells = fin.ops.n_cells
         step_n = ms_n / K - flush_ms
         nodal = {
             "value": world * NN / (step_n * 1e-3), "unit": "solves/s", "ms_per_step": step_n,
-            "workload": f"config[4]: {NN} Matern-5/2 (l=1.6) nodal fields per GPU, per-sample in-kernel FEM assembly "
-                        f"+ PCG, mesh m=3",
-            "mean_pcg_iters": it_sum_n / NN, "all_converged": bool((st_n == 0).all().item()),
+            "workload": f"config[4]: {NN} Matern-5/2 (l=1.6) nodal fields per GPU, per-sample FEM assembly (cell "
+                        f"coefficients) + sparse-direct solve, mesh m=3",
+            "solver": "direct" if nodal_geo else "pcg", "frontal": nodal_geo, "all_converged": ok_n,
             "e2e": {"value": world * NN / ((ms_ne / K - flush_ms) * 1e-3), "unit": "solves/s",
                     "h2d_bytes_per_step": NN * n * 8, "d2h_bytes_per_step": NN * (n_obs * 8 + 4),
                     "ms_per_step": ms_ne / K - flush_ms},
@@ -398,10 +562,9 @@ def run_b200(args):
             "field_sampler": {"value": NN / (sampler_ms * 1e-3), "unit": "fields/s/GPU", "ms": sampler_ms,
                               "what": "tfin_field_sample: Philox normals + fp64 triangular GEMM + exp, device resident",
                               "tflops_fp64": NN * float(n) * n / (sampler_ms * 1e-3) / 1e12},
-            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": None,
-                         "achieved": ((88.0 * n + 8.0 * n_cells) * it_sum_n + NN * n * 8.0) / (step_n * 1e-3) / 1e9,
-                         "note": "algorithmic bytes (88 n + 8 n_cells) per iteration + the k field read once; "
-                                 "on-chip kernel, see roofline.note"},
+            "pcg": {"value": world * NN / ((ms_npcg / 2 - flush_ms) * 1e-3), "unit": "solves/s",
+                    "mean_pcg_iters": it_sum_n / NN, "kernel": "pcg_kernel<nodal> (K2)",
+                    "smem_bytes_per_iteration": (2 * hn.get_int("ell_width_nodal") + 1) * 8 * n},
         }
         # ---- gradient legs: FOM adjoint gradient and reduced gradient, device resident
         if args.grad_batch > 0:
@@ -438,65 +601,83 @@ def run_b200(args):
         del k_dev, k_host
         fin.handle.close()
 
-    # ---- config[3] refined mesh (m=26, n=99 945), nine-param FOM: the genuinely HBM-streaming PCG kernel
+    # ---- config[3] refined mesh (m=26, n=99 945), nine-param FOM: wide-front direct solver (D2) by default, the
+    # HBM-streaming PCG kernel (K4) on a smaller batch next to it, and a STRONG-scaling line (fixed total batch)
     refined = None
     if args.refined_batch > 0:
-        from bayesianinferencedl_b200.assembly import build_operators
         NRf = args.refined_batch
         Vr = get_space(RESOLUTION, m=REFINED_M)
         opsr = build_operators(Vr)
         hr = _cabi.TfinHandle(local_rank)
-        hr.set_operator(opsr.row_ptr, opsr.col_idx, opsr.vals, opsr.rhs)
+        hr.set_operator(opsr.row_ptr, opsr.col_idx, opsr.affine_terms(), opsr.rhs)
         hr.set_observation(*opsr.obs_csr())
-        th_ref_host = torch.from_numpy(np.random.default_rng(REF_SEED + rank).uniform(0.1, 10.0, (NRf, 9))).pin_memory()
-        th_ref = th_ref_host.to(dev)
+        th_ref_np = refined_inputs(NRf, REF_SEED + rank)
+        th_ref = torch.from_numpy(th_ref_np).to(dev)
         q_ref = torch.empty((NRf, 9), dtype=f64, device=dev)
         it_ref = torch.empty(NRf, dtype=torch.int32, device=dev)
         st_ref = torch.empty(NRf, dtype=torch.int32, device=dev)
-
-        def ref_dev():
-            hr.fom_affine_raw(th_ref.data_ptr(), NRf, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, 50000,
-                              qoi=q_ref.data_ptr(), iters=it_ref.data_ptr(), status=st_ref.data_ptr(), stream=sp)
-            return gather_rows(q_ref, NRf * world) if world > 1 else q_ref
-
+        ref_dev = affine_dev(hr, th_ref, NRf, q_ref, it_ref, st_ref, solver=0, maxit=50000)
         ms_ref, l_ref = timed(ref_dev, args.refined_steps, 1, hr)
+        ref_geo = frontal_info(hr) if hr.get_int("fom_solver") == 2 else None
         step_ref = ms_ref / args.refined_steps - flush_ms
-        it_sum_ref = int(it_ref.to(torch.int64).sum().item())
-        bytes_ref = 88.0 * opsr.n * it_sum_ref
-        ach = bytes_ref / (step_ref * 1e-3) / 1e9
+        ok_ref = bool((st_ref == 0).all().item())
+        parity_in["fom_refined"] = (th_ref_np[:4].copy(), q_ref[:4].cpu().numpy())
+        # strong scaling: the SAME total batch whatever the number of ranks
+        tot = args.refined_strong_total
+        lo, hi = min(rank * ((tot + world - 1) // world), tot), min((rank + 1) * ((tot + world - 1) // world), tot)
+        th_s = torch.from_numpy(refined_inputs(tot, REF_SEED)[lo:hi]).to(dev)
+        q_s = torch.empty((max(hi - lo, 1), 9), dtype=f64, device=dev)
+        strong_dev = affine_dev(hr, th_s, hi - lo, q_s, solver=0, maxit=50000) if hi > lo else (lambda: None)
+
+        def strong_step():
+            if hi > lo:
+                hr.set_int("fom_solver", 0)
+                hr.fom_affine_raw(th_s.data_ptr(), hi - lo, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, 50000, qoi=q_s.data_ptr(), stream=sp)
+            if world > 1:
+                gather_rows(q_s[: hi - lo], tot)
+        ms_s, _ = timed(strong_step, args.refined_steps, 1, hr)
+        # streaming PCG (K4): the genuinely HBM-bound kernel of round 1
+        NP = min(args.refined_pcg_batch, NRf)
+        pcgr = None
+        if NP > 0:
+            ref_pcg = affine_dev(hr, th_ref, NP, q_ref, it_ref, st_ref, solver=1, maxit=50000)
+            ms_rp, l_rp = timed(ref_pcg, 1, 1, hr)
+            step_rp = ms_rp - flush_ms
+            it_sum_ref = int(it_ref[:NP].to(torch.int64).sum().item())
+            bytes_ref = 88.0 * opsr.n * it_sum_ref
+            parity_in["fom_refined_pcg"] = (th_ref_np[:4].copy(), q_ref[:4].cpu().numpy())
+            pcgr = {"value": world * NP / (step_rp * 1e-3), "unit": "solves/s", "ms_per_step": step_rp, "samples_per_gpu": NP,
+                    "mean_pcg_iters": it_sum_ref / NP, "all_converged": bool((st_ref[:NP] == 0).all().item()),
+                    "kernel": f"pcg_stream_kernel (K4, tile {hr.get_int('stream_tile')})", "gpu_launches": l_rp,
+                    "roofline": {"bound": "hbm", "achieved": bytes_ref / (step_rp * 1e-3) / 1e9, "peak": None, "unit": "GB/s",
+                                 "frac": None, "algorithmic_bytes_per_launch": bytes_ref,
+                                 "note": "88*n bytes per iteration per sample (SURVEY 8d), each sample counted with its own "
+                                         "iteration count; vectors stream from HBM every pass (working set >> L2)"}}
+        pairs = ref_geo["pair_updates"] if ref_geo else 0
         refined = {
             "value": world * NRf / (step_ref * 1e-3), "unit": "solves/s", "ms_per_step": step_ref,
             "steps": args.refined_steps, "warmup": 1,
             "workload": f"config[3]: refined mesh m={REFINED_M}, n={opsr.n} dofs, nine-param theta~U(0.1,10), "
-                        f"{NRf} samples per GPU per step, streaming PCG kernel (tile {hr.get_int('stream_tile')})",
-            "mean_pcg_iters": it_sum_ref / NRf, "all_converged": bool((st_ref == 0).all().item()),
-            "gpu_launches": l_ref,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": None, "unit": "GB/s", "frac": None,
-                         "kernel": "pcg_stream_kernel", "algorithmic_bytes_per_launch": bytes_ref,
-                         "note": "88*n bytes per iteration per sample (SURVEY 8d), each sample counted with its own "
-                                 "iteration count; vectors stream from HBM every pass (working set >> L2)"},
+                        f"{NRf} samples per GPU per step",
+            "solver": "direct" if ref_geo else "pcg", "frontal": ref_geo, "all_converged": ok_ref, "gpu_launches": l_ref,
+            "roofline": ({"bound": "smem", "unit": "GB/s", "peak": smem_peak,
+                          "achieved": 16.0 * pairs * NRf / (step_ref * 1e-3) / 1e9,
+                          "frac": 16.0 * pairs * NRf / (step_ref * 1e-3) / 1e9 / smem_peak,
+                          "algorithmic_bytes_per_solve": 16.0 * pairs,
+                          "note": "the front lives in shared memory: every pair update reads and writes 8 bytes of it; no "
+                                  "HBM traffic beyond theta / qoi in this mode"} if ref_geo else None),
+            "strong_scaling": {"value": tot / ((ms_s / args.refined_steps - flush_ms) * 1e-3), "unit": "solves/s",
+                               "samples_total": tot, "samples_this_rank": hi - lo, "n_gpus": world,
+                               "ms_per_step": ms_s / args.refined_steps - flush_ms,
+                               "note": "fixed total batch split over the ranks (one sample per CTA: the tail is "
+                                       "ceil(samples / CTAs) waves)"},
+            "pcg_stream": pcgr,
         }
         hr.close()
     clocks = sampler.stop()
 
-    # ---- kernel-only duration of the dominant kernel (PCG) for the roofline: one more step, events tight
-    # around the single launch on its stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = []
-    for _ in range(3):
-        flush.fill_(1)
-        e0.record(stream)
-        h.fom_affine_raw(th_f.data_ptr(), NF, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, 20000, qoi=q_f.data_ptr(),
-                         iters=it_f.data_ptr(), status=st_f.data_ptr(), stream=sp)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        kms.append(e0.elapsed_time(e1))
-    k_ms = float(np.mean(kms))
-    iters_sum = int(it_f.to(torch.int64).sum().item())
-    ok_f = bool((st_f == 0).all().item())
-    ok_r = bool((st_r == 0).all().item())
-
     # DGEMM rate of this GPU (cuBLAS) as the FP64 denominator for the ROM leg
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a = torch.randn(4096, 4096, dtype=f64, device=dev)
     b = torch.randn(4096, 4096, dtype=f64, device=dev)
     for _ in range(2):
@@ -513,6 +694,35 @@ def run_b200(args):
     if rank != 0:
         return
 
+    # ---- parity: first outputs of every leg against the CPU oracle (checker only; outside every timed region)
+    parity, parity_ok = None, True
+    if not args.no_parity:
+        from oracle.thermal_fin_oracle import FinOracle
+        parity = {}
+        orc = FinOracle(V.mesh().coordinates(), V.mesh().cells())
+        for leg in ("fom", "fom_pcg"):
+            th, q = parity_in[leg]
+            parity[leg] = max(relerr(q[s], orc.qoi_operator(orc.forward_nine_param(th[s]))) for s in range(len(th)))
+        th, q = parity_in["rom"]
+        parity["rom"] = max(relerr(q[s], orc.qoi_reduced(orc.forward_nine_param_reduced(th[s], phi), phi)) for s in range(len(th)))
+        if "fom_nodal" in parity_in:
+            kk, q = parity_in["fom_nodal"]
+            parity["fom_nodal"] = max(relerr(q[s], orc.qoi_operator(orc.forward(kk[s]))) for s in range(len(kk)))
+        orcu = FinOracle(opsu.coords, opsu.cells)
+        th, q = parity_in["fom_unstructured"]
+        parity["fom_unstructured"] = max(relerr(q[s], orcu.qoi_operator(orcu.forward_nine_param(th[s]))) for s in range(len(th)))
+        if "fom_refined" in parity_in:
+            orcr = FinOracle(opsr.coords, opsr.cells)
+            for leg in ("fom_refined", "fom_refined_pcg"):
+                if leg in parity_in:
+                    th, q = parity_in[leg]
+                    parity[leg] = max(relerr(q[s], orcr.qoi_operator(orcr.forward_nine_param(th[s]))) for s in range(len(th)))
+        parity_ok = all(v <= PARITY_BOUND[k] for k, v in parity.items())
+        parity["bounds"] = {k: PARITY_BOUND[k] for k in parity if k != "bounds"}
+        parity["what"] = ("max relative error of the observables of the first 64 samples of each leg (4 on the refined mesh) "
+                          "against the CPU oracle (sparse LU); the oracle itself is a restatement, DESIGN.md section 0")
+        parity["ok"] = parity_ok
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -520,33 +730,19 @@ def run_b200(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    traffic, traffic_note, ncu_t = None, None, {}
+    ncu_t = {}
     try:
         ncu_t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        t = ncu_t["pcg_kernel"]
-        # DRAM traffic of the on-chip kernel: operator arrays once + 152 B/sample, scaled to this launch's batch
-        traffic = t["dram_bytes"] + max(0, NF - t["launch_samples"]) * 152.0
-        traffic_note = (f"ncu --set full capture of a {t['launch_samples']}-sample launch: {t['dram_bytes']:.0f} B "
-                        f"(profiles/r1_ncu_summary.md), plus 152 B/sample of theta/qoi for the larger batch")
     except Exception:
         pass
 
-    # algorithmic bytes of one PCG launch: 88 n bytes per iteration per sample + theta in, qoi out
-    alg_bytes = 88.0 * n * iters_sum + NF * (9 * 8 + n_obs * 8 + 8)
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    if refined is not None:
-        refined["roofline"]["peak"] = hbm_peak
-        refined["roofline"]["frac"] = refined["roofline"]["achieved"] / hbm_peak
-        refined["roofline"]["peak_source"] = peak_src
+    if refined is not None and refined["pcg_stream"] is not None:
+        rr = refined["pcg_stream"]["roofline"]
+        rr["peak"], rr["frac"], rr["peak_source"] = hbm_peak, rr["achieved"] / hbm_peak, peak_src
         ts = ncu_t.get("pcg_stream_kernel")
-        refined["roofline"]["traffic"] = (ts["ratio_to_algorithmic"] * refined["roofline"]["algorithmic_bytes_per_launch"]
-                                          if ts else None)
-        refined["roofline"]["traffic_note"] = (
-            f"ncu capture ({ts['launch']}): dram bytes / algorithmic bytes = {ts['ratio_to_algorithmic']:.4f}, applied "
-            f"to this launch" if ts else None)
-    if nodal is not None:
-        nodal["roofline"]["peak"] = hbm_peak
-        nodal["roofline"]["frac"] = nodal["roofline"]["achieved"] / hbm_peak
+        rr["traffic"] = ts["ratio_to_algorithmic"] * rr["algorithmic_bytes_per_launch"] if ts else None
+        rr["traffic_note"] = (f"ncu capture ({ts['launch']}): dram bytes / algorithmic bytes = "
+                              f"{ts['ratio_to_algorithmic']:.4f}, applied to this launch" if ts else None)
     step_ms_f = (ms_f / K) - flush_ms
     step_ms_r = (ms_r / K) - flush_ms
     fom_rate = world * NF / (step_ms_f * 1e-3)
@@ -555,40 +751,71 @@ def run_b200(args):
     rom_e2e_rate = world * NR / ((ms_re / K - flush_ms) * 1e-3)
     rom_flops = 2 * 55 * 3321 + 2 * 10 * 81 + 81 ** 3 / 3 + 2 * 81 ** 2 + 2 * 9 * 81     # SURVEY 8d, ~559 kflop
 
+    # ---- roofline of the dominant kernel of the headline leg
+    if fom_geo:
+        # D1: the front, the right-hand side and the factor ring live in shared memory.  Bytes a solve MUST move there:
+        # 16 per pair update (read + write 8), and per factor entry 16 (gather + zero) + 16 (rhs update) + 16 (backward:
+        # factor row + solution)
+        smem_bytes = 16.0 * fom_geo["pair_updates"] + 48.0 * fom_geo["factor_nnz"]
+        hbm_bytes = 16.0 * (fom_geo["factor_nnz"] + 2 * n) + 9 * 8 + n_obs * 8 + 8     # factor out and back, theta, qoi
+        t1 = ncu_t.get("frontal_lane_kernel")
+        roofline = {
+            "bound": "smem", "achieved": smem_bytes * NF / (k_ms * 1e-3) / 1e9, "peak": smem_peak, "unit": "GB/s",
+            "frac": smem_bytes * NF / (k_ms * 1e-3) / 1e9 / smem_peak,
+            "peak_source": "tfin_smem_bandwidth(): conflict-free 16-byte shared-memory loads on all SMs, measured in this run",
+            "kernel": "frontal_lane_kernel (D1)", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": smem_bytes * NF,
+            "traffic": (t1["dram_bytes"] / t1["launch_samples"] * NF) if t1 else None,
+            "traffic_note": (f"ncu --set full capture of a {t1['launch_samples']}-sample launch ({t1['dram_bytes']:.4g} B of DRAM "
+                             f"traffic = the factor written and read back once), scaled to this batch" if t1 else None),
+            "hbm": {"algorithmic_bytes_per_launch": hbm_bytes * NF, "achieved": hbm_bytes * NF / (k_ms * 1e-3) / 1e9,
+                    "peak": hbm_peak, "frac": hbm_bytes * NF / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src},
+            "note": "sparse-direct solve: the active front of every sample lives in shared memory, the factor makes one "
+                    "round trip through HBM for the backward substitution.  With two resident warps per SM the kernel is "
+                    "bound by instruction latency (ncu: issue slots 11 % busy, shared-memory pipe 25 %), see profiles/",
+        }
+    else:
+        pcg_bytes = (2 * pcg_geo["ell_width"] + 1) * 8.0 * n * iters_sum
+        roofline = {"bound": "smem", "achieved": pcg_bytes / (k_ms * 1e-3) / 1e9, "peak": smem_peak, "unit": "GB/s",
+                    "frac": pcg_bytes / (k_ms * 1e-3) / 1e9 / smem_peak, "kernel": "pcg_kernel<affine>", "kernel_ms": k_ms,
+                    "algorithmic_bytes_per_launch": pcg_bytes, "traffic": None}
+    t_k1 = ncu_t.get("pcg_kernel")
+    pcg_smem_bytes = (2 * pcg_geo["ell_width"] + 1) * 8.0 * n * iters_sum
+    fom_pcg = {
+        "value": world * NF / ((ms_p / max(2, K // 2) - flush_ms) * 1e-3), "unit": "solves/s",
+        "kernel": "pcg_kernel<affine> (K1, on-chip Jacobi-PCG of round 1; fom_solver = 1)", "mean_pcg_iters": iters_sum / NF,
+        "all_converged": ok_p, "geometry": pcg_geo, "gpu_launches": launches_p,
+        "roofline": {"bound": "smem", "achieved": pcg_smem_bytes / (k_ms_p * 1e-3) / 1e9, "peak": smem_peak, "unit": "GB/s",
+                     "frac": pcg_smem_bytes / (k_ms_p * 1e-3) / 1e9 / smem_peak, "kernel_ms": k_ms_p,
+                     "algorithmic_bytes_per_launch": pcg_smem_bytes,
+                     "traffic": (t_k1["dram_bytes"] + max(0, NF - t_k1["launch_samples"]) * 152.0) if t_k1 else None,
+                     "note": "shared-memory bytes per iteration = (W gathered residual entries + W values + 1 store) x 8 B x n "
+                             "rows, W = ELL width; the CG vectors never leave the SM, so the SURVEY 8d HBM model (88 n bytes "
+                             f"per iteration = {88.0 * n * iters_sum / (k_ms_p * 1e-3) / 1e9:.0f} GB/s here) is not a bound"},
+    }
+
     line = {
         "metric": METRIC, "value": fom_rate, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": step_ms_f, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": "FOM leg (value): config[2] five-param batched FOM, QoI = subfin averages; ROM leg (rom): "
-                        "config[1] nine-param batched ROM; fom_refined: config[3]; fom_nodal: config[4]",
-            "fom_samples_per_gpu_per_step": NF, "rom_samples_per_gpu_per_step": NR,
-            "mesh": f"structured conforming fin mesh m=3, n={n} dofs (reference mshr mesh is not shipped)",
-            "n_r": n_r, "pcg_tol": TOL, "mean_pcg_iters": iters_sum / NF, "all_converged": ok_f and ok_r,
-            "pcg_geometry": {"threads": h.get_int("pcg_threads"), "rows_per_thread": h.get_int("pcg_rows_per_thread"),
-                             "ctas_per_sm": h.get_int("pcg_ctas_per_sm"), "smem_bytes": h.get_int("pcg_smem_bytes"),
-                             "ell_width": h.get_int("ell_width")},
-            "l2": f"flushed between steps by a 256 MiB write ({flush_ms:.3f} ms, subtracted)",
-            "parallelism": f"samples sharded x{world}, NCCL all-gather of observables" if world > 1 else "1 GPU",
-        },
-        "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": traffic, "traffic_note": traffic_note, "kernel": "pcg_kernel<affine>", "kernel_ms": k_ms,
-            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-            "onchip": ({"bound": "smem", "pct_of_peak": ncu_t["pcg_kernel"].get("smem_pipe_pct_of_peak"),
-                        "metric": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
-                        "source": "profiles/r1_ncu_summary.json (ncu --set full of a 2960-sample launch)"}
-                       if "pcg_kernel" in ncu_t else None),
-            "note": "algorithmic bytes = 88*n*iterations per solve (SURVEY 8d); at n=1597 the CG vectors and the "
-                    "per-sample operator live in shared memory/registers, so achieved/peak is NOT bounded by 1 "
-                    "and real DRAM traffic (traffic) is orders of magnitude below it",
-        },
+        "config": dict(bench_config(args, world), **{
+            "legs": "value = FOM (direct solver); fom_pcg = same workload, round-1 PCG kernel; rom = config[1] nine-param "
+                    "ROM; fom_unstructured = reference-like mesh; fom_nodal = config[4]; fom_refined = config[3]",
+            "solver": "direct" if fom_geo else "pcg", "frontal": fom_geo, "all_converged": ok_f and ok_r,
+            "l2": f"flushed between steps by a 256 MiB write ({flush_ms:.3f} ms, subtracted)"}),
+        "roofline": roofline,
+        "parity": parity,
+        "gather_order_ok": gather_ok,
         "cpu_baseline": cpu,
         "e2e": {"value": fom_e2e_rate, "unit": "solves/s", "h2d_bytes_per_step": NF * 9 * 8,
                 "d2h_bytes_per_step": NF * (n_obs * 8 + 4 + 4), "ms_per_step": ms_fe / K - flush_ms,
                 "api": "tfin_fom_affine(TFIN_MEM_HOST) on pinned host buffers (the call AffineROMFin makes)"},
+        "e2e_facade": {"value": fac_f, "unit": "solves/s", "api": "AffineROMFin.forward_nine_param_qoi(theta) with pageable "
+                       "numpy in / numpy out, wall clock incl. Python", "rom_value": fac_r,
+                       "rom_api": "AffineROMFin.forward_reduced_qoi(theta)", "matches_device_path_bitwise": facade_same},
         "gpu_launches": launches_f,
         "clocks": clocks,
+        "fom_pcg": fom_pcg,
+        "fom_unstructured": unstructured,
         "fom_refined": refined,
         "fom_nodal": nodal,
         "rom": {
@@ -602,8 +829,15 @@ def run_b200(args):
                          "peak_source": "cuBLAS DGEMM 4096^3 measured in this run",
                          "flops_per_sample": rom_flops},
         },
+        "smem_bandwidth_measured_gbs": smem_peak,
     }
     print(json.dumps(line), flush=True)
+    if not parity_ok:
+        sys.stderr.write(f"bench.py: PARITY FAILURE {json.dumps(parity)}\n")
+        sys.exit(3)
+    if gather_ok is False:
+        sys.stderr.write("bench.py: gathered observables are not in shard order\n")
+        sys.exit(4)
 
 
 def main():
