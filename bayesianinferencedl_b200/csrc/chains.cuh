@@ -41,8 +41,8 @@ struct ChainState {
 };
 
 // One warp per chain.  init != 0: adopt the proposal unconditionally (first evaluation of the start state).
-__global__ void __launch_bounds__(256) chain_accept_kernel(ChainState st, const double* __restrict__ zp,
-                                                           const double* __restrict__ kp, const double* __restrict__ qp,
+__global__ void __launch_bounds__(256) chain_accept_kernel(ChainState st, const double* zp,   // zp may alias st.z (init)
+                                                           const double* kp, const double* __restrict__ qp,
                                                            const int* __restrict__ status_p, const double* __restrict__ data,
                                                            double inv_sigma2, unsigned long long seed, uint32_t step,
                                                            long long chain0, long long C, int n, int n_obs, int init) {
@@ -65,11 +65,16 @@ __global__ void __launch_bounds__(256) chain_accept_kernel(ChainState st, const 
         } else {
             double u1, u2;
             philox_uniform2(seed, (unsigned long long)(chain0 + c), PHILOX_PAIR_UNIFORM, step, u1, u2);
-            accept = valid && log(u1) < st.phi[c] - phi_p;
+            // lane 0 reads the current misfit and broadcasts it: lane 0 also overwrites it below, and the other lanes
+            // must not depend on the warp staying converged in between
+            double phi_cur = lane == 0 ? st.phi[c] : 0.0;
+            phi_cur = __shfl_sync(0xffffffffu, phi_cur, 0);
+            accept = valid && log(u1) < phi_cur - phi_p;
         }
         if (accept) {
+            const bool copy_z = zp != st.z;   // the start state is evaluated in place (init): nothing to copy
             for (int i = lane; i < n; i += 32) {
-                st.z[c * n + i] = zp[c * n + i];
+                if (copy_z) st.z[c * n + i] = zp[c * n + i];
                 if (st.k) st.k[c * n + i] = kp[c * n + i];
             }
             for (int o = lane; o < n_obs; o += 32) st.qoi[c * n_obs + o] = qp[c * n_obs + o];

@@ -80,8 +80,18 @@ class Fin:
             return idx
         path = os.path.join("..", "bayesian_inference", "rand_boundary_indices.npy")   # :226
         if os.path.exists(path):
-            return np.load(path)
-        # the commented recipe of forward_solve.py:223-225
+            idx = np.load(path).astype(np.int64)
+            # the stored indices belong to the dof numbering of the mesh they were drawn on (the reference's mshr mesh)
+            if idx.shape != (self.n_obs,) or idx.min() < 0 or idx.max() >= self.dofs or \
+                    not np.all(np.isin(idx, self.ops.boundary_dofs)):
+                raise ValueError(f"{path}: indices do not address exterior-boundary dofs of this mesh ({self.dofs} dofs); "
+                                 "pass the index array for this mesh as external_obs=<array>")
+            return idx
+        # the commented recipe of forward_solve.py:223-225 -- NOT the reference's stored draw (its .npy is not shipped)
+        import warnings
+        warnings.warn("external_obs=True: ../bayesian_inference/rand_boundary_indices.npy not found; drawing 40 boundary dofs "
+                      "with RandomState(32) as in the commented recipe of forward_solve.py:223-225 -- these are not the "
+                      "reference's stored indices", RuntimeWarning, stacklevel=3)
         rs = np.random.RandomState(32)
         return rs.choice(self.ops.boundary_dofs, self.n_obs)
 
@@ -143,8 +153,15 @@ class Fin:
         if st is not None and np.any(st != _cabi.STATUS_CONVERGED):
             bad = np.nonzero(st != _cabi.STATUS_CONVERGED)[0]
             rr = "" if out.get("relres") is None else f", relres {out['relres'][bad[0]]:.3e}"
-            raise RuntimeError(f"PCG did not converge for {len(bad)} sample(s) (first: {bad[0]}, status "
+            raise RuntimeError(f"solve failed for {len(bad)} sample(s) (first: {bad[0]}, status "
                                f"{int(st[bad[0]])}{rr}); is k > 0 everywhere?")
+        # PCG decides convergence on the recursively updated residual; the TRUE residual returned next to it must agree
+        # (for the direct solver relres is the consistency |b.w - y.y| / y.y of the two substitutions)
+        rr = out.get("relres")
+        if rr is not None and len(rr) and not np.all(rr <= max(1e3 * self.tol, 1e-9)):
+            bad = np.nonzero(~(rr <= max(1e3 * self.tol, 1e-9)))[0]
+            raise RuntimeError(f"true residual {rr[bad[0]]:.3e} of sample {bad[0]} is far above tol = {self.tol:g} "
+                               f"({len(bad)} sample(s)): recursive-residual drift")
 
     # ------------------------------------------------------------------ adjoint gradients
     def gradient(self, k, data, return_cost=False):

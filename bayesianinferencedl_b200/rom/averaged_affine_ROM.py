@@ -153,6 +153,10 @@ class AffineROMFin:
             bad = np.nonzero(st != _cabi.STATUS_CONVERGED)[0]
             raise RuntimeError(f"solve failed for {len(bad)} sample(s) (first: {bad[0]}, status {int(st[bad[0]])}); "
                                "conductivities must be positive")
+        rr = out.get("relres")   # true residual (PCG) / consistency of the two substitutions (direct solver)
+        if rr is not None and len(rr) and not np.all(rr <= max(1e3 * self.tol, 1e-9)):
+            bad = np.nonzero(~(rr <= max(1e3 * self.tol, 1e-9)))[0]
+            raise RuntimeError(f"true residual {rr[bad[0]]:.3e} of sample {bad[0]} is far above tol = {self.tol:g}")
 
     # ------------------------------------------------------------------ reduced-order model
     def forward_reduced(self, k):

@@ -939,3 +939,45 @@ def test_direct_solver_narrow_rows(space_m2, oracle_m2, lanes):
     assert np.array_equal(outn["qoi"], refn["qoi"]) and np.all(out["status"] == 0)
     assert relerr(out["qoi"][74], oracle_m2.qoi_operator(oracle_m2.forward_nine_param(theta[74]))) <= RTOL_FOM
     h.close()
+
+
+def test_external_obs_selector(space_m2, oracle_m2, tmp_path, monkeypatch):
+    """``external_obs=True`` (forward_solve.py:215-228, averaged_affine_ROM.py:195-206): 40 point observations on the
+    exterior boundary instead of the nine sub-fin averages.  The reference loads ``rand_boundary_indices.npy`` (not
+    shipped); without it the commented RandomState(32) recipe is used, with a warning.  Observables = w at those dofs."""
+    from bayesianinferencedl_b200 import AffineROMFin, Fin
+    from bayesianinferencedl_b200.assembly import build_operators
+    ops = build_operators(space_m2)
+    rng = np.random.default_rng(46)
+    phi = np.linalg.qr(rng.standard_normal((ops.n, 10)))[0]
+    with pytest.warns(RuntimeWarning, match="rand_boundary_indices"):
+        fin = Fin(space_m2, external_obs=True)
+    assert fin.n_obs == 40 and fin.B_obs.shape == (40, ops.n) and np.all(fin.B_obs.sum(axis=1) == 1.0)
+    idx = np.argmax(fin.B_obs, axis=1)
+    assert np.all(np.isin(idx, ops.boundary_dofs))
+    assert np.array_equal(idx, np.random.RandomState(32).choice(ops.boundary_dofs, 40))
+    k = np.exp(0.4 * rng.standard_normal((5, ops.n)))
+    q = fin.forward_qoi(k)
+    w = fin.forward(k)[0]
+    for s in range(5):
+        w_ref = oracle_m2.forward(k[s])
+        assert relerr(q[s], w_ref[idx]) <= RTOL_FOM, s
+        assert np.array_equal(q[s], np.asarray(fin.qoi_operator(w[s]))) or relerr(q[s], fin.qoi_operator(w[s])) < 1e-13
+    # explicit index array (what a user with the reference's .npy for THIS mesh would pass) on the affine model + ROM
+    mine = ops.boundary_dofs[:40]
+    rom = AffineROMFin(space_m2, None, phi, external_obs=mine)
+    assert rom.n_obs == 40 and rom.B_obs_phi.shape == (40, 10)
+    theta = rng.uniform(0.1, 3.5, (4, 9))
+    qa, qr = rom.forward_nine_param_qoi(theta), rom.forward_reduced_qoi(theta)
+    for s in range(4):
+        assert relerr(qa[s], oracle_m2.forward_nine_param(theta[s])[mine]) <= RTOL_FOM
+        wr = oracle_m2.forward_nine_param_reduced(theta[s], phi)
+        assert np.max(np.abs(qr[s] - (phi @ wr)[mine])) <= 1e-8 * np.max(np.abs(phi @ wr))
+    # a stored index file that belongs to another mesh is rejected instead of being applied blindly
+    d = tmp_path / "rom"
+    d.mkdir()
+    (tmp_path / "bayesian_inference").mkdir()
+    np.save(tmp_path / "bayesian_inference" / "rand_boundary_indices.npy", np.arange(40) + 10 * ops.n)
+    monkeypatch.chdir(d)
+    with pytest.raises(ValueError, match="do not address"):
+        Fin(space_m2, external_obs=True)
