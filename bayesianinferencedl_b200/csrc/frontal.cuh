@@ -88,9 +88,16 @@ struct StreamRing {
 // ------------------------------------------------------------------------------------------------ D1
 // shared memory per warp:  F[ntri][32] | yv[nslots][32] | qacc[n_obs][32] | cvec[ncv][32] (affine only) |
 //                          factor-row ring [lr_rows][32] (backward substitution) | instruction ring
+// phase: 0 = factorisation and backward substitution in one kernel, 1 = factorisation + forward elimination only (factor
+// blocks of every group stay in HBM), 2 = backward substitution + observables only
+#define FRONTAL_PHASE_BOTH 0
+#define FRONTAL_PHASE_FACTOR 1
+#define FRONTAL_PHASE_BSUB 2
 __host__ __device__ inline size_t frontal_lane_smem(int ntri, int nslots, int n_obs, int ncv_smem, int lr_rows, int lanes,
-                                                    int ring_bytes) {
-    return (size_t)(ntri + nslots + n_obs + ncv_smem + lr_rows) * lanes * sizeof(double) + (size_t)ring_bytes;
+                                                    int ring_bytes, int phase) {
+    const int rows = (phase == FRONTAL_PHASE_BSUB ? 0 : ntri) + nslots + (phase == FRONTAL_PHASE_FACTOR ? 0 : n_obs) +
+                     (phase == FRONTAL_PHASE_BSUB ? 0 : ncv_smem) + (phase == FRONTAL_PHASE_FACTOR ? 0 : lr_rows);
+    return (size_t)rows * lanes * sizeof(double) + (size_t)ring_bytes;
 }
 
 #define FRONTAL_DMAX 7   // the backward substitution prefetches the factor rows of up to DMAX pivots ahead
@@ -111,7 +118,11 @@ __device__ __forceinline__ void cp_async_wait_dyn(unsigned k) {   // k <= FRONTA
     }
 }
 
-template <int CM>
+// Split launch (PHASE 1 then PHASE 2): the factorisation needs the front in shared memory (two warps per SM at n = 1597),
+// the substitution only a right-hand side and the factor-block ring, so eight or more of its warps fit -- and both are
+// bound by instruction latency, i.e. by resident warps.  The factor blocks of all groups of a chunk then live in HBM
+// (workspace row block g), plus two rows per group for y.y and the breakdown flag.
+template <int CM, int PHASE>
 __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalIO io) {
     static_assert(CM % 4 == 0, "columns are read four entries at a time");
     extern __shared__ __align__(16) double fsm[];
@@ -123,18 +134,19 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
     const unsigned rb = 8u * (unsigned)LPG;            // bytes of one [row][lane] row
     // byte-addressed views of this lane's column of every [row][lane] array
     char* F = reinterpret_cast<char*>(fsm + lane);
-    char* yv = F + (size_t)P.ntri * rb;
+    char* yv = F + (size_t)(PHASE == FRONTAL_PHASE_BSUB ? 0 : P.ntri) * rb;
     char* qacc = yv + (size_t)P.nslots * rb;
-    char* cvs = qacc + (size_t)io.n_obs * rb;        // affine only
-    char* Lring = cvs + (size_t)(io.cv_global ? 0 : P.ncv) * rb;
+    char* cvs = qacc + (size_t)(PHASE == FRONTAL_PHASE_FACTOR ? 0 : io.n_obs) * rb;        // affine only
+    char* Lring = cvs + (size_t)((io.cv_global || PHASE == FRONTAL_PHASE_BSUB) ? 0 : P.ncv) * rb;
     StreamRing ring;
-    ring.buf = reinterpret_cast<unsigned char*>(Lring - lane * 8 + (size_t)P.lr_rows * rb);
+    ring.buf = reinterpret_cast<unsigned char*>(Lring - lane * 8 + (size_t)(PHASE == FRONTAL_PHASE_FACTOR ? 0 : P.lr_rows) * rb);
     ring.mask = (unsigned)P.ring_bytes - 1u;
     const unsigned full = 0xffffffffu;
     const long long n_groups = (io.N + LPG - 1) / LPG;
     const int n = P.n;
-    const size_t wrows = (size_t)P.nnzL + 2 * (size_t)n;   // per-CTA workspace rows: per pivot [1/L_jj, y_j, column]
-    char* Lw = reinterpret_cast<char*>(io.work + (size_t)blockIdx.x * wrows * LPG + lane);
+    const size_t wrows = (size_t)P.nnzL + 2 * (size_t)n;   // workspace rows: per pivot [1/L_jj, y_j, column]
+    // one workspace per CTA (both phases in one kernel) or per group (split launch; + 2 rows: y.y, breakdown flag)
+    char* Lw0 = reinterpret_cast<char*>(io.work + lane);
     auto ld = [](const char* base, unsigned off) { return *reinterpret_cast<const double*>(base + off); };
     auto st = [](char* base, unsigned off, double v) { *reinterpret_cast<double*>(base + off) = v; };
 
@@ -146,6 +158,10 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
         const long long s = g * LPG + lane;
         const bool valid = s < io.N && xlane < LPG;
         const long long sc = s < io.N ? s : io.N - 1;
+        char* Lw = Lw0 + (PHASE == FRONTAL_PHASE_BOTH ? (size_t)blockIdx.x * wrows : (size_t)g * (wrows + 2)) * rb;
+        bool bad = false;
+        double yy = 0.0;
+        if (PHASE != FRONTAL_PHASE_BSUB) {
         ring.reset(P.fwd);
         ring.fill(xlane, true);
         cp_async_commit();
@@ -159,10 +175,9 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
         }
         for (int e = 0; e < P.ntri; ++e) st(F, rb * e, 0.0);
         for (int e = 0; e < P.nslots; ++e) st(yv, rb * e, 0.0);
-        for (int o = 0; o < io.n_obs; ++o) st(qacc, rb * o, 0.0);
+        if (PHASE == FRONTAL_PHASE_BOTH)
+            for (int o = 0; o < io.n_obs; ++o) st(qacc, rb * o, 0.0);
 
-        bool bad = false;
-        double yy = 0.0;
         char* Lj = Lw;   // workspace block of the current pivot
         for (int j = -1; j < n; ++j) {
             cp_async_wait<0>();
@@ -267,6 +282,19 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
                 }
             }
             ring.rd += reclen;
+        }
+        if (PHASE == FRONTAL_PHASE_FACTOR) {   // hand y.y and the breakdown flag to the substitution kernel
+            st(Lw, (unsigned)(wrows * rb), yy);
+            st(Lw, (unsigned)((wrows + 1) * rb), bad ? 1.0 : 0.0);
+            cp_async_wait<0>();
+            __syncwarp();
+            continue;
+        }
+        } else {   // PHASE_BSUB: right-hand side slots start empty, y.y / flag come from the factor kernel
+            for (int e = 0; e < P.nslots; ++e) st(yv, rb * e, 0.0);
+            for (int o = 0; o < io.n_obs; ++o) st(qacc, rb * o, 0.0);
+            yy = ld(Lw, (unsigned)(wrows * rb));
+            bad = ld(Lw, (unsigned)((wrows + 1) * rb)) != 0.0;
         }
         // ---- backward substitution L^T w = y (yv doubles as the slot-indexed solution), observables on the fly.  The
         // factor blocks [1/L_jj, y_j, column] come back from HBM through a block ring in shared memory that cp.async fills

@@ -152,19 +152,11 @@ struct FrontalSet {
         // by shared memory whatever the row width, so 32 lanes is the default; 16 / 8 trade lanes for resident warps.
         int lanes = (want_lanes == 8 || want_lanes == 16) ? want_lanes : 32;
         const long long row = 8LL * lanes;
-        // factor-block ring: room for ~4 average blocks ahead, within an even share of the SM for as many warps as fit
-        long long lr = std::min<long long>(96, 4LL * (host.cmax + 2));
-        for (;;) {
-            const long long smem = (base_rows + lr) * row + 8192;   // instruction ring <= 8 KB
-            const long long warps = ((long long)smem_optin + 1024) / (smem + 1024);
-            const long long smem_min = (base_rows + host.cmax + 2) * row + 8192;
-            const long long warps_min = ((long long)smem_optin + 1024) / (smem_min + 1024);
-            if (warps >= warps_min && warps >= 1) break;   // the ring does not cost a resident warp
-            if (lr <= host.cmax + 2) {
-                if (warps_min < 1) lr = 0;                 // D1 cannot serve this front (D2 will)
-                break;
-            }
-            lr = std::max<long long>(host.cmax + 2, lr - 4);
+        // factor-block ring of the substitution kernel (split launch: no front in its shared memory): ~4 blocks ahead
+        long long lr = std::max<long long>(host.cmax + 2, std::min<long long>(64, 4LL * (host.cmax + 2)));
+        {
+            const long long smem_f = (base_rows - n_obs) * row + 8192;   // factor kernel: front + rhs + coefficients + ring
+            if (smem_f + 1024 > (long long)smem_optin + 1024 || host.cmax > 32) lr = 0;   // D1 cannot serve this front
         }
         frontal_pack_streams(host, (int)lr, FRONTAL_DMAX, lanes, &streams);
         if (int e = fwd.upload(streams.fwd, st)) return e;
@@ -271,6 +263,8 @@ struct tfin_ctx {
     int frontal_threads = 0; // D2 threads per CTA, 0 = auto
     int frontal_mode = -1;   // D2: -1 auto, 0 = QOI (extra right-hand sides), 1 = SOLVE (factor to HBM + backward)
     int frontal_lanes = 0;   // D1: samples per warp, 0 = auto, else 8 / 16 / 32 (takes effect at the next tfin_set_*)
+    int frontal_split = 1;   // D1: 1 = factor kernel + substitution kernel, 0 = one fused kernel
+    int last_focc_b = 0;
     int last_solver = 0, last_fkernel = 0, last_fthreads = 0, last_focc = 0;
     size_t last_fsmem = 0;
     // ---- tuning
@@ -1015,9 +1009,13 @@ static int launch_pcg_stream(tfin_ctx* h, const double* d_in, int in_stride, int
 }
 
 // ---- sparse-direct solver (frontal.cuh).  Geometry of the kernel that would serve this operator; kernel = 0 if none.
-static const void* frontal_lane_fn(int cmax) {
-    return cmax <= 8 ? (const void*)frontal_lane_kernel<8> : cmax <= 16 ? (const void*)frontal_lane_kernel<16>
-           : cmax <= 24 ? (const void*)frontal_lane_kernel<24> : (const void*)frontal_lane_kernel<32>;
+static const void* frontal_lane_fn(int cmax, int phase) {
+#define TFIN_LANE_FN(PH)                                                                                             \
+    (cmax <= 8 ? (const void*)frontal_lane_kernel<8, PH> : cmax <= 16 ? (const void*)frontal_lane_kernel<16, PH>     \
+     : cmax <= 24 ? (const void*)frontal_lane_kernel<24, PH> : (const void*)frontal_lane_kernel<32, PH>)
+    return phase == FRONTAL_PHASE_FACTOR ? TFIN_LANE_FN(FRONTAL_PHASE_FACTOR)
+           : phase == FRONTAL_PHASE_BSUB ? TFIN_LANE_FN(FRONTAL_PHASE_BSUB) : TFIN_LANE_FN(FRONTAL_PHASE_BOTH);
+#undef TFIN_LANE_FN
 }
 
 static const void* frontal_cta_fn(int mode, int cmax) {
@@ -1033,6 +1031,9 @@ struct FrontalGeom {
     int mode = 0;     // D2: FRONTAL_MODE_QOI / FRONTAL_MODE_SOLVE
     int threads = 0, occ = 0;
     size_t smem = 0;
+    bool split = false;            // D1: factorisation and substitution as two kernels
+    int occ_b = 0;                 // D1 split: resident warps per SM of the substitution kernel
+    size_t smem_b = 0;
     FrontalCtaSmem cta{};
 };
 
@@ -1045,18 +1046,28 @@ static FrontalGeom frontal_geom(tfin_ctx* h, bool nodal, bool want_w) {
     const int ncv_smem = nodal ? 0 : fs.ncv;
     const int ring = fs.streams.ring_bytes;
     if (h->frontal_kernel != 2 && P.cmax <= 32 && fs.streams.lr_rows > 0) {
-        const void* fn = frontal_lane_fn(P.cmax);
-        const size_t sm = frontal_lane_smem(ntri, P.nslots, h->n_obs, ncv_smem, fs.streams.lr_rows, fs.streams.lanes, ring);
-        if (sm <= (size_t)h->max_smem_optin &&
-            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess) {
+        auto fits = [&](int phase, size_t* sm_out, int* occ_out) {
+            const void* fn = frontal_lane_fn(P.cmax, phase);
+            const size_t sm = frontal_lane_smem(ntri, P.nslots, h->n_obs, ncv_smem, fs.streams.lr_rows, fs.streams.lanes, ring, phase);
+            if (sm > (size_t)h->max_smem_optin ||
+                cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+                return false;
             int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, sm) == cudaSuccess && occ >= 1) {
-                g.kernel = 1;
-                g.threads = 32;
-                g.occ = occ;
-                g.smem = sm;
-                return g;
-            }
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, sm) != cudaSuccess || occ < 1) return false;
+            *sm_out = sm;
+            *occ_out = occ;
+            return true;
+        };
+        if (h->frontal_split != 0 && fits(FRONTAL_PHASE_FACTOR, &g.smem, &g.occ) && fits(FRONTAL_PHASE_BSUB, &g.smem_b, &g.occ_b)) {
+            g.kernel = 1;
+            g.threads = 32;
+            g.split = true;
+            return g;
+        }
+        if (fits(FRONTAL_PHASE_BOTH, &g.smem, &g.occ)) {
+            g.kernel = 1;
+            g.threads = 32;
+            return g;
         }
         cudaGetLastError();
     }
@@ -1105,9 +1116,21 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
     const size_t per_sample_work = (size_t)P.nnzL + 2 * (size_t)P.n;
     // the nodal operator needs the coefficient vector of every sample in HBM: bound that workspace by chunking
     int64_t chunk = N;
+    if (g.kernel == 1 && g.split) {
+        // split launch: the factor blocks of every group of a chunk stay in HBM (<= ~6 GiB).  A chunk is a whole number of
+        // WAVES of the factor kernel (resident warps x samples per warp): a partial last wave would idle most of the GPU
+        // for a full pass (2 ms at n = 1597)
+        const int64_t wave = (int64_t)h->sm_count * g.occ * fs.streams.lanes;
+        const int64_t mem_waves = std::max<int64_t>(1, (((int64_t)6 << 30) / ((int64_t)(per_sample_work + 2) * 8)) / wave);
+        // ... and preferably a whole number of waves of the substitution kernel too
+        int64_t k = g.occ_b / std::__gcd(g.occ, g.occ_b);
+        while (k * 2 <= mem_waves) k *= 2;
+        if (k > mem_waves) k = mem_waves;
+        chunk = std::min<int64_t>(chunk, k * wave);
+    }
     if (nodal) {
         const int64_t cap = std::max<int64_t>(32, ((int64_t)1 << 30) / ((int64_t)fs.ncv * 8) / 32 * 32);
-        chunk = std::min<int64_t>(N, cap);
+        chunk = std::min<int64_t>(chunk, cap);
         if (int e = h->d_fcv.reserve((size_t)((chunk + 31) / 32 * 32) * fs.ncv)) return e;
     }
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
@@ -1133,11 +1156,22 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
         TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
         if (g.kernel == 1) {
             const int lanes = fs.streams.lanes;
-            const int grid = (int)std::min<int64_t>((m + lanes - 1) / lanes, (int64_t)h->sm_count * g.occ);
-            if (int e = h->d_fwork.reserve((size_t)grid * per_sample_work * lanes)) return e;
-            io.work = h->d_fwork.p;
+            const int64_t groups = (m + lanes - 1) / lanes;
+            const int grid = (int)std::min<int64_t>(groups, (int64_t)h->sm_count * g.occ);
             void* args[] = {(void*)&dev, (void*)&io};
-            TFIN_CUDA(cudaLaunchKernel(frontal_lane_fn(P.cmax), dim3(grid), dim3(32), args, g.smem, st));
+            if (g.split) {
+                if (int e = h->d_fwork.reserve((size_t)groups * (per_sample_work + 2) * lanes)) return e;
+                io.work = h->d_fwork.p;
+                TFIN_CUDA(cudaLaunchKernel(frontal_lane_fn(P.cmax, FRONTAL_PHASE_FACTOR), dim3(grid), dim3(32), args, g.smem, st));
+                TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
+                const int grid_b = (int)std::min<int64_t>(groups, (int64_t)h->sm_count * g.occ_b);
+                TFIN_CUDA(cudaLaunchKernel(frontal_lane_fn(P.cmax, FRONTAL_PHASE_BSUB), dim3(grid_b), dim3(32), args, g.smem_b, st));
+                h->launches += 1;
+            } else {
+                if (int e = h->d_fwork.reserve((size_t)grid * per_sample_work * lanes)) return e;
+                io.work = h->d_fwork.p;
+                TFIN_CUDA(cudaLaunchKernel(frontal_lane_fn(P.cmax, FRONTAL_PHASE_BOTH), dim3(grid), dim3(32), args, g.smem, st));
+            }
         } else {
             const int grid = (int)std::min<int64_t>(m, (int64_t)h->sm_count * g.occ);
             if (g.mode == FRONTAL_MODE_SOLVE) {
@@ -1155,6 +1189,7 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
     h->last_fkernel = g.kernel == 1 ? 1 : (g.mode == FRONTAL_MODE_QOI ? 2 : 3);
     h->last_fthreads = g.threads;
     h->last_focc = g.occ;
+    h->last_focc_b = g.split ? g.occ_b : 0;
     h->last_fsmem = g.smem;
     h->last_path = 4;
     return 0;
@@ -2031,6 +2066,7 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
     if (k == "fom_solver") return h->last_solver;          // solver of the last forward solve: 1 PCG, 2 direct
     if (k == "frontal_kernel") return h->last_fkernel;     // 1 = D1, 2 = D2 observables mode, 3 = D2 solve mode
     if (k == "frontal_threads") return h->last_fthreads;
+    if (k == "frontal_bsub_ctas_per_sm") return h->last_focc_b;
     if (k == "frontal_lanes") return h->fr_aff.ok ? h->fr_aff.streams.lanes : -1;
     if (k == "frontal_ring_rows") return h->fr_aff.ok ? h->fr_aff.streams.lr_rows : -1;
     if (k == "frontal_ctas_per_sm") return h->last_focc;
@@ -2103,6 +2139,10 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
                 if (int e = fs->upload(h->stream, h->n_obs, h->max_smem_optin, h->frontal_lanes)) return e;
                 TFIN_CUDA(cudaStreamSynchronize(h->stream));
             }
+        return 0;
+    }
+    if (k == "frontal_split") {
+        h->frontal_split = value != 0;
         return 0;
     }
     if (k == "frontal_mode") {
@@ -2214,8 +2254,9 @@ __global__ void __launch_bounds__(1024) smem_bandwidth_kernel(int iters, double*
     double2 acc = make_double2(0.0, 0.0);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {   // 8 DISTINCT rows per iteration, rotated with `it`: nothing to CSE or hoist
-            const double2 v = sm_bw[t + T * ((u + it) & 7)];
+        for (int u = 0; u < 8; ++u) {   // 8 distinct rows per iteration; asm volatile: one LDS.128 each, nothing CSE'd or hoisted
+            double2 v;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(&sm_bw[t + T * ((u + it) & 7)])));
             acc.x += v.x;
             acc.y += v.y;
         }

@@ -38,7 +38,12 @@ if "small" in which:
         print(f"m=3 affine {name}: {N/ms*1e3:.3e} solves/s  ({ms:.2f} ms; kernel {h.get_int('frontal_kernel')} threads {h.get_int('frontal_threads')} "
               f"ctas/sm {h.get_int('frontal_ctas_per_sm')} smem {h.get_int('frontal_smem_bytes')})", flush=True)
     h.set_int("fom_solver", 2); h.set_int("frontal_kernel", 1)
-    for lanes in (16, 8, 32):
+    for split in (0, 1):
+        h.set_int("frontal_split", split)
+        ms = timeit(lambda: h.fom_affine_raw(theta.data_ptr(), N, 0, 1, 1e-12, 20000, qoi=q.data_ptr(), stream=st))
+        print(f"m=3 affine direct D1 split={split}: {N/ms*1e3:.3e} solves/s (factor ctas/sm {h.get_int('frontal_ctas_per_sm')}, bsub ctas/sm "
+              f"{h.get_int('frontal_bsub_ctas_per_sm')}, ring rows {h.get_int('frontal_ring_rows')})", flush=True)
+    for lanes in (16, 32):
         h.set_int("frontal_lanes", lanes)
         ms = timeit(lambda: h.fom_affine_raw(theta.data_ptr(), N, 0, 1, 1e-12, 20000, qoi=q.data_ptr(), stream=st))
         print(f"m=3 affine direct D1 lanes={lanes}: {N/ms*1e3:.3e} solves/s (ctas/sm {h.get_int('frontal_ctas_per_sm')} smem {h.get_int('frontal_smem_bytes')} ring rows {h.get_int('frontal_ring_rows')})", flush=True)

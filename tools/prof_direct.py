@@ -8,7 +8,7 @@ from bayesianinferencedl_b200.assembly import build_operators
 
 which = sys.argv[1:] or ["d1", "d2"]
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream
-for name, m, N in (("d1", 3, 296 * 32), ("d2", 26, 148), ("d2mid", 8, 148 * 7)):
+for name, m, N in (("d1", 3, 296 * 32), ("d1x6", 3, 296 * 32 * 6), ("d2", 26, 148), ("d2mid", 8, 148 * 7)):
     if name not in which:
         continue
     ops = build_operators(get_space(40, m=m))
