@@ -37,6 +37,7 @@ struct FrontalDev {
     long long nnzL;
     const unsigned char* fwd;      // forward stream (frontal_host.h: frontal_pack_streams)
     const unsigned char* bwd;      // backward stream
+    const unsigned char* fsub;     // D1: forward-substitution stream (adjoint right-hand sides)
 };
 
 struct FrontalIO {
@@ -52,6 +53,10 @@ struct FrontalIO {
     unsigned long long* counter;
     double* work;            // factor workspace
     const double* cv_global; // nodal operator: coefficient vectors [group][ncv][32] (D1) or [sample][ncv] (D2); null = affine
+    // D1 adjoint pass (PHASE_FSUB): right-hand side -B_obs^T (qoi - data); qoi_out is READ, cost_out = 0.5 |qoi - data|^2
+    const double* data;      // (1 | N, n_obs)
+    long long data_stride;   // 0: one shared observation vector
+    double* cost_out;        // (N) | null
 };
 
 __device__ __forceinline__ unsigned tri_u(unsigned s) { return s * (s + 1u) / 2u; }
@@ -93,10 +98,12 @@ struct StreamRing {
 #define FRONTAL_PHASE_BOTH 0
 #define FRONTAL_PHASE_FACTOR 1
 #define FRONTAL_PHASE_BSUB 2
+#define FRONTAL_PHASE_FSUB 3   // forward substitution L y = -B_obs^T (qoi - data) with the stored factor (adjoint solve)
 __host__ __device__ inline size_t frontal_lane_smem(int ntri, int nslots, int n_obs, int ncv_smem, int lr_rows, int lanes,
                                                     int ring_bytes, int phase) {
-    const int rows = (phase == FRONTAL_PHASE_BSUB ? 0 : ntri) + nslots + (phase == FRONTAL_PHASE_FACTOR ? 0 : n_obs) +
-                     (phase == FRONTAL_PHASE_BSUB ? 0 : ncv_smem) + (phase == FRONTAL_PHASE_FACTOR ? 0 : lr_rows);
+    const bool sub = phase == FRONTAL_PHASE_BSUB || phase == FRONTAL_PHASE_FSUB;
+    const int rows = (sub ? 0 : ntri) + nslots + (phase == FRONTAL_PHASE_FACTOR ? 0 : n_obs) + (sub ? 0 : ncv_smem) +
+                     (phase == FRONTAL_PHASE_FACTOR ? 0 : lr_rows);
     return (size_t)rows * lanes * sizeof(double) + (size_t)ring_bytes;
 }
 
@@ -134,10 +141,11 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
     const unsigned rb = 8u * (unsigned)LPG;            // bytes of one [row][lane] row
     // byte-addressed views of this lane's column of every [row][lane] array
     char* F = reinterpret_cast<char*>(fsm + lane);
-    char* yv = F + (size_t)(PHASE == FRONTAL_PHASE_BSUB ? 0 : P.ntri) * rb;
+    constexpr bool SUB = PHASE == FRONTAL_PHASE_BSUB || PHASE == FRONTAL_PHASE_FSUB;   // substitution-only launch
+    char* yv = F + (size_t)(SUB ? 0 : P.ntri) * rb;
     char* qacc = yv + (size_t)P.nslots * rb;
     char* cvs = qacc + (size_t)(PHASE == FRONTAL_PHASE_FACTOR ? 0 : io.n_obs) * rb;        // affine only
-    char* Lring = cvs + (size_t)((io.cv_global || PHASE == FRONTAL_PHASE_BSUB) ? 0 : P.ncv) * rb;
+    char* Lring = cvs + (size_t)((io.cv_global || SUB) ? 0 : P.ncv) * rb;
     StreamRing ring;
     ring.buf = reinterpret_cast<unsigned char*>(Lring - lane * 8 + (size_t)(PHASE == FRONTAL_PHASE_FACTOR ? 0 : P.lr_rows) * rb);
     ring.mask = (unsigned)P.ring_bytes - 1u;
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
         char* Lw = Lw0 + (PHASE == FRONTAL_PHASE_BOTH ? (size_t)blockIdx.x * wrows : (size_t)g * (wrows + 2)) * rb;
         bool bad = false;
         double yy = 0.0;
-        if (PHASE != FRONTAL_PHASE_BSUB) {
+        if (!SUB) {
         ring.reset(P.fwd);
         ring.fill(xlane, true);
         cp_async_commit();
@@ -290,11 +298,22 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
             __syncwarp();
             continue;
         }
-        } else {   // PHASE_BSUB: right-hand side slots start empty, y.y / flag come from the factor kernel
+        } else {   // substitution launch: right-hand side slots start empty, y.y / flag come from the factor kernel
             for (int e = 0; e < P.nslots; ++e) st(yv, rb * e, 0.0);
-            for (int o = 0; o < io.n_obs; ++o) st(qacc, rb * o, 0.0);
             yy = ld(Lw, (unsigned)(wrows * rb));
             bad = ld(Lw, (unsigned)((wrows + 1) * rb)) != 0.0;
+            if (PHASE == FRONTAL_PHASE_FSUB) {   // residual of the observables, kept where the other pass accumulates them
+                const double* d = io.data + (io.data_stride ? sc * io.data_stride : 0);
+                double cost = 0.0;
+                for (int o = 0; o < io.n_obs; ++o) {
+                    const double r = io.qoi_out[(size_t)sc * io.n_obs + o] - d[o];
+                    st(qacc, rb * o, r);
+                    cost = fma(r, r, cost);
+                }
+                if (io.cost_out && valid) io.cost_out[s] = 0.5 * cost;
+            } else {
+                for (int o = 0; o < io.n_obs; ++o) st(qacc, rb * o, 0.0);
+            }
         }
         // ---- backward substitution L^T w = y (yv doubles as the slot-indexed solution), observables on the fly.  The
         // factor blocks [1/L_jj, y_j, column] come back from HBM through a block ring in shared memory that cp.async fills
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
         // how many of the youngest copy groups may still be in flight when the record is consumed (kw).
         cp_async_wait<0>();
         __syncwarp();
-        ring.reset(P.bwd);
+        ring.reset(PHASE == FRONTAL_PHASE_FSUB ? P.fsub : P.bwd);
         ring.fill(xlane, true);
         cp_async_commit();
         cp_async_wait<0>();
@@ -318,7 +337,7 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
             }
         };
-        for (int j = n; j >= 0; --j) {   // j == n: prologue record (initial requests only)
+        for (int j = n; j >= 0; --j) {   // step n - 1 - j of the stream; j == n: prologue record (initial requests only)
             ring.fill(xlane, true);
             const unsigned char* rec = ring.buf + (ring.rd & ring.mask);
             const uint4 h0 = *reinterpret_cast<const uint4*>(rec);        // c | rb p | nobs | dof
@@ -332,6 +351,33 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
                 const char* blk = Lring + *reinterpret_cast<const unsigned*>(rec + 32);
                 const unsigned char* cols = rec + 48 + 16 * npf;
                 const double rinv = ld(blk, 0);
+                if (PHASE == FRONTAL_PHASE_FSUB) {
+                    // forward substitution with the adjoint right-hand side: y_j = (pending + rhs_j) / L_jj, then the
+                    // column pushes it down; y_j replaces the first solve's y_j in the factor block (HBM)
+                    const unsigned char* oval = cols + 4 * ((c + 3u) & ~3u);
+                    const unsigned char* orow = oval + ((8 * nobs + 15) & ~15u);
+                    double rhs = ld(yv, h0.y);
+                    st(yv, h0.y, 0.0);
+                    for (unsigned o = 0; o < nobs; ++o)
+                        rhs = fma(-*reinterpret_cast<const double*>(oval + 8 * o), ld(qacc, *reinterpret_cast<const unsigned*>(orow + 4 * o)), rhs);
+                    const double yj = rhs * rinv;
+                    st(Lw, (*reinterpret_cast<const unsigned*>(rec + 36) + 1u) * rb, yj);
+#pragma unroll
+                    for (int q = 0; q < CM / 4; ++q) {
+                        if (4 * q >= (int)c) break;
+                        const uint4 cc = *reinterpret_cast<const uint4*>(cols + 16 * q);
+                        const double l0 = ld(blk, rb * (2u + 4 * q)), w0 = ld(yv, cc.x);
+                        const double l1 = 4 * q + 1 < (int)c ? ld(blk, rb * (3u + 4 * q)) : 0.0, w1 = ld(yv, cc.y);
+                        const double l2 = 4 * q + 2 < (int)c ? ld(blk, rb * (4u + 4 * q)) : 0.0, w2 = ld(yv, cc.z);
+                        const double l3 = 4 * q + 3 < (int)c ? ld(blk, rb * (5u + 4 * q)) : 0.0, w3 = ld(yv, cc.w);
+                        st(yv, cc.x, fma(-l0, yj, w0));
+                        if (4 * q + 1 < (int)c) st(yv, cc.y, fma(-l1, yj, w1));
+                        if (4 * q + 2 < (int)c) st(yv, cc.z, fma(-l2, yj, w2));
+                        if (4 * q + 3 < (int)c) st(yv, cc.w, fma(-l3, yj, w3));
+                    }
+                    ring.rd += h1.x;
+                    continue;
+                }
                 double acc = ld(blk, rb);
 #pragma unroll
                 for (int q = 0; q < CM / 4; ++q) {
@@ -359,7 +405,7 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
             }
             ring.rd += h1.x;
         }
-        if (valid) {
+        if (valid && PHASE != FRONTAL_PHASE_FSUB) {
             if (io.qoi_out)
                 for (int o = 0; o < io.n_obs; ++o) io.qoi_out[(size_t)s * io.n_obs + o] = ld(qacc, rb * o);
             const bool nan = !(bw == bw);
@@ -696,6 +742,44 @@ __global__ void frontal_cellcoef_kernel(const double* __restrict__ k, long long 
             if (s < N && c < n_cells) cv[(size_t)s * ncv + 1 + c] = tile[sy][tx];
             if (s < N && blockIdx.x == 0 && tx == 0) cv[(size_t)s * ncv] = 1.0;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ gradient form
+// g[s][i] = assemble(k_hat_i * c'(k) * inner(grad w, grad v) * dx) (fom/forward_solve.py:313-314; exp(k): forward_solve_exp.py:299)
+//         = sum over the cells e around vertex i of  weight(e, i) * (w_e^T K_e v_e),
+// weight = 1/3 for the plain parametrisation (k_hat is a hat function, the rest is constant per cell), the k_hat-weighted
+// degree-4 quadrature of exp(k) otherwise (vertex_weight_exp, pcg_small.cuh).  One thread per (sample, vertex).
+__global__ void __launch_bounds__(256) frontal_gradform_kernel(const double* __restrict__ w, const double* __restrict__ v,
+                                                               const double* __restrict__ k, long long N, int n,
+                                                               const int* __restrict__ dptr, const int* __restrict__ dcell,
+                                                               const int* __restrict__ cells, const double* __restrict__ Ke,
+                                                               int coef_mode, double* __restrict__ g) {
+    const long long total = N * n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long s = idx / n;
+        const int i = (int)(idx - s * n);
+        const double* ws = w + s * n;
+        const double* vs = v + s * n;
+        const double* ks = k + s * n;
+        double acc = 0.0;
+        for (int j = dptr[i]; j < dptr[i + 1]; ++j) {
+            const int e = dcell[j];
+            const int ca = cells[3 * e], cb = cells[3 * e + 1], cc = cells[3 * e + 2];
+            const double* K = Ke + 9 * (size_t)e;
+            const double va = vs[ca], vb = vs[cb], vc = vs[cc];
+            const double t0 = fma(K[0], va, fma(K[1], vb, K[2] * vc));
+            const double t1 = fma(K[3], va, fma(K[4], vb, K[5] * vc));
+            const double t2 = fma(K[6], va, fma(K[7], vb, K[8] * vc));
+            const double se = fma(ws[ca], t0, fma(ws[cb], t1, ws[cc] * t2));
+            if (coef_mode == 0) {
+                acc = fma(se, 1.0 / 3.0, acc);
+            } else {
+                const int ob = ca == i ? cb : ca, oc = cc == i ? cb : cc;   // the two other vertices
+                acc = fma(se, vertex_weight_exp(ks[i], ks[ob], ks[oc]), acc);
+            }
+        }
+        g[idx] = acc;
     }
 }
 

@@ -351,11 +351,12 @@ inline void frontal_set_obs(FrontalProgram& P, int n_obs, const int32_t* obs_ptr
 //      256 term padded to 16
 //   backward record (prologue, then j = n-1 .. 0):
 //      +0 u32 c | +4 u32 256 p | +8 u32 nobs | +12 u32 dof | +16 u32 record bytes | +20 u32 npf | kw << 16 | +24 f64 rhs_j
-//      +32 u32 256 x first ring row of this pivot's factor block | +36 pad | +48 npf x {u32 256 ring row, u32 rows, u32
+//      +32 u32 256 x first ring row of this pivot's factor block | +36 u32 workspace row of that block | +48 npf x {u32 256 ring row, u32 rows, u32
 //      source row, pad} (blocks to request now) | u32 col[c4] | nobs x f64 weight padded to 16 | nobs x u32 256 row pad 16
 struct FrontalStreams {
     std::vector<unsigned char> fwd, bwd;     // D2
     std::vector<unsigned char> fwd1, bwd1;   // D1 (empty if the front is too wide for it)
+    std::vector<unsigned char> fsub1;        // D1: forward substitution with a new right-hand side (adjoint solves)
     int max_record = 0;   // largest record of any stream (bytes)
     int ring_bytes = 0;   // power of two
     int lr_rows = 0;      // rows of D1's factor-row ring the backward schedule was simulated for
@@ -474,7 +475,7 @@ inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax,
         b2.pad(16);
     }
     // ------------------------------------------------------------------ D1 forward / backward
-    ByteStream f1, b1;
+    ByteStream f1, b1, s1;
     const uint32_t rb = 8u * (uint32_t)lanes;   // bytes of one [row][lane] row: D1 keeps `lanes` samples per warp
     if (lane_ok) {
         for (int j = -1; j < n; ++j) {
@@ -506,79 +507,86 @@ inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax,
             for (int e = e0; e < e1; ++e) f1.put32(rb * (uint32_t)P.ent_term[e]);
             f1.pad(16);
         }
-        // factor-block ring of the backward substitution: simulate it so that every record says which blocks to request
-        // (up to dmax pivots ahead, as many as fit) and how many of the youngest copy groups may still be pending when it
-        // is consumed.  Step t handles pivot n-1-t; its block [1/L_jj, y_j, column] has c + 2 rows and is contiguous in
-        // the ring (the tail is skipped when it does not fit).  One group is committed per step (group 0 = prologue).
-        struct Blk {
-            int row, rows;
-        };
-        struct Req {
-            uint32_t row, rows, src;
-        };
-        std::vector<Blk> blk(n);
-        std::vector<std::vector<Req>> reqs(n + 1);   // reqs[0] = prologue, reqs[t + 1] = step t
-        std::vector<int> grp(n, -1);
-        std::vector<uint32_t> kw(n, 0);
-        auto rows_of = [&](int t) { const int jj = n - 1 - t; return P.col_ptr[jj + 1] - P.col_ptr[jj] + 2; };
-        auto src_of = [&](int t) { const int jj = n - 1 - t; return (uint32_t)(P.col_ptr[jj] + 2 * jj); };
-        int f = 0, head = 0, oldest = 0;   // frontier step, next free ring row, oldest live step
-        auto try_alloc = [&](int t, int g) -> bool {
-            const int rows = rows_of(t);
-            int cand = head + rows <= lr_rows ? head : 0;
-            for (int pass = 0; pass < 2; ++pass) {
-                bool clash = false;
-                for (int u = oldest; u < t; ++u)
-                    if (cand < blk[u].row + blk[u].rows && blk[u].row < cand + rows) clash = true;
-                if (!clash) {
-                    blk[t] = Blk{cand, rows};
-                    head = cand + rows;
-                    grp[t] = g;
-                    reqs[g].push_back(Req{(uint32_t)cand, (uint32_t)rows, src_of(t)});
-                    return true;
+        // Substitution streams (backward: pivots n-1 .. 0; forward: 0 .. n-1, for adjoint right-hand sides).  The factor
+        // blocks come back from HBM through a block ring in shared memory: simulate it so that every record says which
+        // blocks to request (up to dmax pivots ahead, as many as fit) and how many of the youngest copy groups may still
+        // be pending when it is consumed.  Step t handles pivot piv(t); its block [1/L_jj, y_j, column] has c + 2 rows and
+        // is contiguous in the ring (the tail is skipped when it does not fit).  One copy group is committed per step
+        // (group 0 = prologue).
+        auto pack_sub = [&](bool backward, ByteStream& out) {
+            struct Blk {
+                int row, rows;
+            };
+            struct Req {
+                uint32_t row, rows, src;
+            };
+            std::vector<Blk> blk(n);
+            std::vector<std::vector<Req>> reqs(n + 1);   // reqs[0] = prologue, reqs[t + 1] = step t
+            std::vector<int> grp(n, -1);
+            std::vector<uint32_t> kw(n, 0);
+            auto piv = [&](int t) { return backward ? n - 1 - t : t; };
+            auto rows_of = [&](int t) { const int jj = piv(t); return P.col_ptr[jj + 1] - P.col_ptr[jj] + 2; };
+            auto src_of = [&](int t) { const int jj = piv(t); return (uint32_t)(P.col_ptr[jj] + 2 * jj); };
+            int f = 0, head = 0, oldest = 0;   // frontier step, next free ring row, oldest live step
+            auto try_alloc = [&](int t, int g) -> bool {
+                const int rows = rows_of(t);
+                int cand = head + rows <= lr_rows ? head : 0;
+                for (int pass = 0; pass < 2; ++pass) {
+                    bool clash = false;
+                    for (int u = oldest; u < t; ++u)
+                        if (cand < blk[u].row + blk[u].rows && blk[u].row < cand + rows) clash = true;
+                    if (!clash) {
+                        blk[t] = Blk{cand, rows};
+                        head = cand + rows;
+                        grp[t] = g;
+                        reqs[g].push_back(Req{(uint32_t)cand, (uint32_t)rows, src_of(t)});
+                        return true;
+                    }
+                    if (cand == 0) break;
+                    cand = 0;   // also try the start of the ring
                 }
-                if (cand == 0) break;
-                cand = 0;   // also try the start of the ring
+                return false;
+            };
+            while (f < n && f < dmax && try_alloc(f, 0)) ++f;
+            for (int t = 0; t < n; ++t) {
+                oldest = t;
+                while (f < n && f <= t + dmax && try_alloc(f, t + 1)) ++f;
+                kw[t] = (uint32_t)(t + 1 - grp[t]);   // grp[t] >= 0: once the ring has drained a block of <= lr_rows rows fits
             }
-            return false;
+            for (int t = -1; t < n; ++t) {   // t == -1: prologue record (initial requests only)
+                out.begin();
+                const bool pro = t < 0;
+                const int j = pro ? 0 : piv(t);
+                const int c = pro ? 0 : P.col_ptr[j + 1] - P.col_ptr[j], c4 = (c + 3) & ~3;
+                const int o0 = pro ? 0 : P.obs_ptr[j], o1 = pro ? 0 : P.obs_ptr[j + 1];
+                const std::vector<Req>& rq = reqs[t + 1];
+                out.put32((uint32_t)c);
+                out.put32(pro ? 0u : rb * P.piv_slot[j]);
+                out.put32((uint32_t)(o1 - o0));
+                out.put32(pro ? 0u : (uint32_t)P.perm[j]);
+                out.put32(0u);
+                out.put32((uint32_t)rq.size() | ((pro ? 0u : kw[t]) << 16));
+                out.put64(pro ? 0.0 : P.rhs[j]);
+                out.put32(pro ? 0u : rb * (uint32_t)blk[t].row);
+                out.put32(pro ? 0u : src_of(t));   // workspace row of this pivot's block (the forward pass rewrites y_j)
+                out.put64(0.0);
+                for (const Req& r : rq) {
+                    out.put32(rb * r.row);
+                    out.put32(r.rows);
+                    out.put32(r.src);
+                    out.put32(0u);
+                }
+                for (int a = 0; a < c4; ++a) out.put32(a < c ? rb * P.col_slot[P.col_ptr[j] + a] : 0u);
+                for (int o = o0; o < o1; ++o) out.put64(P.obs_val[o]);
+                out.pad(16);
+                for (int o = o0; o < o1; ++o) out.put32(rb * (uint32_t)P.obs_row[o]);
+                out.pad(16);
+            }
         };
-        while (f < n && f < dmax && try_alloc(f, 0)) ++f;
-        for (int t = 0; t < n; ++t) {
-            oldest = t;
-            while (f < n && f <= t + dmax && try_alloc(f, t + 1)) ++f;
-            kw[t] = (uint32_t)(t + 1 - grp[t]);   // grp[t] >= 0: once the ring has drained a block of <= lr_rows rows fits
-        }
-        for (int j = n; j >= 0; --j) {
-            b1.begin();
-            const bool pro = j == n;
-            const int t = n - 1 - j;
-            const int c = pro ? 0 : P.col_ptr[j + 1] - P.col_ptr[j], c4 = (c + 3) & ~3;
-            const int o0 = pro ? 0 : P.obs_ptr[j], o1 = pro ? 0 : P.obs_ptr[j + 1];
-            const std::vector<Req>& rq = reqs[pro ? 0 : t + 1];
-            b1.put32((uint32_t)c);
-            b1.put32(pro ? 0u : rb * P.piv_slot[j]);
-            b1.put32((uint32_t)(o1 - o0));
-            b1.put32(pro ? 0u : (uint32_t)P.perm[j]);
-            b1.put32(0u);
-            b1.put32((uint32_t)rq.size() | ((pro ? 0u : kw[t]) << 16));
-            b1.put64(pro ? 0.0 : P.rhs[j]);
-            b1.put32(pro ? 0u : rb * (uint32_t)blk[t].row);
-            b1.put32(0u);
-            b1.put64(0.0);
-            for (const Req& r : rq) {
-                b1.put32(rb * r.row);
-                b1.put32(r.rows);
-                b1.put32(r.src);
-                b1.put32(0u);
-            }
-            for (int a = 0; a < c4; ++a) b1.put32(a < c ? rb * P.col_slot[P.col_ptr[j] + a] : 0u);
-            for (int o = o0; o < o1; ++o) b1.put64(P.obs_val[o]);
-            b1.pad(16);
-            for (int o = o0; o < o1; ++o) b1.put32(rb * (uint32_t)P.obs_row[o]);
-            b1.pad(16);
-        }
+        pack_sub(true, b1);
+        pack_sub(false, s1);
     }
-    S.max_record = std::max(std::max(max_len(f2), max_len(b2)), std::max(max_len(f1), max_len(b1)));
+    S.max_record = std::max(std::max(max_len(f2), max_len(b2)), std::max(max_len(f1), std::max(max_len(b1), max_len(s1))));
     // ring: the reader needs the current record complete while the loader runs up to one ring ahead in 512-byte chunks;
     // the records consumed under a wait that leaves dmax + 1 copy groups pending must be older than those groups
     int ring = 2048;
@@ -589,6 +597,7 @@ inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax,
     if (lane_ok) {
         S.fwd1 = frontal_detail::finish_stream(f1, 20, ring);
         S.bwd1 = frontal_detail::finish_stream(b1, 16, ring);
+        S.fsub1 = frontal_detail::finish_stream(s1, 16, ring);
     }
 }
 

@@ -134,12 +134,13 @@ struct FrontalSet {
     FrontalProgram host;
     FrontalStreams streams;
     int ncv = 0;
-    DevBuf<unsigned char> fwd, bwd, fwd1, bwd1;
+    DevBuf<unsigned char> fwd, bwd, fwd1, bwd1, fsub1;
     void release() {
         fwd.release();
         bwd.release();
         fwd1.release();
         bwd1.release();
+        fsub1.release();
         ok = false;
     }
     // (re)pack the instruction streams from the host program and copy them to the device.  D1 geometry is fixed here
@@ -162,6 +163,7 @@ struct FrontalSet {
         if (int e = fwd.upload(streams.fwd, st)) return e;
         if (int e = bwd.upload(streams.bwd, st)) return e;
         if (int e = fwd1.upload(streams.fwd1, st)) return e;
+        if (int e = fsub1.upload(streams.fsub1, st)) return e;
         return bwd1.upload(streams.bwd1, st);
     }
     FrontalDev dev(bool lane_kernel) const {
@@ -177,6 +179,7 @@ struct FrontalSet {
         d.nnzL = host.nnzL;
         d.fwd = lane_kernel ? fwd1.p : fwd.p;
         d.bwd = lane_kernel ? bwd1.p : bwd.p;
+        d.fsub = fsub1.p;
         return d;
     }
 };
@@ -257,7 +260,7 @@ struct tfin_ctx {
     FrontalSet fr_aff, fr_nod;
     std::vector<int32_t> h_obs_ptr, h_obs_idx;
     std::vector<double> h_obs_val;
-    DevBuf<double> d_fwork, d_fcv;
+    DevBuf<double> d_fwork, d_fcv, d_fw, d_fv;
     int fom_solver = 0;      // 0 auto (direct where the front fits on chip), 1 PCG, 2 direct
     int frontal_kernel = 0;  // 0 auto, 1 = D1 (sample per thread), 2 = D2 (sample per CTA)
     int frontal_threads = 0; // D2 threads per CTA, 0 = auto
@@ -347,6 +350,8 @@ extern "C" int tfin_destroy(tfin_handle_t h) {
     h->fr_nod.release();
     h->d_fwork.release();
     h->d_fcv.release();
+    h->d_fw.release();
+    h->d_fv.release();
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1014,7 +1019,8 @@ static const void* frontal_lane_fn(int cmax, int phase) {
     (cmax <= 8 ? (const void*)frontal_lane_kernel<8, PH> : cmax <= 16 ? (const void*)frontal_lane_kernel<16, PH>     \
      : cmax <= 24 ? (const void*)frontal_lane_kernel<24, PH> : (const void*)frontal_lane_kernel<32, PH>)
     return phase == FRONTAL_PHASE_FACTOR ? TFIN_LANE_FN(FRONTAL_PHASE_FACTOR)
-           : phase == FRONTAL_PHASE_BSUB ? TFIN_LANE_FN(FRONTAL_PHASE_BSUB) : TFIN_LANE_FN(FRONTAL_PHASE_BOTH);
+           : phase == FRONTAL_PHASE_BSUB ? TFIN_LANE_FN(FRONTAL_PHASE_BSUB)
+           : phase == FRONTAL_PHASE_FSUB ? TFIN_LANE_FN(FRONTAL_PHASE_FSUB) : TFIN_LANE_FN(FRONTAL_PHASE_BOTH);
 #undef TFIN_LANE_FN
 }
 
@@ -1191,6 +1197,84 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
     h->last_focc = g.occ;
     h->last_focc_b = g.split ? g.occ_b : 0;
     h->last_fsmem = g.smem;
+    h->last_path = 4;
+    return 0;
+}
+
+// Fin.gradient (fom/forward_solve.py:293-322) with the direct solver: factorise once, then three substitution passes with
+// the stored factor -- backward (w and the observables), forward with the adjoint right-hand side -B_obs^T (qoi - data),
+// backward again (adjoint state v) -- and the gradient form.  Device pointers; d_data (1 | N, n_obs).
+static int launch_frontal_gradient(tfin_ctx* h, const FrontalGeom& g, const double* d_k, int64_t N, const double* d_data,
+                                   int64_t data_stride, double* d_grad, double* d_cost, double* d_qoi, int* d_status,
+                                   cudaStream_t st) {
+    FrontalSet& fs = h->fr_nod;
+    const FrontalProgram& P = fs.host;
+    const FrontalDev dev = fs.dev(true);
+    const int lanes = fs.streams.lanes, n = P.n, nobs = h->n_obs;
+    const size_t per_sample_work = (size_t)P.nnzL + 2 * (size_t)n;
+    const int64_t wave = (int64_t)h->sm_count * g.occ * lanes;
+    const int64_t mem_waves = std::max<int64_t>(1, (((int64_t)6 << 30) / ((int64_t)(per_sample_work + 2) * 8)) / wave);
+    int64_t kk = g.occ_b / std::__gcd(g.occ, g.occ_b);
+    if (kk > mem_waves) kk = mem_waves;
+    const int64_t cvcap = std::max<int64_t>(32, ((int64_t)1 << 30) / ((int64_t)fs.ncv * 8) / 32 * 32);
+    const int64_t chunk = std::min<int64_t>(N, std::min<int64_t>(kk * wave, cvcap));
+    if (int e = h->d_fcv.reserve((size_t)((chunk + 31) / 32 * 32) * fs.ncv)) return e;
+    if (int e = h->d_fw.reserve((size_t)chunk * n)) return e;
+    if (int e = h->d_fv.reserve((size_t)chunk * n)) return e;
+    if (!d_qoi) {   // the adjoint right-hand side needs the observables
+        if (int e = h->d_qoi.reserve((size_t)N * nobs)) return e;
+        d_qoi = h->d_qoi.p;
+    }
+    const void* fn_f = frontal_lane_fn(P.cmax, FRONTAL_PHASE_FACTOR);
+    const void* fn_b = frontal_lane_fn(P.cmax, FRONTAL_PHASE_BSUB);
+    const void* fn_s = frontal_lane_fn(P.cmax, FRONTAL_PHASE_FSUB);
+    TFIN_CUDA(cudaFuncSetAttribute(fn_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_b));
+    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, N - s0);
+        const int64_t groups = (m + lanes - 1) / lanes;
+        if (int e = h->d_fwork.reserve((size_t)groups * (per_sample_work + 2) * lanes)) return e;
+        FrontalIO io{};
+        io.in = d_k + (size_t)s0 * n;
+        io.N = m;
+        io.in_stride = n;
+        io.n_obs = nobs;
+        io.counter = h->d_counter.p;
+        io.work = h->d_fwork.p;
+        io.cv_global = h->d_fcv.p;
+        io.data = d_data + (data_stride ? (size_t)s0 * data_stride : 0);
+        io.data_stride = data_stride;
+        const dim3 cgrid((unsigned)((h->n_cells + 31) / 32), (unsigned)((m + 31) / 32));
+        frontal_cellcoef_kernel<<<cgrid, dim3(32, 8), 0, st>>>(io.in, (long long)m, n, h->n_cells, h->d_cells.p, h->coef_mode, lanes,
+                                                              h->d_fcv.p);
+        const int grid_f = (int)std::min<int64_t>(groups, (int64_t)h->sm_count * g.occ);
+        const int grid_b = (int)std::min<int64_t>(groups, (int64_t)h->sm_count * g.occ_b);
+        void* args[] = {(void*)&dev, (void*)&io};
+        auto run = [&](const void* fn, int grid, size_t smem) -> int {
+            TFIN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, sizeof(unsigned long long), st));
+            TFIN_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(32), args, smem, st));
+            return 0;
+        };
+        if (int e = run(fn_f, grid_f, g.smem)) return e;                       // A = L L^T, y = L^-1 b
+        io.w_out = h->d_fw.p;
+        io.qoi_out = d_qoi + (size_t)s0 * nobs;
+        io.status_out = d_status ? d_status + s0 : nullptr;
+        if (int e = run(fn_b, grid_b, g.smem_b)) return e;                     // w = L^-T y, qoi = B_obs w
+        io.cost_out = d_cost ? d_cost + s0 : nullptr;
+        if (int e = run(fn_s, grid_b, g.smem_b)) return e;                     // y' = L^-1 (-B_obs^T (qoi - data))
+        io.w_out = h->d_fv.p;
+        io.qoi_out = nullptr;
+        io.status_out = nullptr;
+        io.cost_out = nullptr;
+        if (int e = run(fn_b, grid_b, g.smem_b)) return e;                     // v = L^-T y'
+        const int64_t total = m * (int64_t)n;
+        const int gb = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+        frontal_gradform_kernel<<<gb, 256, 0, st>>>(h->d_fw.p, h->d_fv.p, io.in, (long long)m, n, h->d_dptr.p, h->d_dcell.p,
+                                                    h->d_cells.p, h->d_Ke.p, h->coef_mode, d_grad + (size_t)s0 * n);
+        TFIN_CUDA(cudaGetLastError());
+        h->launches += 6;
+    }
+    h->last_solver = 2;
+    h->last_fkernel = 1;
     h->last_path = 4;
     return 0;
 }
@@ -1753,6 +1837,35 @@ static int fom_adjoint(tfin_handle_t h, int mode, const double* k, int64_t N, in
         return fail(TFIN_E_ARG, "tfin_fom_nodal_gradient: data must have 1 or N rows");
     if (N == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (mode == 1 && h->fom_solver != 1 && h->precision == 64 && h->small_ok) {
+        // direct solver: one factorisation serves the forward and the adjoint solve
+        const FrontalGeom g = frontal_geom(h, true, true);
+        if (g.kernel == 1 && g.split) {
+            Staged sg{h, st, mem == TFIN_MEM_HOST};
+            const int n = h->n, nobs = h->n_obs;
+            const double *d_k, *d_data;
+            if (int e = sg.in(k, (size_t)N * n, h->d_in, &d_k)) return e;
+            if (int e = sg.in(data, (size_t)data_rows * nobs, h->d_data, &d_data)) return e;
+            double *d_grad, *d_cost, *d_qoi;
+            int *d_iters, *d_status;
+            if (int e = sg.out_alloc(grad_out, (size_t)N * n, h->d_grad, &d_grad)) return e;
+            if (int e = sg.out_alloc(cost_out, (size_t)N, h->d_cost, &d_cost)) return e;
+            if (int e = sg.out_alloc(qoi_out, (size_t)N * nobs, h->d_qoi, &d_qoi)) return e;
+            if (int e = sg.out_alloc(iters_out, (size_t)N, h->d_iters, &d_iters)) return e;
+            if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
+            if (d_iters) TFIN_CUDA(cudaMemsetAsync(d_iters, 0, (size_t)N * sizeof(int), st));
+            if (int e = launch_frontal_gradient(h, g, d_k, N, d_data, data_rows == 1 ? 0 : nobs, d_grad, d_cost, d_qoi, d_status, st))
+                return e;
+            if (int e = sg.out_copy(grad_out, (size_t)N * n, d_grad)) return e;
+            if (int e = sg.out_copy(cost_out, (size_t)N, d_cost)) return e;
+            if (int e = sg.out_copy(qoi_out, (size_t)N * nobs, d_qoi)) return e;
+            if (int e = sg.out_copy(iters_out, (size_t)N, d_iters)) return e;
+            if (int e = sg.out_copy(status_out, (size_t)N, d_status)) return e;
+            if (sg.host) TFIN_CUDA(cudaStreamSynchronize(st));
+            return 0;
+        }
+        if (h->fom_solver == 2) return fail(TFIN_E_STATE, "fom_solver = 2 (direct) but the front is too wide for the direct gradient path");
+    }
     if (mode == 1 && mem == TFIN_MEM_HOST && h->host_chunk > 0 && N > h->host_chunk) {  // pipelined host path
         std::vector<double> hd(data, data + (size_t)data_rows * h->n_obs);
         if (int e = h->d_data.upload(hd, st)) return e;

@@ -981,3 +981,28 @@ def test_external_obs_selector(space_m2, oracle_m2, tmp_path, monkeypatch):
     monkeypatch.chdir(d)
     with pytest.raises(ValueError, match="do not address"):
         Fin(space_m2, external_obs=True)
+
+
+def test_gradient_direct_vs_pcg_and_oracle(space_m2, oracle_m2):
+    """Fin.gradient through the direct solver (one factorisation, three substitution passes, gradient-form kernel) against
+    the fused PCG adjoint kernel (fom_solver = 1) and the oracle; shared and per-sample observations; 70 samples."""
+    from bayesianinferencedl_b200 import Fin
+    fin = Fin(space_m2)
+    rng = np.random.default_rng(47)
+    k = np.exp(0.4 * rng.standard_normal((70, fin.dofs)))
+    data = rng.uniform(0.5, 2.0, (70, 9))
+    g, cost = fin.gradient(k, data, return_cost=True)
+    assert fin.handle.get_int("fom_solver") == 2 and fin.handle.get_int("frontal_kernel") == 1
+    g1 = fin.gradient(k, data[0])
+    fin.handle.set_int("fom_solver", 1)
+    try:
+        gp, costp = fin.gradient(k, data, return_cost=True)
+        assert fin.handle.get_int("fom_solver") == 1
+    finally:
+        fin.handle.set_int("fom_solver", 0)
+    assert np.max(np.abs(g - gp)) <= 1e-9 * np.max(np.abs(gp)) and relerr(cost, costp) <= 1e-10
+    for s in (0, 33, 69):
+        ref = np.asarray(oracle_m2.gradient(k[s], data[s])).ravel()
+        assert np.max(np.abs(g[s] - ref)) <= 1e-9 * np.max(np.abs(ref)), s
+    ref0 = np.asarray(oracle_m2.gradient(k[5], data[0])).ravel()
+    assert np.max(np.abs(g1[5] - ref0)) <= 1e-9 * np.max(np.abs(ref0))
