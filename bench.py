@@ -573,6 +573,8 @@ def run_b200(args):
             g_n = torch.empty((NG, n), dtype=f64, device=dev)
             c_n = torch.empty(NG, dtype=f64, device=dev)
 
+            hn.set_int("fom_solver", 0)
+
             def fom_grad():
                 rc = lib.tfin_fom_nodal_gradient(hn._h, k_dev.data_ptr(), NG, _cabi.MEM_DEVICE, TOL, 20000,
                                                  data_dev.data_ptr(), 1, g_n.data_ptr(), c_n.data_ptr(), None, None,
@@ -593,7 +595,9 @@ def run_b200(args):
             ms_gr, lgr = timed(rom_grad, K, Wm)
             nodal["gradients"] = {
                 "fom": {"value": world * NG / ((ms_g / K - flush_ms) * 1e-3), "unit": "gradients/s",
-                        "what": f"Fin.gradient batched: forward + adjoint PCG + gradient form in one kernel, {NG} fields",
+                        "what": f"Fin.gradient batched ({NG} fields): direct solver = one factorisation, backward / adjoint-forward / "
+                                f"backward substitution passes and the gradient-form kernel (PCG path: forward + adjoint PCG + "
+                                f"gradient form in one kernel)", "solver": "direct" if hn.get_int("fom_solver") == 2 else "pcg",
                         "gpu_launches": lg, "all_converged": bool((st_n[:NG] == 0).all().item())},
                 "rom": {"value": world * NG / ((ms_gr / K - flush_ms) * 1e-3), "unit": "gradients/s",
                         "what": f"AffineROMFin.grad_reduced batched (nodal in, nodal out), {NG} fields",
