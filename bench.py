@@ -349,7 +349,7 @@ def run_b200(args):
             hh.fom_affine_raw(th.data_ptr(), N, _cabi.IN_PARAMS, _cabi.MEM_DEVICE, TOL, maxit, qoi=q.data_ptr(),
                               iters=it.data_ptr() if it is not None else 0, status=st.data_ptr() if st is not None else 0,
                               stream=sp)
-            return gather_rows(q, N * world) if world > 1 else q
+            return gather_rows(q[:N], N * world) if world > 1 else q
         return run
 
     def frontal_info(hh):
