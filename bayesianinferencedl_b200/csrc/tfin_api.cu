@@ -2358,30 +2358,34 @@ extern "C" void tfin_frontal_free(void* prog) { delete static_cast<tfin_frontal_
 
 // ------------------------------------------------------------------------------------------------ micro-benchmarks
 // Shared-memory read bandwidth of the device (all SMs): the roofline denominator of the on-chip kernels (K1/K2 PCG, D1 /
-// D2 frontal solver), which never touch HBM in their inner loops.  Conflict-free 16-byte loads, 8 per iteration.
+// D2 frontal solver), which never touch HBM in their inner loops.  Conflict-free 8-byte loads, 16 per iteration.
 __global__ void __launch_bounds__(1024) smem_bandwidth_kernel(int iters, double* sink) {
-    extern __shared__ __align__(16) double2 sm_bw[];
+    extern __shared__ __align__(16) double sm_bw[];
     const int t = threadIdx.x, T = blockDim.x;
-    for (int i = t; i < 8 * T; i += T) sm_bw[i] = make_double2(1.0 + i, 2.0);
+    for (int i = t; i < 16 * T; i += T) sm_bw[i] = 1.0 + i;
     __syncthreads();
-    double2 acc = make_double2(0.0, 0.0);
+    // 8-byte loads, the access width of the solver kernels (a warp reads one 256-byte row = 2 wavefronts); 16 distinct rows
+    // per iteration through asm volatile, so that nothing is merged, hoisted or dropped
+    const unsigned base = smem_u32(sm_bw + t);
+    double acc0 = 0.0, acc1 = 0.0;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {   // 8 distinct rows per iteration; asm volatile: one LDS.128 each, nothing CSE'd or hoisted
-            double2 v;
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(&sm_bw[t + T * ((u + it) & 7)])));
-            acc.x += v.x;
-            acc.y += v.y;
+        for (int u = 0; u < 16; u += 2) {
+            double v0, v1;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(base + 8u * T * u));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(base + 8u * T * (u + 1)));
+            acc0 += v0;
+            acc1 += v1;
         }
     }
-    if (acc.x + acc.y == -1.0) sink[blockIdx.x] = acc.x;   // never true: keeps the loads alive
+    if (acc0 + acc1 == -1.0) sink[blockIdx.x] = acc0;   // never true: keeps the loads alive
 }
 
 extern "C" int tfin_smem_bandwidth(tfin_handle_t h, double* gbs_out) {
     CHECK_HANDLE(h);
     if (!gbs_out) return fail(TFIN_E_ARG, "tfin_smem_bandwidth: gbs_out is NULL");
     const int T = 1024, iters = 20000;
-    const size_t smem = (size_t)8 * T * sizeof(double2);
+    const size_t smem = (size_t)16 * T * sizeof(double);
     TFIN_CUDA(cudaFuncSetAttribute(smem_bandwidth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     TFIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smem_bandwidth_kernel, T, smem));
@@ -2400,6 +2404,6 @@ extern "C" int tfin_smem_bandwidth(tfin_handle_t h, double* gbs_out) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     h->launches += 2;
-    *gbs_out = (double)grid * T * iters * 8.0 * 16.0 / (ms * 1e-3) / 1e9;
+    *gbs_out = (double)grid * T * iters * 16.0 * 8.0 / (ms * 1e-3) / 1e9;
     return 0;
 }

@@ -766,7 +766,7 @@ def run_b200(args):
         roofline = {
             "bound": "smem", "achieved": smem_bytes * NF / (k_ms * 1e-3) / 1e9, "peak": smem_peak, "unit": "GB/s",
             "frac": smem_bytes * NF / (k_ms * 1e-3) / 1e9 / smem_peak,
-            "peak_source": "tfin_smem_bandwidth(): conflict-free 16-byte shared-memory loads on all SMs, measured in this run",
+            "peak_source": "tfin_smem_bandwidth(): conflict-free 8-byte shared-memory loads (the solver kernels' access width) on all SMs, measured in this run",
             "kernel": "frontal_lane_kernel (D1)", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": smem_bytes * NF,
             "traffic": (t1["dram_bytes"] / t1["launch_samples"] * NF) if t1 else None,
             "traffic_note": (f"ncu --set full capture of a {t1['launch_samples']}-sample launch ({t1['dram_bytes']:.4g} B of DRAM "
@@ -801,11 +801,12 @@ def run_b200(args):
         "metric": METRIC, "value": fom_rate, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": step_ms_f, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": dict(bench_config(args, world), **{
+        "config": bench_config(args, world),     # identical to the reference arm's for the same flags
+        "details": {
             "legs": "value = FOM (direct solver); fom_pcg = same workload, round-1 PCG kernel; rom = config[1] nine-param "
                     "ROM; fom_unstructured = reference-like mesh; fom_nodal = config[4]; fom_refined = config[3]",
             "solver": "direct" if fom_geo else "pcg", "frontal": fom_geo, "all_converged": ok_f and ok_r,
-            "l2": f"flushed between steps by a 256 MiB write ({flush_ms:.3f} ms, subtracted)"}),
+            "l2": f"flushed between steps by a 256 MiB write ({flush_ms:.3f} ms, subtracted)"},
         "roofline": roofline,
         "parity": parity,
         "gather_order_ok": gather_ok,

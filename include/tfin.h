@@ -256,8 +256,8 @@ int64_t tfin_frontal_array(void* prog, const char* name, void* dst, int64_t dst_
 void tfin_frontal_free(void* prog);
 
 /*
- * Micro-benchmark: aggregate shared-memory read bandwidth of the device in GB/s (conflict-free 16-byte loads on every
- * SM).  The on-chip kernels (PCG K1/K2, frontal D1/D2) keep their working set in shared memory, so this -- not HBM -- is
+ * Micro-benchmark: aggregate shared-memory read bandwidth of the device in GB/s (conflict-free 8-byte loads, the access width of
+ * the solver kernels, on every SM).  The on-chip kernels (PCG K1/K2, frontal D1/D2) keep their working set in shared memory, so this -- not HBM -- is
  * the roofline denominator bench.py reports them against.
  */
 int tfin_smem_bandwidth(tfin_handle_t h, double* gbs_out);
