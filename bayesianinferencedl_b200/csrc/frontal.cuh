@@ -543,13 +543,32 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
                     ypiv[rtid] = v * rinv;
                 }
             }
-            for (unsigned q = (unsigned)rtid; q < npos; q += NT) {   // threads from the top: one assembly position each
-                unsigned e = 0;
-                for (unsigned q2 = 0; q2 < q; ++q2) e += posv[2 * q2 + 1];
-                const unsigned cnt = posv[2 * q + 1];
-                double sum = 0.0;
-                for (unsigned k = 0; k < cnt; ++k, ++e) sum = fma(coefv[e], cv[termv[e]], sum);
-                F[posv[2 * q]] += sum;
+            // assembly of column j + 1 by ONE warp: lane e forms the product of entry e, lane q sums the entries of
+            // position q with shuffles (the serial per-position loop was the critical path of this phase)
+            if (warp == (nw >= 2 ? nw - 2 : 0)) {   // not the warp that forms the pivot row of the right-hand sides
+                const unsigned rl = 31u - (unsigned)lane;
+                if (nent <= 32u && npos <= 32u) {
+                    const double prod = rl < nent ? coefv[rl] * cv[termv[rl]] : 0.0;
+                    const unsigned pw = rl < npos ? posv[2 * rl + 1] : 0u;
+                    const unsigned cnt = pw & 255u, e0 = pw >> 8;
+                    unsigned cmax_w = cnt;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cmax_w = max(cmax_w, __shfl_xor_sync(0xffffffffu, cmax_w, o));
+                    double sum = 0.0;
+                    for (unsigned k = 0; k < cmax_w; ++k) {
+                        const double pk = __shfl_sync(0xffffffffu, prod, 31 - (int)min(e0 + k, 31u));
+                        if (k < cnt) sum += pk;
+                    }
+                    if (rl < npos) F[posv[2 * rl]] += sum;
+                } else {
+                    for (unsigned q = rl; q < npos; q += 32) {
+                        const unsigned pw = posv[2 * q + 1], cnt = pw & 255u;
+                        unsigned e = pw >> 8;
+                        double sum = 0.0;
+                        for (unsigned k = 0; k < cnt; ++k, ++e) sum = fma(coefv[e], cv[termv[e]], sum);
+                        F[posv[2 * q]] += sum;
+                    }
+                }
             }
             __syncthreads();
             // ---- U_j: rank-1 update of the front and of the right-hand sides

@@ -335,7 +335,7 @@ inline void frontal_set_obs(FrontalProgram& P, int n_obs, const int32_t* obs_ptr
 // D2 (sample per CTA) streams
 //   forward record (prologue j = -1 with c = 0, then j = 0 .. n-1), 16-byte aligned, little endian:
 //      +0 u32 c | +4 u32 pivot slot | +8 u32 npos | +12 u32 nent | +16 u32 nobs | +20 u32 record bytes | +24 f64 rhs_j
-//      +32 c x u16 slots (padded to 8) | npos x {u32 address, u32 entries} | nent x f64 coef | nent x u32 term (padded
+//      +32 c x u16 slots (padded to 8) | npos x {u32 address, u32 entries | first entry << 8} | nent x f64 coef | nent x u32 term (padded
 //      to 8) | nobs x f64 weight | nobs x u32 row (padded to 8) | pad to 16
 //      (npos / nent describe the assembly of column j + 1, which step j performs; nobs the observation weights of pivot j)
 //   backward record (a prologue with c = 0, then j = n-1 .. 0):
@@ -445,7 +445,7 @@ inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax,
         f2.pad(8);
         for (int q = q0; q < q1; ++q) {
             f2.put32(P.asm_addr[q]);
-            f2.put32((uint32_t)(P.asm_eptr[q + 1] - P.asm_eptr[q]));
+            f2.put32((uint32_t)(P.asm_eptr[q + 1] - P.asm_eptr[q]) | ((uint32_t)(P.asm_eptr[q] - e0) << 8));   // count | first entry << 8
         }
         for (int e = e0; e < e1; ++e) f2.put64(P.ent_coef[e]);
         for (int e = e0; e < e1; ++e) f2.put32((uint32_t)P.ent_term[e]);

@@ -2365,15 +2365,16 @@ __global__ void __launch_bounds__(1024) smem_bandwidth_kernel(int iters, double*
     for (int i = t; i < 16 * T; i += T) sm_bw[i] = 1.0 + i;
     __syncthreads();
     // 8-byte loads, the access width of the solver kernels (a warp reads one 256-byte row = 2 wavefronts); 16 distinct rows
-    // per iteration through asm volatile, so that nothing is merged, hoisted or dropped
+    // per iteration through ld.volatile (ptxas hoists / merges plain ld.shared even inside asm volatile: an earlier version
+    // executed a quarter of its loads, ncu smsp__inst_executed_op_shared_ld), so that nothing is merged, hoisted or dropped
     const unsigned base = smem_u32(sm_bw + t);
     double acc0 = 0.0, acc1 = 0.0;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 16; u += 2) {
             double v0, v1;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(base + 8u * T * u));
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(base + 8u * T * (u + 1)));
+            asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v0) : "r"(base + 8u * T * u));
+            asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v1) : "r"(base + 8u * T * (u + 1)));
             acc0 += v0;
             acc1 += v1;
         }
