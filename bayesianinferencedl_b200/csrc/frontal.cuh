@@ -57,6 +57,7 @@ struct FrontalIO {
     const double* data;      // (1 | N, n_obs)
     long long data_stride;   // 0: one shared observation vector
     double* cost_out;        // (N) | null
+    int unit_row;            // data == null: right-hand side -B_obs[unit_row, :]^T (one row of the sensitivity)
 };
 
 __device__ __forceinline__ unsigned tri_u(unsigned s) { return s * (s + 1u) / 2u; }
@@ -303,14 +304,18 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
             yy = ld(Lw, (unsigned)(wrows * rb));
             bad = ld(Lw, (unsigned)((wrows + 1) * rb)) != 0.0;
             if (PHASE == FRONTAL_PHASE_FSUB) {   // residual of the observables, kept where the other pass accumulates them
-                const double* d = io.data + (io.data_stride ? sc * io.data_stride : 0);
-                double cost = 0.0;
-                for (int o = 0; o < io.n_obs; ++o) {
-                    const double r = io.qoi_out[(size_t)sc * io.n_obs + o] - d[o];
-                    st(qacc, rb * o, r);
-                    cost = fma(r, r, cost);
+                if (io.data) {
+                    const double* d = io.data + (io.data_stride ? sc * io.data_stride : 0);
+                    double cost = 0.0;
+                    for (int o = 0; o < io.n_obs; ++o) {
+                        const double r = io.qoi_out[(size_t)sc * io.n_obs + o] - d[o];
+                        st(qacc, rb * o, r);
+                        cost = fma(r, r, cost);
+                    }
+                    if (io.cost_out && valid) io.cost_out[s] = 0.5 * cost;
+                } else {
+                    for (int o = 0; o < io.n_obs; ++o) st(qacc, rb * o, o == io.unit_row ? 1.0 : 0.0);
                 }
-                if (io.cost_out && valid) io.cost_out[s] = 0.5 * cost;
             } else {
                 for (int o = 0; o < io.n_obs; ++o) st(qacc, rb * o, 0.0);
             }
@@ -773,7 +778,7 @@ __global__ void __launch_bounds__(256) frontal_gradform_kernel(const double* __r
                                                                const double* __restrict__ k, long long N, int n,
                                                                const int* __restrict__ dptr, const int* __restrict__ dcell,
                                                                const int* __restrict__ cells, const double* __restrict__ Ke,
-                                                               int coef_mode, double* __restrict__ g) {
+                                                               int coef_mode, double* __restrict__ g, long long g_stride) {
     const long long total = N * n;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long s = idx / n;
@@ -798,7 +803,7 @@ __global__ void __launch_bounds__(256) frontal_gradform_kernel(const double* __r
                 acc = fma(se, vertex_weight_exp(ks[i], ks[ob], ks[oc]), acc);
             }
         }
-        g[idx] = acc;
+        g[s * g_stride + i] = acc;   // g_stride = n (gradient) or n_obs n (one row of the Jacobian)
     }
 }
 

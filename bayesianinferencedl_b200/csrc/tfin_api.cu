@@ -1204,9 +1204,10 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
 // Fin.gradient (fom/forward_solve.py:293-322) with the direct solver: factorise once, then three substitution passes with
 // the stored factor -- backward (w and the observables), forward with the adjoint right-hand side -B_obs^T (qoi - data),
 // backward again (adjoint state v) -- and the gradient form.  Device pointers; d_data (1 | N, n_obs).
+// sens != 0: Fin.sensitivity (:324-342) instead -- n_obs adjoint solves A v_o = -B_obs[o, :]^T, d_grad is the (N, n_obs, n) Jacobian.
 static int launch_frontal_gradient(tfin_ctx* h, const FrontalGeom& g, const double* d_k, int64_t N, const double* d_data,
                                    int64_t data_stride, double* d_grad, double* d_cost, double* d_qoi, int* d_status,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, bool sens = false) {
     FrontalSet& fs = h->fr_nod;
     const FrontalProgram& P = fs.host;
     const FrontalDev dev = fs.dev(true);
@@ -1259,19 +1260,30 @@ static int launch_frontal_gradient(tfin_ctx* h, const FrontalGeom& g, const doub
         io.qoi_out = d_qoi + (size_t)s0 * nobs;
         io.status_out = d_status ? d_status + s0 : nullptr;
         if (int e = run(fn_b, grid_b, g.smem_b)) return e;                     // w = L^-T y, qoi = B_obs w
-        io.cost_out = d_cost ? d_cost + s0 : nullptr;
-        if (int e = run(fn_s, grid_b, g.smem_b)) return e;                     // y' = L^-1 (-B_obs^T (qoi - data))
-        io.w_out = h->d_fv.p;
-        io.qoi_out = nullptr;
-        io.status_out = nullptr;
-        io.cost_out = nullptr;
-        if (int e = run(fn_b, grid_b, g.smem_b)) return e;                     // v = L^-T y'
         const int64_t total = m * (int64_t)n;
         const int gb = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
-        frontal_gradform_kernel<<<gb, 256, 0, st>>>(h->d_fw.p, h->d_fv.p, io.in, (long long)m, n, h->d_dptr.p, h->d_dcell.p,
-                                                    h->d_cells.p, h->d_Ke.p, h->coef_mode, d_grad + (size_t)s0 * n);
+        double* const qoi_chunk = io.qoi_out;
+        const int n_adj = sens ? nobs : 1;
+        for (int o = 0; o < n_adj; ++o) {
+            io.w_out = nullptr;
+            io.qoi_out = qoi_chunk;             // read by the gradient's right-hand side
+            io.status_out = nullptr;
+            io.data = sens ? nullptr : d_data + (data_stride ? (size_t)s0 * data_stride : 0);
+            io.unit_row = o;
+            io.cost_out = (!sens && d_cost) ? d_cost + s0 : nullptr;
+            if (int e = run(fn_s, grid_b, g.smem_b)) return e;                 // y' = L^-1 (-B_obs^T (qoi - data))  |  L^-1 (-B_obs[o]^T)
+            io.w_out = h->d_fv.p;
+            io.qoi_out = nullptr;
+            io.cost_out = nullptr;
+            if (int e = run(fn_b, grid_b, g.smem_b)) return e;                 // v = L^-T y'
+            double* gout = sens ? d_grad + ((size_t)s0 * nobs + o) * n : d_grad + (size_t)s0 * n;
+            frontal_gradform_kernel<<<gb, 256, 0, st>>>(h->d_fw.p, h->d_fv.p, io.in, (long long)m, n, h->d_dptr.p, h->d_dcell.p,
+                                                        h->d_cells.p, h->d_Ke.p, h->coef_mode, gout,
+                                                        sens ? (long long)nobs * n : (long long)n);
+            h->launches += 3;
+        }
         TFIN_CUDA(cudaGetLastError());
-        h->launches += 6;
+        h->launches += 3;
     }
     h->last_solver = 2;
     h->last_fkernel = 1;
@@ -1837,26 +1849,29 @@ static int fom_adjoint(tfin_handle_t h, int mode, const double* k, int64_t N, in
         return fail(TFIN_E_ARG, "tfin_fom_nodal_gradient: data must have 1 or N rows");
     if (N == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    if (mode == 1 && h->fom_solver != 1 && h->precision == 64 && h->small_ok) {
+    if ((mode == 1 || mode == 2) && h->fom_solver != 1 && h->precision == 64 && h->small_ok) {
         // direct solver: one factorisation serves the forward and the adjoint solve
         const FrontalGeom g = frontal_geom(h, true, true);
         if (g.kernel == 1 && g.split) {
             Staged sg{h, st, mem == TFIN_MEM_HOST};
             const int n = h->n, nobs = h->n_obs;
-            const double *d_k, *d_data;
+            const double *d_k, *d_data = nullptr;
+            const size_t grad_rows = mode == 2 ? (size_t)N * nobs : (size_t)N;
             if (int e = sg.in(k, (size_t)N * n, h->d_in, &d_k)) return e;
-            if (int e = sg.in(data, (size_t)data_rows * nobs, h->d_data, &d_data)) return e;
+            if (mode == 1)
+                if (int e = sg.in(data, (size_t)data_rows * nobs, h->d_data, &d_data)) return e;
             double *d_grad, *d_cost, *d_qoi;
             int *d_iters, *d_status;
-            if (int e = sg.out_alloc(grad_out, (size_t)N * n, h->d_grad, &d_grad)) return e;
+            if (int e = sg.out_alloc(grad_out, grad_rows * n, h->d_grad, &d_grad)) return e;
             if (int e = sg.out_alloc(cost_out, (size_t)N, h->d_cost, &d_cost)) return e;
             if (int e = sg.out_alloc(qoi_out, (size_t)N * nobs, h->d_qoi, &d_qoi)) return e;
             if (int e = sg.out_alloc(iters_out, (size_t)N, h->d_iters, &d_iters)) return e;
             if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
             if (d_iters) TFIN_CUDA(cudaMemsetAsync(d_iters, 0, (size_t)N * sizeof(int), st));
-            if (int e = launch_frontal_gradient(h, g, d_k, N, d_data, data_rows == 1 ? 0 : nobs, d_grad, d_cost, d_qoi, d_status, st))
+            if (int e = launch_frontal_gradient(h, g, d_k, N, d_data, data_rows == 1 ? 0 : nobs, d_grad, d_cost, d_qoi, d_status, st,
+                                                mode == 2))
                 return e;
-            if (int e = sg.out_copy(grad_out, (size_t)N * n, d_grad)) return e;
+            if (int e = sg.out_copy(grad_out, grad_rows * n, d_grad)) return e;
             if (int e = sg.out_copy(cost_out, (size_t)N, d_cost)) return e;
             if (int e = sg.out_copy(qoi_out, (size_t)N * nobs, d_qoi)) return e;
             if (int e = sg.out_copy(iters_out, (size_t)N, d_iters)) return e;

@@ -170,7 +170,10 @@ int tfin_rom_gradient(tfin_handle_t h, const double* in, int64_t N, int32_t in_k
  * Batched adjoint gradient of J_s = 0.5 ||B_obs w_s - data_s||^2 with respect to the nodal conductivity:
  * = Fin.gradient(k, data) (fom/forward_solve.py:293-322) for N samples.  The forward solve, the adjoint solve
  * A v = -B_obs^T (B_obs w - data) (the reference's dense np.linalg.solve, :310) and the gradient form
- * assemble(k_hat * inner(grad w, grad v) * dx) (:313-314) run in one kernel on the same on-chip operator.
+ * assemble(k_hat * inner(grad w, grad v) * dx) (:313-314).  Default (fom_solver 0 / 2, fronts of <= 32 nodes): ONE sparse
+ * direct factorisation serves both solves -- backward substitution (w, observables), forward substitution with the adjoint
+ * right-hand side, backward substitution (v), gradient-form kernel; tol / maxit are ignored and iters_out is 0.  Otherwise
+ * (fom_solver = 1, wider fronts): forward PCG, adjoint PCG and the gradient form in one kernel on the same on-chip operator.
  *   data: (data_rows, n_obs) with data_rows == 1 (one observation vector for all samples) or N
  *   grad_out (N, n), cost_out (N) | NULL = J_s, qoi_out (N, n_obs) | NULL, iters_out (forward solve) | NULL,
  *   status_out | NULL (worst of the forward and adjoint solves)
@@ -181,7 +184,8 @@ int tfin_fom_nodal_gradient(tfin_handle_t h, const double* k, int64_t N, int32_t
 
 /*
  * Batched Jacobian of the observables with respect to the nodal conductivity:
- * = Fin.sensitivity(k) (fom/forward_solve.py:324-342): n_obs adjoint solves A v_o = -B_obs[o,:]^T per sample.
+ * = Fin.sensitivity(k) (fom/forward_solve.py:324-342): n_obs adjoint solves A v_o = -B_obs[o,:]^T per sample (with the direct
+ * solver: n_obs forward + backward substitution passes on the one factor).
  *   jac_out (N, n_obs, n)
  */
 int tfin_fom_nodal_sensitivity(tfin_handle_t h, const double* k, int64_t N, int32_t mem, double tol, int32_t maxit,

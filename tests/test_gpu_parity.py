@@ -1005,3 +1005,14 @@ def test_gradient_direct_vs_pcg_and_oracle(space_m2, oracle_m2):
         assert np.max(np.abs(g[s] - ref)) <= 1e-9 * np.max(np.abs(ref)), s
     ref0 = np.asarray(oracle_m2.gradient(k[5], data[0])).ravel()
     assert np.max(np.abs(g1[5] - ref0)) <= 1e-9 * np.max(np.abs(ref0))
+    # Fin.sensitivity (the full Jacobian, n_obs adjoint solves on the same factor): direct vs PCG vs oracle
+    J = fin.sensitivity(k[:9])
+    assert fin.handle.get_int("fom_solver") == 2 and J.shape == (9, 9, fin.dofs)
+    fin.handle.set_int("fom_solver", 1)
+    try:
+        Jp = fin.sensitivity(k[:9])
+    finally:
+        fin.handle.set_int("fom_solver", 0)
+    assert np.max(np.abs(J - Jp)) <= 1e-9 * np.max(np.abs(Jp))
+    Jref = np.asarray(oracle_m2.sensitivity(k[4]))
+    assert np.max(np.abs(J[4] - Jref)) <= 1e-9 * np.max(np.abs(Jref))
