@@ -59,6 +59,8 @@ SIGNATURES = {
     "tfin_subfin_avg": (C.c_int, [_handle, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "tfin_frontal_analyze": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tfin_frontal_analyze_ex": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
     "tfin_frontal_array": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "tfin_frontal_free": (None, [C.c_void_p]),
     "tfin_smem_bandwidth": (C.c_int, [_handle, C.POINTER(C.c_double)]),

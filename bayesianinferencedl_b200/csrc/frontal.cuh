@@ -33,7 +33,8 @@ struct FrontalDev {
     int ntri;                      // nslots (nslots + 1) / 2
     int ring_bytes;                // power of two, see frontal_pack_streams
     int lr_rows;                   // D1: rows of the factor-row ring of the backward substitution
-    int lanes;                     // D1: samples per warp (32, 16 or 8): fewer lanes = narrower rows = more resident warps
+    int lanes;                     // D1: samples per warp (<= 32): fewer lanes = narrower rows = more resident warps
+    int ring_fwd1;                 // D1 factor kernel: its own (smaller) instruction ring, bytes (power of two)
     long long nnzL;
     const unsigned char* fwd;      // forward stream (frontal_host.h: frontal_pack_streams)
     const unsigned char* bwd;      // backward stream
@@ -105,7 +106,7 @@ __host__ __device__ inline size_t frontal_lane_smem(int ntri, int nslots, int n_
     const bool sub = phase == FRONTAL_PHASE_BSUB || phase == FRONTAL_PHASE_FSUB;
     const int rows = (sub ? 0 : ntri) + nslots + (phase == FRONTAL_PHASE_FACTOR ? 0 : n_obs) + (sub ? 0 : ncv_smem) +
                      (phase == FRONTAL_PHASE_FACTOR ? 0 : lr_rows);
-    return (size_t)rows * lanes * sizeof(double) + (size_t)ring_bytes;
+    return (((size_t)rows * lanes * sizeof(double) + 15) & ~(size_t)15) + (size_t)ring_bytes;   // ring_bytes: of this phase
 }
 
 #define FRONTAL_DMAX 7   // the backward substitution prefetches the factor rows of up to DMAX pivots ahead
@@ -134,11 +135,14 @@ template <int CM, int PHASE>
 __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalIO io) {
     static_assert(CM % 4 == 0, "columns are read four entries at a time");
     extern __shared__ __align__(16) double fsm[];
-    // A warp carries LPG = P.lanes samples (32, 16 or 8); with fewer than 32 the upper lanes shadow the lower ones (same
-    // addresses, same values), which costs nothing but lets 2-4 x more warps share the SM's shared memory: the kernel is
-    // bound by instruction latency, not by lanes.
+    // A warp carries LPG = P.lanes <= 32 samples; with fewer than 32 the upper lanes shadow the lower ones (same
+    // addresses, same values), which costs nothing but lets more warps share the SM's shared memory: the kernel is bound
+    // by instruction latency, i.e. by samples in flight = resident warps x LPG, and shared memory bounds that product
+    // (n = 1597: 3 warps x 25 samples instead of 2 x 32).
+    // Shadow lanes all take the LAST sample's column: same address as lane LPG - 1, i.e. a broadcast -- any other choice
+    // (say xlane % LPG) puts a second, different word on banks the real lanes use and costs a third wavefront per access.
     const int LPG = P.lanes, xlane = threadIdx.x;
-    const int lane = xlane & (LPG - 1);
+    const int lane = xlane < LPG ? xlane : LPG - 1;
     const unsigned rb = 8u * (unsigned)LPG;            // bytes of one [row][lane] row
     // byte-addressed views of this lane's column of every [row][lane] array
     char* F = reinterpret_cast<char*>(fsm + lane);
@@ -148,8 +152,12 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
     char* cvs = qacc + (size_t)(PHASE == FRONTAL_PHASE_FACTOR ? 0 : io.n_obs) * rb;        // affine only
     char* Lring = cvs + (size_t)((io.cv_global || SUB) ? 0 : P.ncv) * rb;
     StreamRing ring;
-    ring.buf = reinterpret_cast<unsigned char*>(Lring - lane * 8 + (size_t)(PHASE == FRONTAL_PHASE_FACTOR ? 0 : P.lr_rows) * rb);
-    ring.mask = (unsigned)P.ring_bytes - 1u;
+    {
+        const size_t off = (size_t)((Lring - lane * 8) - reinterpret_cast<char*>(fsm)) +
+                           (size_t)(PHASE == FRONTAL_PHASE_FACTOR ? 0 : P.lr_rows) * rb;
+        ring.buf = reinterpret_cast<unsigned char*>(fsm) + ((off + 15) & ~(size_t)15);
+    }
+    ring.mask = (unsigned)(PHASE == FRONTAL_PHASE_FACTOR ? P.ring_fwd1 : P.ring_bytes) - 1u;
     const unsigned full = 0xffffffffu;
     const long long n_groups = (io.N + LPG - 1) / LPG;
     const int n = P.n;

@@ -164,7 +164,7 @@ inline std::vector<int> frontal_postorder(int n, const std::vector<int>& parent,
 // success, else the reason the mesh is not supported.
 inline std::string frontal_build(int n, const int32_t* rp, const int32_t* ci, const double* rhs,
                                  const std::function<void(int, std::vector<FrontalTermEntry>&)>& entry_terms,
-                                 FrontalProgram* out) {
+                                 FrontalProgram* out, bool lookahead = true) {
     std::vector<int> roots;
     for (int i = 0; i < n; ++i)
         if (rhs[i] != 0.0) roots.push_back(i);
@@ -244,8 +244,16 @@ inline std::string frontal_build(int n, const int32_t* rp, const int32_t* ci, co
         ensure_column(0, -1);
         for (int j = 0; j < n; ++j) {
             for (int q = c.sptr[j]; q < c.sptr[j + 1]; ++q) ensure(c.sidx[q], j);
-            if (j + 1 < n) ensure_column(j + 1, j);
-            free_slots.push(c.slot[j]);
+            // lookahead: column j + 1 gets its slots while pivot j still holds its own (the sample-per-CTA kernel assembles
+            // it concurrently with the update of step j).  Without: the pivot's slot is recycled first -- legal for a
+            // kernel that assembles column j + 1 after it has gathered (and zeroed) column j, and one slot smaller.
+            if (lookahead) {
+                if (j + 1 < n) ensure_column(j + 1, j);
+                free_slots.push(c.slot[j]);
+            } else {
+                free_slots.push(c.slot[j]);
+                if (j + 1 < n) ensure_column(j + 1, j);
+            }
         }
         c.nslots = top;
     };
@@ -359,6 +367,7 @@ struct FrontalStreams {
     std::vector<unsigned char> fsub1;        // D1: forward substitution with a new right-hand side (adjoint solves)
     int max_record = 0;   // largest record of any stream (bytes)
     int ring_bytes = 0;   // power of two
+    int ring_fwd1 = 0;    // D1 factor kernel alone: ring of its forward stream (power of two <= ring_bytes)
     int lr_rows = 0;      // rows of D1's factor-row ring the backward schedule was simulated for
     int lanes = 32;       // samples per warp the D1 streams were scaled for (row = 8 * lanes bytes)
 };
@@ -389,7 +398,7 @@ struct ByteStream {
 };
 // Re-lay the records so that none straddles a multiple of `ring` (pad the previous record, whose length field sits at
 // `len_off`), then append the zero padding the ring loader may prefetch beyond the last record.
-inline std::vector<unsigned char> finish_stream(const ByteStream& in, size_t len_off, int ring) {
+inline std::vector<unsigned char> finish_stream(const ByteStream& in, size_t len_off, int ring, int tail = 0) {
     std::vector<unsigned char> out;
     size_t prev = (size_t)-1;
     for (size_t r = 0; r < in.starts.size(); ++r) {
@@ -406,16 +415,19 @@ inline std::vector<unsigned char> finish_stream(const ByteStream& in, size_t len
         uint32_t l32 = (uint32_t)len;
         for (int k = 0; k < 4; ++k) out[prev + len_off + k] = (unsigned char)(l32 >> (8 * k));
     }
-    out.resize((out.size() + 511) / 512 * 512 + (size_t)ring + 512, 0);
+    out.resize((out.size() + 511) / 512 * 512 + (size_t)std::max(ring, tail) + 512, 0);
     return out;
 }
 }  // namespace frontal_detail
 
-inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax, int lanes, FrontalStreams* out) {
+// P1: the program the sample-per-thread streams are packed from (built without lookahead: fewer slots), default P.
+inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax, int lanes, FrontalStreams* out,
+                                 const FrontalProgram* P1 = nullptr) {
     using frontal_detail::ByteStream;
     FrontalStreams& S = *out;
     S = FrontalStreams();
     const int n = P.n;
+    const FrontalProgram& PD2 = P;
     const bool lane_ok = lr_rows >= P.cmax + 2 && P.cmax <= 32;
     S.lr_rows = lane_ok ? lr_rows : 0;
     S.lanes = lanes;
@@ -478,6 +490,7 @@ inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax,
     ByteStream f1, b1, s1;
     const uint32_t rb = 8u * (uint32_t)lanes;   // bytes of one [row][lane] row: D1 keeps `lanes` samples per warp
     if (lane_ok) {
+        const FrontalProgram& P = P1 ? *P1 : PD2;   // shadows the D2 program for the rest of this block
         for (int j = -1; j < n; ++j) {
             f1.begin();
             const int c = j >= 0 ? P.col_ptr[j + 1] - P.col_ptr[j] : 0, c4 = (c + 3) & ~3;
@@ -595,7 +608,12 @@ inline void frontal_pack_streams(const FrontalProgram& P, int lr_rows, int dmax,
     S.fwd = frontal_detail::finish_stream(f2, 20, ring);
     S.bwd = frontal_detail::finish_stream(b2, 16, ring);
     if (lane_ok) {
-        S.fwd1 = frontal_detail::finish_stream(f1, 20, ring);
+        // the factor kernel of the split launch keeps nothing but the front and this ring in shared memory: size its ring
+        // for its own records (a multiple-of-ring_fwd1 boundary is never straddled, so the larger ring reads it as well)
+        int rf = 2048;
+        while (rf < 3 * max_len(f1) + 1024) rf *= 2;
+        S.ring_fwd1 = std::min(rf, ring);
+        S.fwd1 = frontal_detail::finish_stream(f1, 20, S.ring_fwd1, ring);
         S.bwd1 = frontal_detail::finish_stream(b1, 16, ring);
         S.fsub1 = frontal_detail::finish_stream(s1, 16, ring);
     }

@@ -127,11 +127,16 @@ static void align_ell_slots(int n, int W, const int32_t* col_idx, std::vector<st
     }
 }
 
+#define FRONTAL_WORK_BYTES ((long long)6 << 30)   // HBM workspace of the split launch: factor blocks of one chunk
+static int g_sm_count = 148;          // set by tfin_create
+static int g_frontal_ring_rows = 0;   // tuning knob "frontal_ring_rows": rows of D1's factor-block ring, 0 = auto
+
 // Device copy of one frontal program (frontal_host.h) -- the sparse-direct solver D1 / D2.
 struct FrontalSet {
     bool ok = false;
     std::string why = "no operator";
-    FrontalProgram host;
+    FrontalProgram host;     // D2 (slots of column j + 1 allocated one step early)
+    FrontalProgram host1;    // D1 (no lookahead: one slot fewer, i.e. ~8 % less shared memory per sample at n = 1597)
     FrontalStreams streams;
     int ncv = 0;
     DevBuf<unsigned char> fwd, bwd, fwd1, bwd1, fsub1;
@@ -146,20 +151,52 @@ struct FrontalSet {
     // (re)pack the instruction streams from the host program and copy them to the device.  D1 geometry is fixed here
     // (n_obs and the affine coefficient rows are known): samples per warp `lanes` (rows of 8 * lanes bytes) and the rows of
     // the factor-block ring, which gets the shared memory that the resident warps leave free.
-    int upload(cudaStream_t st, int n_obs, int smem_optin, int want_lanes) {
-        const int ntri = host.nslots * (host.nslots + 1) / 2;
-        const int base_rows = ntri + host.nslots + n_obs + (ncv <= TFIN_MAX_TERMS ? ncv : 0);
-        // Throughput of the (latency-bound) kernel is samples in flight / pass latency, and samples in flight are bounded
-        // by shared memory whatever the row width, so 32 lanes is the default; 16 / 8 trade lanes for resident warps.
-        int lanes = (want_lanes == 8 || want_lanes == 16) ? want_lanes : 32;
-        const long long row = 8LL * lanes;
+    int upload(cudaStream_t st, int n_obs, int smem_optin, int smem_per_sm, int want_lanes) {
+        const int ntri = host1.nslots * (host1.nslots + 1) / 2;
+        const int base_rows = ntri + host1.nslots + n_obs + (ncv <= TFIN_MAX_TERMS ? ncv : 0);
+        // Throughput of the (latency-bound) kernel is samples in flight / pass latency, and samples in flight = resident
+        // warps x samples per warp are bounded by the SM's shared memory (228 KiB, 1 KiB reserved per CTA): pick the
+        // (warps, lanes) pair with the largest product, fewer warps on a tie.  n = 1597: 3 x 25 = 75 instead of 2 x 32.
         // factor-block ring of the substitution kernel (split launch: no front in its shared memory): ~4 blocks ahead
         long long lr = std::max<long long>(host.cmax + 2, std::min<long long>(64, 4LL * (host.cmax + 2)));
-        {
-            const long long smem_f = (base_rows - n_obs) * row + 8192;   // factor kernel: front + rhs + coefficients + ring
-            if (smem_f + 1024 > (long long)smem_optin + 1024 || host.cmax > 32) lr = 0;   // D1 cannot serve this front
+        if (g_frontal_ring_rows > 0) lr = std::max<long long>(host.cmax + 2, g_frontal_ring_rows);
+        frontal_pack_streams(host, (int)lr, FRONTAL_DMAX, 32, &streams, &host1);
+        const long long rows_f = base_rows - n_obs;   // factor kernel: front + rhs + coefficients (+ its instruction ring)
+        int lanes = 0, warps_f = 1;
+        if (host.cmax <= 32) {
+            if (want_lanes >= 4 && want_lanes <= 32) {
+                if (rows_f * 8 * want_lanes + 16 + streams.ring_fwd1 <= (long long)smem_optin) lanes = want_lanes;
+                if (lanes) warps_f = (int)std::max<long long>(1, smem_per_sm / (rows_f * 8 * lanes + 16 + streams.ring_fwd1 + 1024));
+            } else {
+                long long best = 0;
+                for (int w = 1; w <= 6; ++w) {
+                    const long long per_cta = std::min<long long>(smem_optin, smem_per_sm / w - 1024);
+                    const long long l = std::min<long long>(32, (per_cta - streams.ring_fwd1 - 16) / (rows_f * 8));
+                    if (l >= 8 && w * l > best) {
+                        best = w * l;
+                        lanes = (int)l;
+                        warps_f = w;
+                    }
+                }
+            }
         }
-        frontal_pack_streams(host, (int)lr, FRONTAL_DMAX, lanes, &streams);
+        if (lanes == 0) lr = 0;   // D1 cannot serve this front
+        if (lanes && g_frontal_ring_rows == 0) {
+            // One pass of the substitution kernel costs about half a factor pass however few warps it carries, so it should
+            // cover a whole chunk (the factor waves whose blocks fit the HBM workspace, launch_frontal): shrink its block ring
+            // (less prefetch distance; >= ~3 blocks stay ahead) until enough of its warps are resident for that.
+            const long long per_sample = ((long long)host.nnzL + 2LL * host.n + 2) * 8;
+            const long long wave = (long long)g_sm_count * warps_f * lanes;
+            const long long mem_waves = std::max<long long>(1, std::min<long long>(4, FRONTAL_WORK_BYTES / per_sample / wave));
+            const long long lr_min = std::max<long long>(host.cmax + 2, std::min<long long>(lr, 3LL * (host.cmax / 2 + 2)));
+            for (; lr > lr_min; lr -= 4) {
+                const long long sm_b = (host1.nslots + n_obs + lr) * 8LL * lanes + 16 + streams.ring_bytes + 1024;
+                if (smem_per_sm / sm_b >= warps_f * mem_waves) break;
+            }
+            lr = std::max(lr, lr_min);
+        }
+        if (lanes != 32 || lr != streams.lr_rows)
+            frontal_pack_streams(host, (int)lr, FRONTAL_DMAX, lanes ? lanes : 32, &streams, &host1);
         if (int e = fwd.upload(streams.fwd, st)) return e;
         if (int e = bwd.upload(streams.bwd, st)) return e;
         if (int e = fwd1.upload(streams.fwd1, st)) return e;
@@ -169,13 +206,14 @@ struct FrontalSet {
     FrontalDev dev(bool lane_kernel) const {
         FrontalDev d{};
         d.n = host.n;
-        d.nslots = host.nslots;
+        d.nslots = lane_kernel ? host1.nslots : host.nslots;
         d.cmax = host.cmax;
         d.ncv = ncv;
-        d.ntri = host.nslots * (host.nslots + 1) / 2;
+        d.ntri = d.nslots * (d.nslots + 1) / 2;
         d.ring_bytes = streams.ring_bytes;
         d.lr_rows = streams.lr_rows;
         d.lanes = streams.lanes;
+        d.ring_fwd1 = streams.ring_fwd1;
         d.nnzL = host.nnzL;
         d.fwd = lane_kernel ? fwd1.p : fwd.p;
         d.bwd = lane_kernel ? bwd1.p : bwd.p;
@@ -188,6 +226,7 @@ struct tfin_ctx {
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
+    int smem_per_sm = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
 
@@ -265,7 +304,7 @@ struct tfin_ctx {
     int frontal_kernel = 0;  // 0 auto, 1 = D1 (sample per thread), 2 = D2 (sample per CTA)
     int frontal_threads = 0; // D2 threads per CTA, 0 = auto
     int frontal_mode = -1;   // D2: -1 auto, 0 = QOI (extra right-hand sides), 1 = SOLVE (factor to HBM + backward)
-    int frontal_lanes = 0;   // D1: samples per warp, 0 = auto, else 8 / 16 / 32 (takes effect at the next tfin_set_*)
+    int frontal_lanes = 0;   // D1: samples per warp, 0 = auto (most samples in flight), else 4..32
     int frontal_split = 1;   // D1: 1 = factor kernel + substitution kernel, 0 = one fused kernel
     int last_focc_b = 0;
     int last_solver = 0, last_fkernel = 0, last_fthreads = 0, last_focc = 0;
@@ -299,6 +338,8 @@ extern "C" int tfin_create(int device, tfin_handle_t* out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    g_sm_count = prop.multiProcessorCount;
     TFIN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (int err = c->d_counter.reserve(1)) return err;
     *out = c;
@@ -511,9 +552,10 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
             }
         };
         h->fr_aff.why = frontal_build(n, row_ptr, col_idx, rhs, terms, &h->fr_aff.host);
+        if (h->fr_aff.why.empty()) h->fr_aff.why = frontal_build(n, row_ptr, col_idx, rhs, terms, &h->fr_aff.host1, false);
         if (h->fr_aff.why.empty()) {
             h->fr_aff.ncv = n_terms;
-            if (int e = h->fr_aff.upload(h->stream, 0, h->max_smem_optin, h->frontal_lanes)) return e;
+            if (int e = h->fr_aff.upload(h->stream, 0, h->max_smem_optin, h->smem_per_sm, h->frontal_lanes)) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
             h->fr_aff.ok = true;
         }
@@ -574,7 +616,8 @@ extern "C" int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_
     for (FrontalSet* fs : {&h->fr_aff, &h->fr_nod})
         if (fs->ok) {
             frontal_set_obs(fs->host, n_obs, ptr, idx, val);
-            if (int e = fs->upload(h->stream, n_obs, h->max_smem_optin, h->frontal_lanes)) return e;
+            frontal_set_obs(fs->host1, n_obs, ptr, idx, val);
+            if (int e = fs->upload(h->stream, n_obs, h->max_smem_optin, h->smem_per_sm, h->frontal_lanes)) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
         }
     // B_obs^T as CSR over the n dofs: right-hand sides of the adjoint solves
@@ -638,11 +681,14 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
         std::vector<double> rhs_host(n);
         TFIN_CUDA(cudaMemcpy(rhs_host.data(), h->d_rhs.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
         h->fr_nod.why = frontal_build(n, rp.data(), ci.data(), rhs_host.data(), terms, &h->fr_nod.host);
+        if (h->fr_nod.why.empty())
+            h->fr_nod.why = frontal_build(n, rp.data(), ci.data(), rhs_host.data(), terms, &h->fr_nod.host1, false);
         if (h->fr_nod.why.empty()) {
             h->fr_nod.ncv = n_cells + 1;
             if (!h->h_obs_ptr.empty())
-                frontal_set_obs(h->fr_nod.host, h->n_obs, h->h_obs_ptr.data(), h->h_obs_idx.data(), h->h_obs_val.data());
-            if (int e = h->fr_nod.upload(h->stream, h->n_obs, h->max_smem_optin, h->frontal_lanes)) return e;
+                for (FrontalProgram* fp : {&h->fr_nod.host, &h->fr_nod.host1})
+                    frontal_set_obs(*fp, h->n_obs, h->h_obs_ptr.data(), h->h_obs_idx.data(), h->h_obs_val.data());
+            if (int e = h->fr_nod.upload(h->stream, h->n_obs, h->max_smem_optin, h->smem_per_sm, h->frontal_lanes)) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
             h->fr_nod.ok = true;
         }
@@ -1054,7 +1100,9 @@ static FrontalGeom frontal_geom(tfin_ctx* h, bool nodal, bool want_w) {
     if (h->frontal_kernel != 2 && P.cmax <= 32 && fs.streams.lr_rows > 0) {
         auto fits = [&](int phase, size_t* sm_out, int* occ_out) {
             const void* fn = frontal_lane_fn(P.cmax, phase);
-            const size_t sm = frontal_lane_smem(ntri, P.nslots, h->n_obs, ncv_smem, fs.streams.lr_rows, fs.streams.lanes, ring, phase);
+            const int ns1 = fs.host1.nslots;
+            const size_t sm = frontal_lane_smem(ns1 * (ns1 + 1) / 2, ns1, h->n_obs, ncv_smem, fs.streams.lr_rows, fs.streams.lanes,
+                                                phase == FRONTAL_PHASE_FACTOR ? fs.streams.ring_fwd1 : ring, phase);
             if (sm > (size_t)h->max_smem_optin ||
                 cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
                 return false;
@@ -1127,17 +1175,25 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
         // WAVES of the factor kernel (resident warps x samples per warp): a partial last wave would idle most of the GPU
         // for a full pass (2 ms at n = 1597)
         const int64_t wave = (int64_t)h->sm_count * g.occ * fs.streams.lanes;
-        const int64_t mem_waves = std::max<int64_t>(1, (((int64_t)6 << 30) / ((int64_t)(per_sample_work + 2) * 8)) / wave);
-        // ... and preferably a whole number of waves of the substitution kernel too
-        int64_t k = g.occ_b / std::__gcd(g.occ, g.occ_b);
-        while (k * 2 <= mem_waves) k *= 2;
-        if (k > mem_waves) k = mem_waves;
+        const int64_t mem_waves = std::max<int64_t>(1, ((int64_t)FRONTAL_WORK_BYTES / ((int64_t)(per_sample_work + 2) * 8)) / wave);
+        // ... and the substitution kernel runs ceil(k occ / occ_b) passes of its own on a chunk of k waves (a pass of it
+        // takes ~0.55 of a factor pass, however empty): take the k <= mem_waves with the most samples per unit time
+        int64_t k = 1;
+        double best = 0.0;
+        for (int64_t kk = 1; kk <= std::min<int64_t>(mem_waves, 64); ++kk) {
+            const double passes_b = (double)((kk * g.occ + g.occ_b - 1) / g.occ_b);
+            const double eff = (double)kk / ((double)kk + 0.55 * passes_b);
+            if (eff > best * 1.01) {
+                best = eff;
+                k = kk;
+            }
+        }
         chunk = std::min<int64_t>(chunk, k * wave);
     }
     if (nodal) {
         const int64_t cap = std::max<int64_t>(32, ((int64_t)1 << 30) / ((int64_t)fs.ncv * 8) / 32 * 32);
         chunk = std::min<int64_t>(chunk, cap);
-        if (int e = h->d_fcv.reserve((size_t)((chunk + 31) / 32 * 32) * fs.ncv)) return e;
+        if (int e = h->d_fcv.reserve((size_t)(chunk + 96) * fs.ncv)) return e;   // whole 32-sample tiles, whole groups
     }
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
         const int64_t m = std::min<int64_t>(chunk, N - s0);
@@ -1214,12 +1270,22 @@ static int launch_frontal_gradient(tfin_ctx* h, const FrontalGeom& g, const doub
     const int lanes = fs.streams.lanes, n = P.n, nobs = h->n_obs;
     const size_t per_sample_work = (size_t)P.nnzL + 2 * (size_t)n;
     const int64_t wave = (int64_t)h->sm_count * g.occ * lanes;
-    const int64_t mem_waves = std::max<int64_t>(1, (((int64_t)6 << 30) / ((int64_t)(per_sample_work + 2) * 8)) / wave);
-    int64_t kk = g.occ_b / std::__gcd(g.occ, g.occ_b);
-    if (kk > mem_waves) kk = mem_waves;
+    const int64_t mem_waves = std::max<int64_t>(1, ((int64_t)FRONTAL_WORK_BYTES / ((int64_t)(per_sample_work + 2) * 8)) / wave);
+    int64_t kk = 1;   // waves per chunk: as launch_frontal, with three more substitution passes per chunk
+    {
+        double best = 0.0;
+        for (int64_t c = 1; c <= std::min<int64_t>(mem_waves, 64); ++c) {
+            const double passes_b = (double)((c * g.occ + g.occ_b - 1) / g.occ_b);
+            const double eff = (double)c / ((double)c + 0.55 * (sens ? 1 + 2 * h->n_obs : 3) * passes_b);
+            if (eff > best * 1.01) {
+                best = eff;
+                kk = c;
+            }
+        }
+    }
     const int64_t cvcap = std::max<int64_t>(32, ((int64_t)1 << 30) / ((int64_t)fs.ncv * 8) / 32 * 32);
     const int64_t chunk = std::min<int64_t>(N, std::min<int64_t>(kk * wave, cvcap));
-    if (int e = h->d_fcv.reserve((size_t)((chunk + 31) / 32 * 32) * fs.ncv)) return e;
+    if (int e = h->d_fcv.reserve((size_t)(chunk + 96) * fs.ncv)) return e;
     if (int e = h->d_fw.reserve((size_t)chunk * n)) return e;
     if (int e = h->d_fv.reserve((size_t)chunk * n)) return e;
     if (!d_qoi) {   // the adjoint right-hand side needs the observables
@@ -2202,6 +2268,7 @@ extern "C" int64_t tfin_get_int(tfin_handle_t h, const char* key) {
     if (k == "frontal_ok") return h->fr_aff.ok ? 1 : 0;
     if (k == "frontal_nodal_ok") return h->fr_nod.ok ? 1 : 0;
     if (k == "frontal_slots") return h->fr_aff.ok ? h->fr_aff.host.nslots : -1;
+    if (k == "frontal_slots_lane") return h->fr_aff.ok ? h->fr_aff.host1.nslots : -1;
     if (k == "frontal_cmax") return h->fr_aff.ok ? h->fr_aff.host.cmax : -1;
     if (k == "frontal_nnz_factor") return h->fr_aff.ok ? h->fr_aff.host.nnzL : -1;
     if (k == "frontal_pair_updates") return h->fr_aff.ok ? (int64_t)h->fr_aff.host.pair_updates : -1;
@@ -2258,13 +2325,18 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
         h->frontal_threads = (int)value;
         return 0;
     }
-    if (k == "frontal_lanes") {
-        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(TFIN_E_ARG, "frontal_lanes must be 0, 8, 16 or 32");
-        h->frontal_lanes = (int)value;
+    if (k == "frontal_lanes" || k == "frontal_ring_rows") {
+        if (k == "frontal_ring_rows") {
+            if (value < 0 || value > 4096) return fail(TFIN_E_ARG, "frontal_ring_rows must be 0 (auto) .. 4096");
+            g_frontal_ring_rows = (int)value;
+        } else {
+            if (value != 0 && (value < 4 || value > 32)) return fail(TFIN_E_ARG, "frontal_lanes must be 0 (auto) or 4..32");
+            h->frontal_lanes = (int)value;
+        }
         for (FrontalSet* fs : {&h->fr_aff, &h->fr_nod})   // repack the D1 streams for the new row width
             if (fs->ok) {
                 DeviceGuard guard(h->device);
-                if (int e = fs->upload(h->stream, h->n_obs, h->max_smem_optin, h->frontal_lanes)) return e;
+                if (int e = fs->upload(h->stream, h->n_obs, h->max_smem_optin, h->smem_per_sm, h->frontal_lanes)) return e;
                 TFIN_CUDA(cudaStreamSynchronize(h->stream));
             }
         return 0;
@@ -2321,6 +2393,12 @@ struct tfin_frontal_program {
 extern "C" int tfin_frontal_analyze(int32_t n, int32_t nnz, const int32_t* row_ptr, const int32_t* col_idx, int32_t n_terms,
                                     const double* vals, const double* rhs, int32_t n_obs, const int32_t* obs_ptr,
                                     const int32_t* obs_idx, const double* obs_val, void** out) {
+    return tfin_frontal_analyze_ex(n, nnz, row_ptr, col_idx, n_terms, vals, rhs, n_obs, obs_ptr, obs_idx, obs_val, 1, out);
+}
+
+extern "C" int tfin_frontal_analyze_ex(int32_t n, int32_t nnz, const int32_t* row_ptr, const int32_t* col_idx, int32_t n_terms,
+                                       const double* vals, const double* rhs, int32_t n_obs, const int32_t* obs_ptr,
+                                       const int32_t* obs_idx, const double* obs_val, int32_t lookahead, void** out) {
     if (n <= 0 || nnz <= 0 || !row_ptr || !col_idx || !vals || !rhs || !out || n_terms < 1)
         return fail(TFIN_E_ARG, "tfin_frontal_analyze: bad argument");
     auto* fp = new tfin_frontal_program();
@@ -2330,7 +2408,7 @@ extern "C" int tfin_frontal_analyze(int32_t n, int32_t nnz, const int32_t* row_p
             if (v != 0.0) o.push_back(FrontalTermEntry{t, v});
         }
     };
-    const std::string why = frontal_build(n, row_ptr, col_idx, rhs, terms, &fp->P);
+    const std::string why = frontal_build(n, row_ptr, col_idx, rhs, terms, &fp->P, lookahead != 0);
     if (!why.empty()) {
         delete fp;
         return fail(TFIN_E_STATE, "tfin_frontal_analyze: %s", why.c_str());

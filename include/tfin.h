@@ -256,6 +256,11 @@ int tfin_subfin_avg(tfin_handle_t h, const double* k, int64_t N, int32_t mem, do
 int tfin_frontal_analyze(int32_t n, int32_t nnz, const int32_t* row_ptr, const int32_t* col_idx, int32_t n_terms,
                          const double* vals, const double* rhs, int32_t n_obs, const int32_t* obs_ptr,
                          const int32_t* obs_idx, const double* obs_val, void** out);
+/* lookahead = 1: as tfin_frontal_analyze (front slots of column j + 1 allocated one step early -- the sample-per-CTA kernel
+ * assembles it while step j updates); 0: the pivot's slot is recycled first (the sample-per-thread kernel's program). */
+int tfin_frontal_analyze_ex(int32_t n, int32_t nnz, const int32_t* row_ptr, const int32_t* col_idx, int32_t n_terms,
+                            const double* vals, const double* rhs, int32_t n_obs, const int32_t* obs_ptr,
+                            const int32_t* obs_idx, const double* obs_val, int32_t lookahead, void** out);
 int64_t tfin_frontal_array(void* prog, const char* name, void* dst, int64_t dst_bytes);
 void tfin_frontal_free(void* prog);
 
@@ -278,7 +283,9 @@ int64_t tfin_get_int(tfin_handle_t h, const char* key);
  * otherwise; 1 = always PCG (tol / maxit apply); 2 = direct required (fails if unavailable).  With the direct solver
  * tol / maxit are ignored, iters_out is 0 and relres_out is the consistency |b.w - y.y| / y.y of the two substitutions
  * (0 in the observables-only mode of the wide-front kernel, which has no backward substitution);
- * "frontal_kernel" (0 auto, 1 = sample per thread, 2 = sample per CTA), "frontal_threads", "frontal_mode";
+ * "frontal_kernel" (0 auto, 1 = sample per thread, 2 = sample per CTA), "frontal_threads", "frontal_mode",
+ * "frontal_split", "frontal_lanes" (samples per warp of the sample-per-thread kernel: 0 = auto, the (warps per SM,
+ * samples per warp) pair with the most samples in flight that shared memory allows; or 4..32; results do not depend on it);
  * "nodal_coef_mode": 0 = conductivity k (fom/forward_solve.py:160), 1 = conductivity exp(k) integrated with the
  * degree-3 rule of dolfin's form compiler (fom/forward_solve_exp.py:160) in tfin_fom_nodal / tfin_rom_nodal /
  * tfin_pcn_chains(model 0), and the gradient form k_hat exp(k) grad z . grad v with its degree-4 rule (:299, :328) in

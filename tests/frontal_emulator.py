@@ -19,7 +19,7 @@ _ARRAYS = {"perm": np.int32, "piv_slot": np.uint16, "col_ptr": np.int32, "col_sl
 _SCALARS = ("n", "nslots", "cmax", "nnzL", "pair_updates")
 
 
-def fetch_program(ops, obs_csr=None):
+def fetch_program(ops, obs_csr=None, lookahead=True):
     """ops: assembly.FinOperators.  Returns a dict of numpy arrays / ints."""
     lib = _cabi.load_library()
     rp, ci = np.ascontiguousarray(ops.row_ptr, np.int32), np.ascontiguousarray(ops.col_idx, np.int32)
@@ -28,9 +28,9 @@ def fetch_program(ops, obs_csr=None):
     optr, oidx = np.ascontiguousarray(optr, np.int32), np.ascontiguousarray(oidx, np.int32)
     oval = np.ascontiguousarray(oval, np.float64)
     prog = C.c_void_p()
-    rc = lib.tfin_frontal_analyze(ops.n, ci.shape[0], rp.ctypes.data, ci.ctypes.data, vals.shape[0], vals.ctypes.data,
-                                  rhs.ctypes.data, optr.shape[0] - 1, optr.ctypes.data, oidx.ctypes.data,
-                                  oval.ctypes.data, C.byref(prog))
+    rc = lib.tfin_frontal_analyze_ex(ops.n, ci.shape[0], rp.ctypes.data, ci.ctypes.data, vals.shape[0], vals.ctypes.data,
+                                     rhs.ctypes.data, optr.shape[0] - 1, optr.ctypes.data, oidx.ctypes.data,
+                                     oval.ctypes.data, 1 if lookahead else 0, C.byref(prog))
     if rc != 0:
         raise RuntimeError(lib.tfin_last_error().decode())
     out = {}

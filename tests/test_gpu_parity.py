@@ -919,9 +919,10 @@ def test_config4_refined_mesh_at_full_size():
     h.close()
 
 
-@pytest.mark.parametrize("lanes", [8, 16])
+@pytest.mark.parametrize("lanes", [8, 16, 25, 27])
 def test_direct_solver_narrow_rows(space_m2, oracle_m2, lanes):
-    """D1 with 8 / 16 samples per warp (narrower shared-memory rows, more resident warps): same results bit for bit."""
+    """D1 with fewer than 32 samples per warp (narrower shared-memory rows, more resident warps; the default picks the
+    pair with the most samples in flight, 3 x 25 on the reference-size mesh): same results bit for bit, odd counts too."""
     from bayesianinferencedl_b200.assembly import build_operators
     ops = build_operators(space_m2)
     h = _handle_for(ops, cells=True)
@@ -930,6 +931,7 @@ def test_direct_solver_narrow_rows(space_m2, oracle_m2, lanes):
     rng = np.random.default_rng(45)
     theta = rng.uniform(0.1, 10.0, (75, 9))
     k = np.exp(0.5 * rng.standard_normal((21, ops.n)))
+    h.set_int("frontal_lanes", 32)
     ref, refn = h.fom_affine(theta, want_w=True), h.fom_nodal(k)
     assert h.get_int("frontal_lanes") == 32
     h.set_int("frontal_lanes", lanes)

@@ -4,7 +4,7 @@ import csv, subprocess, sys
 rep, pat = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", f"regex:{pat}",
-                      "--launch-skip", "0", "--launch-count", "1"], capture_output=True, text=True).stdout
+                      "--launch-skip", (sys.argv[4] if len(sys.argv) > 4 else "0"), "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, cur, agg = None, None, {}
 for r in rows:
