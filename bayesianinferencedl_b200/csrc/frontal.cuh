@@ -59,6 +59,10 @@ struct FrontalIO {
     long long data_stride;   // 0: one shared observation vector
     double* cost_out;        // (N) | null
     int unit_row;            // data == null: right-hand side -B_obs[unit_row, :]^T (one row of the sensitivity)
+    // D2 adjoint solve (MODE_SOLVE, adj != 0): the matrix is factorised again with the right-hand side
+    // -B_obs^T res, res = qoi_in - data (adj = 1) or the unit vector e_unit_row (adj = 2); w_out receives the adjoint state
+    int adj;
+    const double* qoi_in;    // (N, n_obs), adj = 1
 };
 
 __device__ __forceinline__ unsigned tri_u(unsigned s) { return s * (s + 1u) / 2u; }
@@ -450,7 +454,7 @@ struct FrontalCtaSmem {
         L.lcol = take((size_t)cmax * 8);
         L.ypiv = take((size_t)R * 8);
         L.red = take(2 * 32 * 8);
-        L.qacc = take((size_t)n_obs * 8);
+        L.qacc = take((size_t)n_obs * 16);   // observables | residual of the adjoint right-hand side
         L.cvec = take((size_t)ncv_smem * 8);
         L.cslot = take((size_t)cmax * 4);
         L.ring = take((size_t)ring_bytes);
@@ -460,7 +464,7 @@ struct FrontalCtaSmem {
 };
 
 template <int MODE, int NU>   // NU: the column fits 32 * NU entries
-__global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L) {
+__global__ void __launch_bounds__(NU >= 8 ? 512 : 768) frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L) {
     extern __shared__ __align__(16) unsigned char fsm_raw[];
     double* F = reinterpret_cast<double*>(fsm_raw + L.F);
     double* yv = reinterpret_cast<double*>(fsm_raw + L.yv);
@@ -506,8 +510,19 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
         for (int e = tid; e < P.ntri; e += NT) F[e] = 0.0;
         for (int e = tid; e < P.nslots * R; e += NT) yv[e] = 0.0;
         for (int o = tid; o < io.n_obs; o += NT) qacc[o] = 0.0;
+        double* res = qacc + io.n_obs;
+        const bool adj = MODE == FRONTAL_MODE_SOLVE && io.adj != 0;
+        if (adj)
+            for (int o = tid; o < io.n_obs; o += NT)
+                res[o] = io.adj == 2 ? (o == io.unit_row ? 1.0 : 0.0)
+                                     : io.qoi_in[(size_t)s * io.n_obs + o] - io.data[(size_t)s * io.data_stride + o];
         if (loader) cp_async_wait<0>();
         __syncthreads();
+        if (adj && io.cost_out && tid == 0) {
+            double cost = 0.0;
+            for (int o = 0; o < io.n_obs; ++o) cost = fma(res[o], res[o], cost);
+            io.cost_out[s] = 0.5 * cost;
+        }
 
         bool bad = false;
         double myq = 0.0;   // QOI mode: thread rtid = 1 + o accumulates observable o; rtid = 0 accumulates y.y
@@ -548,7 +563,11 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
                     double v = yv[p * R + rtid];
                     yv[p * R + rtid] = 0.0;
                     if (rtid == 0) {
-                        v += __longlong_as_double(((long long)h1.w << 32) | h1.z);
+                        if (adj) {   // -B_obs^T res at this pivot's dof
+                            for (unsigned o = 0; o < nobs; ++o) v = fma(-ovalv[o], res[orowv[o]], v);
+                        } else {
+                            v += __longlong_as_double(((long long)h1.w << 32) | h1.z);
+                        }
                     } else {
                         for (unsigned o = 0; o < nobs; ++o)
                             if ((int)orowv[o] == rtid - 1) v += ovalv[o];
@@ -718,7 +737,7 @@ __global__ void frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L)
             ring.rd += reclen;
         }
         if (tid == 0) {
-            if (io.qoi_out)
+            if (io.qoi_out && !adj)
                 for (int o = 0; o < io.n_obs; ++o) io.qoi_out[(size_t)s * io.n_obs + o] = qacc[o];
             if (io.status_out) io.status_out[s] = (bad || !(bw == bw)) ? TFIN_STATUS_BREAKDOWN : TFIN_STATUS_CONVERGED;
             if (io.iters_out) io.iters_out[s] = 0;

@@ -704,6 +704,18 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
         if (!h->fr_nod.ok)
             return fail(TFIN_E_STATE, "tfin_set_cells: n = %d is beyond the on-chip PCG (n <= 8191) and the direct solver is unavailable: %s",
                         h->n, h->fr_nod.why.c_str());
+        // cells around every dof (those of its diagonal entry): the gradient-form kernel walks them
+        std::vector<int> dptr(n + 1, 0), dcell;
+        for (int i = 0; i < n; ++i) {
+            dptr[i] = (int)dcell.size();
+            for (int j = rp[i]; j < rp[i + 1]; ++j)
+                if (ci[j] == i)
+                    for (auto& pc : contrib[j]) dcell.push_back(pc.first);
+        }
+        dptr[n] = (int)dcell.size();
+        if (int e = h->d_dptr.upload(dptr, h->stream)) return e;
+        if (int e = h->d_dcell.upload(dcell, h->stream)) return e;
+        TFIN_CUDA(cudaStreamSynchronize(h->stream));
         h->Wn = 0;
         h->n_cells = n_cells;
         return 0;
@@ -1138,7 +1150,7 @@ static FrontalGeom frontal_geom(tfin_ctx* h, bool nodal, bool want_w) {
         const double pairs = 0.5 * P.cmax * (P.cmax + 1.0);
         T = 32 * (int)std::min(16.0, std::max(1.0, std::ceil(pairs / (32.0 * 12.0))));
     }
-    T = std::max(32, std::min(1024, (T + 31) & ~31));
+    T = std::max(32, std::min(512, (T + 31) & ~31));   // __launch_bounds__(512): 128 registers per thread
     const void* fn = frontal_cta_fn(mode, P.cmax);
     if (!fn) return g;   // columns of more than 256 entries: PCG
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
@@ -1160,8 +1172,19 @@ static FrontalGeom frontal_geom(tfin_ctx* h, bool nodal, bool want_w) {
 }
 
 // d_in: theta (N, in_stride) for the affine operator, nodal fields k (N, n) for the nodal one.
+// Adjoint right-hand side of a D2 solve (FrontalIO::adj): pointers of sample 0 of the batch.
+struct FrontalAdjArgs {
+    int mode;                // 1 = -B_obs^T (qoi_in - data), 2 = -B_obs[unit_row]^T
+    const double* qoi_in;    // (N, n_obs)
+    const double* data;      // (1 | N, n_obs)
+    int64_t data_stride;
+    double* cost_out;        // (N) | null
+    int unit_row;
+};
+
 static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const double* d_in, int in_stride, int64_t N,
-                          double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres, cudaStream_t st) {
+                          double* d_w, double* d_qoi, int* d_iters, int* d_status, double* d_relres, cudaStream_t st,
+                          const FrontalAdjArgs* adj = nullptr) {
     FrontalSet& fs = nodal ? h->fr_nod : h->fr_aff;
     if (!fs.ok || g.kernel == 0)
         return fail(TFIN_E_STATE, "direct solver unavailable for this operator: %s", fs.ok ? "front does not fit shared memory" : fs.why.c_str());
@@ -1208,6 +1231,15 @@ static int launch_frontal(tfin_ctx* h, bool nodal, const FrontalGeom& g, const d
         io.status_out = d_status ? d_status + s0 : nullptr;
         io.relres_out = d_relres ? d_relres + s0 : nullptr;
         io.counter = h->d_counter.p;
+        if (adj) {
+            if (g.kernel != 2 || g.mode != FRONTAL_MODE_SOLVE) return fail(TFIN_E_STATE, "adjoint right-hand side: sample-per-CTA solve mode only");
+            io.adj = adj->mode;
+            io.qoi_in = adj->qoi_in ? adj->qoi_in + (size_t)s0 * h->n_obs : nullptr;
+            io.data = adj->data ? adj->data + (size_t)s0 * adj->data_stride : nullptr;
+            io.data_stride = adj->data_stride;
+            io.cost_out = adj->cost_out ? adj->cost_out + s0 : nullptr;
+            io.unit_row = adj->unit_row;
+        }
         if (nodal) {
             const dim3 cgrid((unsigned)((h->n_cells + 31) / 32), (unsigned)((m + 31) / 32));
             frontal_cellcoef_kernel<<<cgrid, dim3(32, 8), 0, st>>>(io.in, (long long)m, P.n, h->n_cells, h->d_cells.p,
@@ -1353,6 +1385,52 @@ static int launch_frontal_gradient(tfin_ctx* h, const FrontalGeom& g, const doub
     }
     h->last_solver = 2;
     h->last_fkernel = 1;
+    h->last_path = 4;
+    return 0;
+}
+
+// Fin.gradient / Fin.sensitivity on meshes whose front is too wide for the sample-per-thread kernel: the sample-per-CTA
+// kernel solves A w = b (solution + observables), then A v = -B_obs^T (qoi - data) (or one unit row per observable) by
+// factorising again -- its factor blocks are per CTA, not per sample -- and the gradient form follows.
+static int launch_frontal_gradient_cta(tfin_ctx* h, const FrontalGeom& g, const double* d_k, int64_t N, const double* d_data,
+                                       int64_t data_stride, double* d_grad, double* d_cost, double* d_qoi, int* d_status,
+                                       cudaStream_t st, bool sens) {
+    const int n = h->n, nobs = h->n_obs;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(N, ((int64_t)1 << 30) / ((int64_t)n * 8)));
+    if (int e = h->d_fw.reserve((size_t)chunk * n)) return e;
+    if (int e = h->d_fv.reserve((size_t)chunk * n)) return e;
+    if (!d_qoi) {
+        if (int e = h->d_qoi.reserve((size_t)N * nobs)) return e;
+        d_qoi = h->d_qoi.p;
+    }
+    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, N - s0);
+        const double* kin = d_k + (size_t)s0 * n;
+        if (int e = launch_frontal(h, true, g, kin, n, m, h->d_fw.p, d_qoi + (size_t)s0 * nobs, nullptr,
+                                   d_status ? d_status + s0 : nullptr, nullptr, st))
+            return e;
+        const int64_t total = m * (int64_t)n;
+        const int gb = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+        const int n_adj = sens ? nobs : 1;
+        for (int o = 0; o < n_adj; ++o) {
+            FrontalAdjArgs a{};
+            a.mode = sens ? 2 : 1;
+            a.qoi_in = d_qoi + (size_t)s0 * nobs;
+            a.data = sens ? nullptr : d_data + (data_stride ? (size_t)s0 * data_stride : 0);
+            a.data_stride = data_stride;
+            a.cost_out = (!sens && d_cost) ? d_cost + s0 : nullptr;
+            a.unit_row = o;
+            if (int e = launch_frontal(h, true, g, kin, n, m, h->d_fv.p, nullptr, nullptr, nullptr, nullptr, st, &a)) return e;
+            double* gout = sens ? d_grad + ((size_t)s0 * nobs + o) * n : d_grad + (size_t)s0 * n;
+            frontal_gradform_kernel<<<gb, 256, 0, st>>>(h->d_fw.p, h->d_fv.p, kin, (long long)m, n, h->d_dptr.p, h->d_dcell.p,
+                                                        h->d_cells.p, h->d_Ke.p, h->coef_mode, gout,
+                                                        sens ? (long long)nobs * n : (long long)n);
+            TFIN_CUDA(cudaGetLastError());
+            h->launches += 1;
+        }
+    }
+    h->last_solver = 2;
+    h->last_fkernel = 3;
     h->last_path = 4;
     return 0;
 }
@@ -1915,10 +1993,11 @@ static int fom_adjoint(tfin_handle_t h, int mode, const double* k, int64_t N, in
         return fail(TFIN_E_ARG, "tfin_fom_nodal_gradient: data must have 1 or N rows");
     if (N == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    if ((mode == 1 || mode == 2) && h->fom_solver != 1 && h->precision == 64 && h->small_ok) {
-        // direct solver: one factorisation serves the forward and the adjoint solve
+    if ((mode == 1 || mode == 2) && h->fom_solver != 1 && h->precision == 64) {
+        // direct solver: one factorisation serves the forward and the adjoint solve (sample-per-thread kernel), or one
+        // factorisation per solve on wide fronts (sample-per-CTA kernel)
         const FrontalGeom g = frontal_geom(h, true, true);
-        if (g.kernel == 1 && g.split) {
+        if ((g.kernel == 1 && g.split) || (g.kernel == 2 && g.mode == FRONTAL_MODE_SOLVE)) {
             Staged sg{h, st, mem == TFIN_MEM_HOST};
             const int n = h->n, nobs = h->n_obs;
             const double *d_k, *d_data = nullptr;
@@ -1934,9 +2013,15 @@ static int fom_adjoint(tfin_handle_t h, int mode, const double* k, int64_t N, in
             if (int e = sg.out_alloc(iters_out, (size_t)N, h->d_iters, &d_iters)) return e;
             if (int e = sg.out_alloc(status_out, (size_t)N, h->d_status, &d_status)) return e;
             if (d_iters) TFIN_CUDA(cudaMemsetAsync(d_iters, 0, (size_t)N * sizeof(int), st));
-            if (int e = launch_frontal_gradient(h, g, d_k, N, d_data, data_rows == 1 ? 0 : nobs, d_grad, d_cost, d_qoi, d_status, st,
-                                                mode == 2))
-                return e;
+            if (g.kernel == 1) {
+                if (int e = launch_frontal_gradient(h, g, d_k, N, d_data, data_rows == 1 ? 0 : nobs, d_grad, d_cost, d_qoi, d_status,
+                                                    st, mode == 2))
+                    return e;
+            } else {
+                if (int e = launch_frontal_gradient_cta(h, g, d_k, N, d_data, data_rows == 1 ? 0 : nobs, d_grad, d_cost, d_qoi,
+                                                        d_status, st, mode == 2))
+                    return e;
+            }
             if (int e = sg.out_copy(grad_out, grad_rows * n, d_grad)) return e;
             if (int e = sg.out_copy(cost_out, (size_t)N, d_cost)) return e;
             if (int e = sg.out_copy(qoi_out, (size_t)N * nobs, d_qoi)) return e;

@@ -891,6 +891,37 @@ def test_direct_solver_mid_and_refined_meshes():
         h.close()
 
 
+def test_gradient_and_sensitivity_on_wide_fronts():
+    """Fin.gradient / Fin.sensitivity above the on-chip PCG's ~4100 dofs: the sample-per-CTA kernel solves
+    the state and, factorising again with the right-hand side -B_obs^T (qoi - data) (or -B_obs[o]^T), the adjoint; the
+    gradient-form kernel follows.  m = 8 (n = 10 017 dofs), against the oracle's sparse LU."""
+    from bayesianinferencedl_b200 import Fin, get_space
+    from bayesianinferencedl_b200.assembly import build_operators
+    from oracle.thermal_fin_oracle import FinOracle
+    V = get_space(40, m=8)
+    fin = Fin(V)
+    assert fin.dofs > 8191
+    ops = build_operators(V)
+    orc = FinOracle(ops.coords, ops.cells)
+    rng = np.random.default_rng(48)
+    k = np.exp(0.3 * rng.standard_normal((5, fin.dofs)))
+    data = rng.uniform(0.5, 2.0, (5, 9))
+    g, cost = fin.gradient(k, data, return_cost=True)
+    assert fin.handle.get_int("fom_solver") == 2 and fin.handle.get_int("frontal_kernel") == 3
+    for s in (0, 4):
+        ref = np.asarray(orc.gradient(k[s], data[s])).ravel()
+        assert np.max(np.abs(g[s] - ref)) <= 1e-9 * np.max(np.abs(ref)), s
+        q = orc.qoi_operator(orc.forward(k[s]))
+        assert abs(cost[s] - 0.5 * np.sum((q - data[s]) ** 2)) <= 1e-10 * cost[s]
+    g1 = fin.gradient(k[:2], data[0])                      # one shared observation vector
+    ref = np.asarray(orc.gradient(k[1], data[0])).ravel()
+    assert np.max(np.abs(g1[1] - ref)) <= 1e-9 * np.max(np.abs(ref))
+    J = fin.sensitivity(k[:2])
+    assert J.shape == (2, 9, fin.dofs)
+    Jref = np.asarray(orc.sensitivity(k[1]))
+    assert np.max(np.abs(J[1] - Jref)) <= 1e-9 * np.max(np.abs(Jref))
+
+
 def test_config4_refined_mesh_at_full_size():
     """BASELINE config 4 at its own size: m = 26, n = 99 945, theta ~ U(0.1, 10)^9.  Direct solver (D2, both modes) and the
     streaming PCG (K4) against the oracle's sparse LU: observables to 1e-10 relative, w to 1e-10 of its maximum."""
