@@ -350,8 +350,9 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
                 const uint4 r = *reinterpret_cast<const uint4*>(rq + 16 * i);   // rb x ring row | rows | source row
                 unsigned dst = lring_s + r.x;
                 const char* src = Lw + (size_t)r.z * rb;
-                for (unsigned k = 0; k < r.y; ++k, dst += rb, src += rb)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                if (xlane < LPG)   // shadow lanes would write lane LPG - 1's word again: serialised as bank conflicts
+                    for (unsigned k = 0; k < r.y; ++k, dst += rb, src += rb)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
             }
         };
         for (int j = n; j >= 0; --j) {   // step n - 1 - j of the stream; j == n: prologue record (initial requests only)

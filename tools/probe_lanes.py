@@ -8,16 +8,13 @@ from bayesianinferencedl_b200.assembly import build_operators
 
 lanes_list = [int(a) for a in sys.argv[1:] if "=" not in a] or [32, 27, 24, 20, 16, 12, 8]
 rr_list = [int(a[3:]) for a in sys.argv[1:] if a.startswith("rr=")] or [0]
-nw_list = [int(a[3:]) for a in sys.argv[1:] if a.startswith("nw=")] or [2]
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream
 ops = build_operators(get_space(40, m=3))
 h = _cabi.TfinHandle(0)
 h.set_operator(ops.row_ptr, ops.col_idx, ops.vals, ops.rhs); h.set_observation(*ops.obs_csr())
 h.set_int("fom_solver", 2)
 rng = np.random.default_rng(2)
-for lanes, rr, nw in [(l, r, w) for l in lanes_list for r in rr_list for w in nw_list]:
-    h.set_int("frontal_warps", nw)
-    print("warps", nw, end="  ")
+for lanes, rr in [(l, r) for l in lanes_list for r in rr_list]:
     h.set_int("frontal_ring_rows", rr)
     h.set_int("frontal_lanes", lanes)
     th = torch.tensor(rng.uniform(0.1, 3.5, (64, 9)), device="cuda")
