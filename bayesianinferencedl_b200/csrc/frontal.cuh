@@ -72,16 +72,20 @@ struct StreamRing {
     unsigned char* buf;         // shared memory, mask + 1 bytes
     const unsigned char* src;   // global stream, zero padded by one ring + 512 bytes
     unsigned mask, fetched, rd;
+    unsigned buf_s;             // shared-window address of buf, formed once (the conversion reads a special register)
     __device__ __forceinline__ void reset(const unsigned char* s) {
         src = s;
         fetched = 0;
         rd = 0;
+        buf_s = smem_u32(buf);
     }
     // prefetch whole 512-byte chunks while they fit ahead of the reader; `issue` selects the lanes that copy (one warp).
     // The caller commits the copy group.
     __device__ __forceinline__ void fill(int lane, bool issue) {
         while (fetched + 512u - rd <= mask + 1u) {
-            if (issue) cp_async16(buf + ((fetched + lane * 16u) & mask), src + fetched + lane * 16u);
+            if (issue)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(buf_s + ((fetched + lane * 16u) & mask)),
+                             "l"(src + fetched + lane * 16u) : "memory");
             fetched += 512u;
         }
     }
