@@ -774,8 +774,9 @@ def run_b200(args):
             "hbm": {"algorithmic_bytes_per_launch": hbm_bytes * NF, "achieved": hbm_bytes * NF / (k_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "frac": hbm_bytes * NF / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src},
             "note": "sparse-direct solve: the active front of every sample lives in shared memory, the factor makes one "
-                    "round trip through HBM for the backward substitution.  With two resident warps per SM the kernel is "
-                    "bound by instruction latency (ncu: issue slots 11 % busy, shared-memory pipe 25 %), see profiles/",
+                    "round trip through HBM for the backward substitution.  Shared memory bounds the samples in flight "
+                    "(three warps of 27 samples per SM at n = 1597) and the kernel is bound by instruction latency "
+                    "(ncu: issue slots 14 % busy, shared-memory pipe 33 %), see profiles/r2_ncu_frontal.md",
         }
     else:
         pcg_bytes = (2 * pcg_geo["ell_width"] + 1) * 8.0 * n * iters_sum
