@@ -128,8 +128,12 @@ static void align_ell_slots(int n, int W, const int32_t* col_idx, std::vector<st
 }
 
 #define FRONTAL_WORK_BYTES ((long long)6 << 30)   // HBM workspace of the split launch: factor blocks of one chunk
-static int g_sm_count = 148;          // set by tfin_create
-static int g_frontal_ring_rows = 0;   // tuning knob "frontal_ring_rows": rows of D1's factor-block ring, 0 = auto
+// Device limits and tuning knobs FrontalSet::upload sizes the sample-per-thread kernels for.
+struct FrontalCfg {
+    int smem_optin, smem_per_sm, sm_count;
+    int want_lanes;   // "frontal_lanes": samples per warp, 0 = auto
+    int ring_rows;    // "frontal_ring_rows": rows of the substitution kernel's factor-block ring, 0 = auto
+};
 
 // Device copy of one frontal program (frontal_host.h) -- the sparse-direct solver D1 / D2.
 struct FrontalSet {
@@ -151,7 +155,8 @@ struct FrontalSet {
     // (re)pack the instruction streams from the host program and copy them to the device.  D1 geometry is fixed here
     // (n_obs and the affine coefficient rows are known): samples per warp `lanes` (rows of 8 * lanes bytes) and the rows of
     // the factor-block ring, which gets the shared memory that the resident warps leave free.
-    int upload(cudaStream_t st, int n_obs, int smem_optin, int smem_per_sm, int want_lanes) {
+    int upload(cudaStream_t st, int n_obs, const FrontalCfg& cfg) {
+        const int smem_optin = cfg.smem_optin, smem_per_sm = cfg.smem_per_sm, want_lanes = cfg.want_lanes;
         const int ntri = host1.nslots * (host1.nslots + 1) / 2;
         const int base_rows = ntri + host1.nslots + n_obs + (ncv <= TFIN_MAX_TERMS ? ncv : 0);
         // Throughput of the (latency-bound) kernel is samples in flight / pass latency, and samples in flight = resident
@@ -159,7 +164,7 @@ struct FrontalSet {
         // (warps, lanes) pair with the largest product, fewer warps on a tie.  n = 1597: 3 x 25 = 75 instead of 2 x 32.
         // factor-block ring of the substitution kernel (split launch: no front in its shared memory): ~4 blocks ahead
         long long lr = std::max<long long>(host.cmax + 2, std::min<long long>(64, 4LL * (host.cmax + 2)));
-        if (g_frontal_ring_rows > 0) lr = std::max<long long>(host.cmax + 2, g_frontal_ring_rows);
+        if (cfg.ring_rows > 0) lr = std::max<long long>(host.cmax + 2, cfg.ring_rows);
         frontal_pack_streams(host, (int)lr, FRONTAL_DMAX, 32, &streams, &host1);
         const long long rows_f = base_rows - n_obs;   // factor kernel: front + rhs + coefficients (+ its instruction ring)
         int lanes = 0, warps_f = 1;
@@ -181,12 +186,12 @@ struct FrontalSet {
             }
         }
         if (lanes == 0) lr = 0;   // D1 cannot serve this front
-        if (lanes && g_frontal_ring_rows == 0) {
+        if (lanes && cfg.ring_rows == 0) {
             // One pass of the substitution kernel costs about half a factor pass however few warps it carries, so it should
             // cover a whole chunk (the factor waves whose blocks fit the HBM workspace, launch_frontal): shrink its block ring
             // (less prefetch distance; >= ~3 blocks stay ahead) until enough of its warps are resident for that.
             const long long per_sample = ((long long)host.nnzL + 2LL * host.n + 2) * 8;
-            const long long wave = (long long)g_sm_count * warps_f * lanes;
+            const long long wave = (long long)cfg.sm_count * warps_f * lanes;
             const long long mem_waves = std::max<long long>(1, std::min<long long>(4, FRONTAL_WORK_BYTES / per_sample / wave));
             const long long lr_min = std::max<long long>(host.cmax + 2, std::min<long long>(lr, 3LL * (host.cmax / 2 + 2)));
             for (; lr > lr_min; lr -= 4) {
@@ -305,6 +310,8 @@ struct tfin_ctx {
     int frontal_threads = 0; // D2 threads per CTA, 0 = auto
     int frontal_mode = -1;   // D2: -1 auto, 0 = QOI (extra right-hand sides), 1 = SOLVE (factor to HBM + backward)
     int frontal_lanes = 0;   // D1: samples per warp, 0 = auto (most samples in flight), else 4..32
+    int frontal_ring_rows = 0;   // D1: rows of the substitution kernel's factor-block ring, 0 = auto
+    FrontalCfg frontal_cfg() const { return FrontalCfg{max_smem_optin, smem_per_sm, sm_count, frontal_lanes, frontal_ring_rows}; }
     int frontal_split = 1;   // D1: 1 = factor kernel + substitution kernel, 0 = one fused kernel
     int last_focc_b = 0;
     int last_solver = 0, last_fkernel = 0, last_fthreads = 0, last_focc = 0;
@@ -339,7 +346,6 @@ extern "C" int tfin_create(int device, tfin_handle_t* out) {
     c->sm_count = prop.multiProcessorCount;
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
-    g_sm_count = prop.multiProcessorCount;
     TFIN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (int err = c->d_counter.reserve(1)) return err;
     *out = c;
@@ -555,7 +561,7 @@ extern "C" int tfin_set_operator(tfin_handle_t h, int32_t n, int32_t nnz, const 
         if (h->fr_aff.why.empty()) h->fr_aff.why = frontal_build(n, row_ptr, col_idx, rhs, terms, &h->fr_aff.host1, false);
         if (h->fr_aff.why.empty()) {
             h->fr_aff.ncv = n_terms;
-            if (int e = h->fr_aff.upload(h->stream, 0, h->max_smem_optin, h->smem_per_sm, h->frontal_lanes)) return e;
+            if (int e = h->fr_aff.upload(h->stream, 0, h->frontal_cfg())) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
             h->fr_aff.ok = true;
         }
@@ -617,7 +623,7 @@ extern "C" int tfin_set_observation(tfin_handle_t h, int32_t n_obs, const int32_
         if (fs->ok) {
             frontal_set_obs(fs->host, n_obs, ptr, idx, val);
             frontal_set_obs(fs->host1, n_obs, ptr, idx, val);
-            if (int e = fs->upload(h->stream, n_obs, h->max_smem_optin, h->smem_per_sm, h->frontal_lanes)) return e;
+            if (int e = fs->upload(h->stream, n_obs, h->frontal_cfg())) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
         }
     // B_obs^T as CSR over the n dofs: right-hand sides of the adjoint solves
@@ -688,7 +694,7 @@ extern "C" int tfin_set_cells(tfin_handle_t h, int32_t n_cells, const int32_t* c
             if (!h->h_obs_ptr.empty())
                 for (FrontalProgram* fp : {&h->fr_nod.host, &h->fr_nod.host1})
                     frontal_set_obs(*fp, h->n_obs, h->h_obs_ptr.data(), h->h_obs_idx.data(), h->h_obs_val.data());
-            if (int e = h->fr_nod.upload(h->stream, h->n_obs, h->max_smem_optin, h->smem_per_sm, h->frontal_lanes)) return e;
+            if (int e = h->fr_nod.upload(h->stream, h->n_obs, h->frontal_cfg())) return e;
             TFIN_CUDA(cudaStreamSynchronize(h->stream));
             h->fr_nod.ok = true;
         }
@@ -2413,7 +2419,7 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
     if (k == "frontal_lanes" || k == "frontal_ring_rows") {
         if (k == "frontal_ring_rows") {
             if (value < 0 || value > 4096) return fail(TFIN_E_ARG, "frontal_ring_rows must be 0 (auto) .. 4096");
-            g_frontal_ring_rows = (int)value;
+            h->frontal_ring_rows = (int)value;
         } else {
             if (value != 0 && (value < 4 || value > 32)) return fail(TFIN_E_ARG, "frontal_lanes must be 0 (auto) or 4..32");
             h->frontal_lanes = (int)value;
@@ -2421,7 +2427,7 @@ extern "C" int tfin_set_int(tfin_handle_t h, const char* key, int64_t value) {
         for (FrontalSet* fs : {&h->fr_aff, &h->fr_nod})   // repack the D1 streams for the new row width
             if (fs->ok) {
                 DeviceGuard guard(h->device);
-                if (int e = fs->upload(h->stream, h->n_obs, h->max_smem_optin, h->smem_per_sm, h->frontal_lanes)) return e;
+                if (int e = fs->upload(h->stream, h->n_obs, h->frontal_cfg())) return e;
                 TFIN_CUDA(cudaStreamSynchronize(h->stream));
             }
         return 0;

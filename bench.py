@@ -357,7 +357,9 @@ def run_b200(args):
                            "observables through extra right-hand sides)", 3: "D2 frontal_cta_kernel (sample per CTA, "
                            "factor in HBM + backward substitution)"}.get(hh.get_int("frontal_kernel"), "?"),
                 "threads": hh.get_int("frontal_threads"), "ctas_per_sm": hh.get_int("frontal_ctas_per_sm"),
-                "smem_bytes": hh.get_int("frontal_smem_bytes"), "front_slots": hh.get_int("frontal_slots"),
+                "smem_bytes": hh.get_int("frontal_smem_bytes"),
+                "front_slots": hh.get_int("frontal_slots_lane" if hh.get_int("frontal_kernel") == 1 else "frontal_slots"),
+                "substitution_ctas_per_sm": hh.get_int("frontal_bsub_ctas_per_sm"),
                 "max_column": hh.get_int("frontal_cmax"), "factor_nnz": hh.get_int("frontal_nnz_factor"),
                 "pair_updates": hh.get_int("frontal_pair_updates"), "samples_per_warp": hh.get_int("frontal_lanes")}
 

@@ -971,6 +971,12 @@ def test_direct_solver_narrow_rows(space_m2, oracle_m2, lanes):
     assert np.array_equal(out["qoi"], ref["qoi"]) and np.array_equal(out["w"], ref["w"])
     assert np.array_equal(outn["qoi"], refn["qoi"]) and np.all(out["status"] == 0)
     assert relerr(out["qoi"][74], oracle_m2.qoi_operator(oracle_m2.forward_nine_param(theta[74]))) <= RTOL_FOM
+    # the factor-block ring of the substitution kernel (prefetch distance) is a pure tuning knob as well
+    h.set_int("frontal_ring_rows", h.get_int("frontal_cmax") + 2)
+    out2 = h.fom_affine(theta, want_w=True)
+    assert h.get_int("frontal_ring_rows") == h.get_int("frontal_cmax") + 2
+    assert np.array_equal(out2["qoi"], ref["qoi"]) and np.array_equal(out2["w"], ref["w"])
+    h.set_int("frontal_ring_rows", 0)
     h.close()
 
 
