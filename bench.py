@@ -61,7 +61,8 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-fom-sample", type=int, default=65536, help="CPU baseline FOM sample (~10 s on 16 cores)")
     ap.add_argument("--cpu-rom-sample", type=int, default=65536)
-    ap.add_argument("--grad-batch", type=int, default=16384, help="samples per GPU per step of the gradient legs (0 = skip)")
+    ap.add_argument("--grad-batch", type=int, default=100_000,
+                    help="samples per GPU per step of the gradient legs (capped by --nodal-batch: the same fields; 0 = skip)")
     ap.add_argument("--ref-step-samples", type=int, default=8192, help="--impl reference: CPU solves per step")
     return ap.parse_args()
 
