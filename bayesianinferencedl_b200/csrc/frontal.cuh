@@ -469,7 +469,7 @@ struct FrontalCtaSmem {
 };
 
 template <int MODE, int NU>   // NU: the column fits 32 * NU entries
-__global__ void __launch_bounds__(NU >= 8 ? 512 : 768) frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L) {
+__global__ void __launch_bounds__(NU >= 8 ? 512 : (NU >= 4 ? 768 : 1024), 1) frontal_cta_kernel(FrontalDev P, FrontalIO io, FrontalCtaSmem L) {
     extern __shared__ __align__(16) unsigned char fsm_raw[];
     double* F = reinterpret_cast<double*>(fsm_raw + L.F);
     double* yv = reinterpret_cast<double*>(fsm_raw + L.yv);

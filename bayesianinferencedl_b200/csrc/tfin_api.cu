@@ -1154,7 +1154,7 @@ static FrontalGeom frontal_geom(tfin_ctx* h, bool nodal, bool want_w) {
     int T = h->frontal_threads;
     if (T <= 0) {
         const double pairs = 0.5 * P.cmax * (P.cmax + 1.0);
-        T = 32 * (int)std::min(16.0, std::max(1.0, std::ceil(pairs / (32.0 * 12.0))));
+        T = 32 * (int)std::min(16.0, std::max(1.0, std::ceil(pairs / (32.0 * 16.0))));
     }
     T = std::max(32, std::min(512, (T + 31) & ~31));   // __launch_bounds__(512): 128 registers per thread
     const void* fn = frontal_cta_fn(mode, P.cmax);
