@@ -135,7 +135,7 @@ __device__ __forceinline__ void cp_async_wait_dyn(unsigned k) {   // k <= FRONTA
     }
 }
 
-// Split launch (PHASE 1 then PHASE 2): the factorisation needs the front in shared memory (two warps per SM at n = 1597),
+// Split launch (PHASE 1 then PHASE 2): the factorisation needs the front in shared memory (three warps of 27 samples per SM at n = 1597),
 // the substitution only a right-hand side and the factor-block ring, so eight or more of its warps fit -- and both are
 // bound by instruction latency, i.e. by resident warps.  The factor blocks of all groups of a chunk then live in HBM
 // (workspace row block g), plus two rows per group for y.y and the breakdown flag.
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(32) frontal_lane_kernel(FrontalDev P, FrontalI
     // A warp carries LPG = P.lanes <= 32 samples; with fewer than 32 the upper lanes shadow the lower ones (same
     // addresses, same values), which costs nothing but lets more warps share the SM's shared memory: the kernel is bound
     // by instruction latency, i.e. by samples in flight = resident warps x LPG, and shared memory bounds that product
-    // (n = 1597: 3 warps x 25 samples instead of 2 x 32).
+    // (n = 1597: 3 warps x 27 samples instead of 2 x 32).
     // Shadow lanes all take the LAST sample's column: same address as lane LPG - 1, i.e. a broadcast -- any other choice
     // (say xlane % LPG) puts a second, different word on banks the real lanes use and costs a third wavefront per access.
     const int LPG = P.lanes, xlane = threadIdx.x;

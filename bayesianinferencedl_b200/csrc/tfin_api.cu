@@ -161,7 +161,7 @@ struct FrontalSet {
         const int base_rows = ntri + host1.nslots + n_obs + (ncv <= TFIN_MAX_TERMS ? ncv : 0);
         // Throughput of the (latency-bound) kernel is samples in flight / pass latency, and samples in flight = resident
         // warps x samples per warp are bounded by the SM's shared memory (228 KiB, 1 KiB reserved per CTA): pick the
-        // (warps, lanes) pair with the largest product, fewer warps on a tie.  n = 1597: 3 x 25 = 75 instead of 2 x 32.
+        // (warps, lanes) pair with the largest product, fewer warps on a tie.  n = 1597: 3 x 27 = 81 instead of 2 x 32.
         // factor-block ring of the substitution kernel (split launch: no front in its shared memory): ~4 blocks ahead
         long long lr = std::max<long long>(host.cmax + 2, std::min<long long>(64, 4LL * (host.cmax + 2)));
         if (cfg.ring_rows > 0) lr = std::max<long long>(host.cmax + 2, cfg.ring_rows);

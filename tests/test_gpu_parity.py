@@ -953,7 +953,7 @@ def test_config4_refined_mesh_at_full_size():
 @pytest.mark.parametrize("lanes", [8, 16, 25, 27])
 def test_direct_solver_narrow_rows(space_m2, oracle_m2, lanes):
     """D1 with fewer than 32 samples per warp (narrower shared-memory rows, more resident warps; the default picks the
-    pair with the most samples in flight, 3 x 25 on the reference-size mesh): same results bit for bit, odd counts too."""
+    pair with the most samples in flight, 3 x 27 on the reference-size mesh): same results bit for bit, odd counts too."""
     from bayesianinferencedl_b200.assembly import build_operators
     ops = build_operators(space_m2)
     h = _handle_for(ops, cells=True)
