@@ -21,6 +21,7 @@ for lanes, rr in [(l, r) for l in lanes_list for r in rr_list]:
     q = torch.empty((64, 9), device="cuda", dtype=torch.float64)
     h.fom_affine_raw(th.data_ptr(), 64, 0, 1, 1e-12, 50000, qoi=q.data_ptr(), stream=st)
     occ, occ_b = h.get_int("frontal_ctas_per_sm"), h.get_int("frontal_bsub_ctas_per_sm")
+    lanes = h.get_int("frontal_lanes")          # the automatic choice when 0 was asked for
     print("ring rows", h.get_int("frontal_ring_rows"), end="  ")
     for waves in (4,):
         N = 148 * occ * lanes * waves
