@@ -302,7 +302,7 @@ __device__ __forceinline__ void rom_chol_panel(double* __restrict__ A, double* _
 }
 
 template <int MAXM /* ceil((n_r+1)/32) */, bool ADJ = false>
-__global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict__ C, long long s_begin,
+__global__ void __launch_bounds__(256, 1) rom_chol_kernel(const double* __restrict__ C, long long s_begin,
                                                        long long s_end, int nr, int n_obs,
                                                        const double* __restrict__ obs_phi,  // [n_obs][nr]
                                                        double* __restrict__ wr_out, double* __restrict__ qoi_out,
@@ -315,27 +315,56 @@ __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict_
     double* dinv = A + Taug;
     double* wv = dinv + nr;
     const int nrow = nr + 1;
+    // The observation rows (B_obs phi) of this lane's entries, read once per warp instead of once per sample: the
+    // projection then works on the register-distributed solution and never touches memory.
+    constexpr int NOBS_REG = 9;
+    const bool obs_reg = n_obs <= NOBS_REG;
+    double op[NOBS_REG][MAXM];
+#pragma unroll
+    for (int o = 0; o < NOBS_REG; ++o)
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m)
+            op[o][m] = (obs_reg && o < n_obs && lane + 32 * m < nr) ? obs_phi[o * nr + lane + 32 * m] : 0.0;
+    // The packed matrix arrives in four cp.async groups cut at columns 8 / 24 / 48: the left-looking factorisation of
+    // panel j0 needs columns < j0 + 8 only, i.e. a prefix of the packed array, so it starts after the first ~18 % have
+    // landed and the rest of the load hides behind the first panels.
+    const bool staged = (Taug & 1) == 0;   // rows of C are 16-byte aligned when Taug is even (per_warp is)
+    int cut[5];                            // group g = double2 elements [cut[g], cut[g + 1])
+    cut[0] = 0;
+    cut[1] = rom_col_off(min(8, nr), nr) >> 1;
+    cut[2] = rom_col_off(min(24, nr), nr) >> 1;
+    cut[3] = rom_col_off(min(48, nr), nr) >> 1;
+    cut[4] = Taug >> 1;
+    const unsigned A_s = smem_u32(A);
 
     for (long long s = s_begin + (long long)blockIdx.x * wpb + warp; s < s_end;
          s += (long long)gridDim.x * wpb) {
         const double* src = C + (size_t)(s - s_begin) * Taug;
-        if ((Taug & 1) == 0) {  // rows of C are 16-byte aligned when Taug is even (per_warp is): 16-byte copies
+        if (staged) {
             const double2* src2 = reinterpret_cast<const double2*>(src);
-            double2* A2 = reinterpret_cast<double2*>(A);
-            for (int e = lane; e < (Taug >> 1); e += 32) {
-                double2 v;
-                asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(src2 + e));
-                A2[e] = v;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                for (int e = cut[g] + lane; e < cut[g + 1]; e += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(A_s + 16u * (unsigned)e), "l"(src2 + e) : "memory");
+                cp_async_commit();
             }
         } else {
             for (int e = lane; e < Taug; e += 32) A[e] = ldg_stream(src + e);
+            __syncwarp();
         }
-        __syncwarp();
         int status = TFIN_STATUS_CONVERGED;
         // Panel-blocked left-looking Cholesky, 8 columns at a time: the update from the finished columns runs on the
         // tensor cores (DMMA), the panel itself is factored in registers.  Both are instantiated for the number of
         // 32-row slabs that still hold rows (warp-uniform), so empty slabs cost no issue slots at all.
         for (int j0 = 0; j0 < nr; j0 += 8) {
+            if (staged) {   // wait for the groups that hold columns < j0 + 8 (an element that straddles a cut counts as late)
+                const int need = (rom_col_off(min(j0 + 8, nr), nr) + 1) >> 1;
+                if (need > cut[3]) cp_async_wait<0>();
+                else if (need > cut[2]) cp_async_wait<1>();
+                else if (need > cut[1]) cp_async_wait<2>();
+                else cp_async_wait<3>();
+                __syncwarp();
+            }
             const int mact = min(MAXM, (nrow - j0 + 31) >> 5);
             if (MAXM >= 4 && mact == 4) {
                 if (j0) rom_chol_sweep_mma<(MAXM >= 4 ? 4 : 1)>(A, j0, nr, lane);
@@ -377,18 +406,37 @@ __global__ void __launch_bounds__(256) rom_chol_kernel(const double* __restrict_
             double rv[MAXM], cost = 0.0;
 #pragma unroll
             for (int m = 0; m < MAXM; ++m) rv[m] = 0.0;
-            for (int o = 0; o < n_obs; ++o) {
-                double acc = 0.0;
-                for (int j = lane; j < nr; j += 32) acc = fma(obs_phi[o * nr + j], wv[j], acc);
-                acc = warp_sum(acc);
-                if (qoi_out && lane == 0) qoi_out[s * n_obs + o] = acc;
-                if (ADJ) {  // reduced adjoint right-hand side (B_obs phi)^T (data - qoi), :338-339
-                    const double res = adj.data[s * adj.data_stride + o] - acc;
-                    cost = fma(res, res, cost);
+            if (obs_reg) {
 #pragma unroll
-                    for (int m = 0; m < MAXM; ++m) {
-                        const int j = lane + 32 * m;
-                        if (j < nr) rv[m] = fma(obs_phi[o * nr + j], res, rv[m]);
+                for (int o = 0; o < NOBS_REG; ++o) {
+                    if (o >= n_obs) break;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < MAXM; ++m)   // yv: the solution, lane-distributed (entries past n_r hold junk)
+                        acc = fma(op[o][m], lane + 32 * m < nr ? yv[m] : 0.0, acc);
+                    acc = warp_sum(acc);
+                    if (qoi_out && lane == 0) qoi_out[s * n_obs + o] = acc;
+                    if (ADJ) {  // reduced adjoint right-hand side (B_obs phi)^T (data - qoi), :338-339
+                        const double res = adj.data[s * adj.data_stride + o] - acc;
+                        cost = fma(res, res, cost);
+#pragma unroll
+                        for (int m = 0; m < MAXM; ++m) rv[m] = fma(op[o][m], res, rv[m]);
+                    }
+                }
+            } else {
+                for (int o = 0; o < n_obs; ++o) {
+                    double acc = 0.0;
+                    for (int j = lane; j < nr; j += 32) acc = fma(obs_phi[o * nr + j], wv[j], acc);
+                    acc = warp_sum(acc);
+                    if (qoi_out && lane == 0) qoi_out[s * n_obs + o] = acc;
+                    if (ADJ) {  // reduced adjoint right-hand side (B_obs phi)^T (data - qoi), :338-339
+                        const double res = adj.data[s * adj.data_stride + o] - acc;
+                        cost = fma(res, res, cost);
+#pragma unroll
+                        for (int m = 0; m < MAXM; ++m) {
+                            const int j = lane + 32 * m;
+                            if (j < nr) rv[m] = fma(obs_phi[o * nr + j], res, rv[m]);
+                        }
                     }
                 }
             }

@@ -1766,7 +1766,7 @@ static int rom_run(tfin_ctx* h, const RomSrc& src, int nr, int nobs, const doubl
     int wpb = std::min<int>(8, (int)((size_t)(h->max_smem_optin - 1024) / ((size_t)per_warp * 8)));
     if (wpb < 1) return fail(TFIN_E_STATE, "tfin_rom: n_r = %d does not fit shared memory", nr);
     const size_t chol_smem = (size_t)wpb * per_warp * 8 + 256;  // + slack for the unchecked panel-sweep loads
-    const int64_t chunk = h->rom_chunk > 0 ? h->rom_chunk : (int64_t)h->sm_count * wpb * 8;
+    const int64_t chunk = h->rom_chunk > 0 ? h->rom_chunk : (int64_t)h->sm_count * wpb * 16;   // 16 samples per warp: 516 MB of packed operators at n_r = 81
     if (int e = h->d_romC.reserve((size_t)std::min<int64_t>(chunk, N) * Taug)) return e;
     size_t comb_smem = 0, gram_smem = 0;
     int gram_threads = 0, gram_occ = 1;
@@ -1791,6 +1791,9 @@ static int rom_run(tfin_ctx* h, const RomSrc& src, int nr, int nobs, const doubl
                     : (maxm == 1 ? rom_chol_kernel<1, false> : maxm == 2 ? rom_chol_kernel<2, false>
                        : maxm == 3 ? rom_chol_kernel<3, false> : rom_chol_kernel<4, false>);
     TFIN_CUDA(cudaFuncSetAttribute(chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+    int chol_occ = 1;
+    TFIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&chol_occ, chol, wpb * 32, chol_smem));
+    if (chol_occ < 1) return fail(TFIN_E_STATE, "tfin_rom: the Cholesky kernel does not fit an SM (n_r = %d)", nr);
     const RomAdj a = adj ? *adj : RomAdj{};
     for (int64_t s0 = 0; s0 < N; s0 += chunk) {
         const int64_t s1 = std::min<int64_t>(N, s0 + chunk);
@@ -1815,7 +1818,8 @@ static int rom_run(tfin_ctx* h, const RomSrc& src, int nr, int nobs, const doubl
                 h->launches += 1;
             }
         }
-        const int g2 = (int)std::min<int64_t>((s1 - s0 + wpb - 1) / wpb, (int64_t)h->sm_count * 4);
+        // persistent grid: every warp keeps its observation rows in registers across the samples it takes
+        const int g2 = (int)std::min<int64_t>((s1 - s0 + wpb - 1) / wpb, (int64_t)h->sm_count * chol_occ);
         chol<<<g2, wpb * 32, chol_smem, st>>>(h->d_romC.p, s0, s1, nr, nobs, d_obs_phi, d_wr, d_qoi, d_status, a);
         h->launches += 2;
     }
